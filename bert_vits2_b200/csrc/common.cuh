@@ -1,0 +1,59 @@
+// Common device/host helpers for libbv2 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+#include <string>
+#include <stdexcept>
+
+namespace bv2 {
+
+// Activation layout used by every internal buffer ("c4"): [B][C/4][T][4] fp32 -- four consecutive
+// channels of one time step form one 16-byte element; time is the next-fastest dimension.  Rationale
+// (DESIGN.md): (1) a time-shifted window of a [C/4][T][4] tile is a pure 16-byte-granular address
+// offset, so the k taps of a dilated Conv1d become k tcgen05 smem-descriptor start addresses over ONE
+// staged tile (K-major, no-swizzle canonical layout with SBO=128 B); (2) TMEM epilogues (one thread per
+// time row, channels in registers) store 16-byte vectors that are contiguous across a warp.
+struct Act {
+    float* p = nullptr;
+    int B = 0, C = 0, T = 0;  // C multiple of 4
+    __host__ __device__ size_t elems() const { return (size_t)B * C * T; }
+};
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define BV2_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            throw ::bv2::Error(-3, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+    } while (0)
+
+#define BV2_CHECK(cond, msg)                                                                        \
+    do {                                                                                            \
+        if (!(cond)) throw ::bv2::Error(-2, std::string("check failed: ") + #cond + " : " + (msg)); \
+    } while (0)
+
+__device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // F.softplus threshold=20
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace bv2

@@ -1,0 +1,926 @@
+// libbv2: engine (weights, workspace, stage orchestration) and the C ABI declared in include/bv2.h.
+// Orchestrates the path of reference models.SynthesizerTrn.infer (models.py:1026-1074).
+#include <algorithm>
+#include <cstring>
+#include <functional>
+#include <cuda_fp16.h>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/bv2.h"
+#include "common.cuh"
+#include "kernels_simt.cuh"
+#include "tc_conv.cuh"
+
+namespace bv2 {
+
+struct HostTensor {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+    int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+struct ConvW { float* w = nullptr; float* b = nullptr; int Cin = 0, Cout = 0, Cout_w = 0, K = 1; TcConvW tc; };
+struct LnW { float* g = nullptr; float* b = nullptr; int C = 0; };
+struct EncLayerW { ConvW qkv, o, f1, f2; LnW n1, n2; float* relk = nullptr; float* relv = nullptr; };
+struct EncoderW { std::vector<EncLayerW> layers; int g_off = 0; int kernel = 3; };
+struct DdsW { std::vector<float*> sep_w, sep_b; std::vector<ConvW> c1; std::vector<LnW> n1, n2; };
+struct ConvFlowW { float* pre_w = nullptr; float* pre_b = nullptr; DdsW dds; ConvW proj; };
+struct CouplingW {
+    ConvW pre, post; int s = 0;  // orientation (Flip folded into weights)
+    EncoderW enc;                // transformer flow
+    std::vector<ConvW> wn_in, wn_res, wn_skip; int wn_g_off = 0;  // WN flow
+};
+struct ResBlockW { std::vector<ConvW> c1, c2; int k = 3; std::vector<int> dil; };
+struct UpW { float* w = nullptr; float* b = nullptr; int Cin = 0, Cout = 0, K = 0, u = 0; };
+
+struct DebugBuf { const float* p; int B, C, T; int c4; };
+
+class Arena {
+public:
+    ~Arena() { if (base_) cudaFree(base_); }
+    void reset() { off_ = 0; }
+    void ensure(size_t bytes) {
+        if (bytes <= cap_) return;
+        if (base_) { cudaDeviceSynchronize(); cudaFree(base_); base_ = nullptr; cap_ = 0; }
+        BV2_CUDA(cudaMalloc(&base_, bytes));
+        cap_ = bytes;
+    }
+    float* alloc(size_t nfloats) {
+        size_t bytes = (nfloats * sizeof(float) + 255) & ~(size_t)255;
+        BV2_CHECK(off_ + bytes <= cap_, "workspace overflow");
+        float* p = reinterpret_cast<float*>(static_cast<char*>(base_) + off_);
+        off_ += bytes;
+        return p;
+    }
+    Act act(int B, int C, int T) { Act a; a.B = B; a.C = C; a.T = T; a.p = alloc((size_t)B * C * T); return a; }
+    size_t cap() const { return cap_; }
+    size_t used() const { return off_; }
+    void release(size_t mark) { off_ = mark; }  // stack discipline; safe because all users are stream-ordered
+private:
+    void* base_ = nullptr; size_t cap_ = 0, off_ = 0;
+};
+
+}  // namespace bv2
+
+using namespace bv2;
+
+struct bv2_engine {
+    bv2_config cfg{};
+    int device = 0;
+    std::mutex mu;
+    std::string err;
+    std::unordered_map<std::string, HostTensor> host;
+    bool finalized = false;
+    std::vector<void*> dev_allocs;
+    int64_t launches = 0;
+    int num_sms = 148;
+
+    // ---- device weights
+    float *emb = nullptr, *temb = nullptr, *lemb = nullptr, *emb_g = nullptr;
+    ConvW bert_proj, enc_proj;
+    EncoderW enc_p;
+    ConvW sdp_pre, sdp_proj; DdsW sdp_dds; std::vector<ConvFlowW> sdp_flows;  // index by flow id (1,3,5,7)
+    float ea_m[2] = {0, 0}, ea_logs[2] = {0, 0};
+    ConvW dp_c1, dp_c2, dp_proj; LnW dp_n1, dp_n2;
+    std::vector<CouplingW> flows;
+    ConvW conv_pre; std::vector<UpW> ups; std::vector<ResBlockW> resblocks; float* conv_post_w = nullptr;
+    float *gproj_w = nullptr, *gproj_b = nullptr; int gproj_n = 0;
+    int goff_dec = 0, goff_sdp = 0, goff_dp = 0;
+    float dconst = 0.f;
+
+    // ---- workspace / per-call state
+    Arena ws, persist;  // persist: state kept between infer_begin and infer_finish
+    std::map<std::string, DebugBuf> dbg;
+    struct {
+        bool active = false; int B = 0, T = 0, F = 0;
+        float* stats = nullptr; int* cum = nullptr; long long* ylen = nullptr; int* ylen32 = nullptr; int* lens = nullptr;
+        float* gproj = nullptr; float* w_ceil = nullptr;
+    } st;
+    long long* h_ylen = nullptr;  // pinned
+
+    ~bv2_engine() {
+        for (void* p : dev_allocs) cudaFree(p);
+        if (h_ylen) cudaFreeHost(h_ylen);
+    }
+
+    // ---------------------------------------------------------------- weights
+    const HostTensor& W(const std::string& k) const {
+        auto it = host.find(k);
+        if (it == host.end()) throw Error(BV2_ERR_STATE, "missing weight: " + k);
+        return it->second;
+    }
+    float* upload(const std::vector<float>& v) {
+        void* p = nullptr;
+        BV2_CUDA(cudaMalloc(&p, std::max<size_t>(v.size(), 4) * sizeof(float)));
+        BV2_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+        dev_allocs.push_back(p);
+        return static_cast<float*>(p);
+    }
+    // torch.nn.utils.weight_norm fold, dim=0: w = g * v / ||v|| over dims (1,2)  
+    std::vector<float> fold_wn(const std::string& name, std::vector<int64_t>* shape) const {
+        const HostTensor& v = W(name + ".weight_v");
+        const HostTensor& g = W(name + ".weight_g");
+        int64_t d0 = v.shape[0], inner = v.numel() / d0;
+        BV2_CHECK(g.numel() == d0, "weight_g shape " + name);
+        std::vector<float> w(v.data.size());
+        for (int64_t i = 0; i < d0; i++) {
+            double n = 0;
+            for (int64_t j = 0; j < inner; j++) { double x = v.data[i * inner + j]; n += x * x; }
+            float norm = (float)std::sqrt(n);
+            float s = g.data[i] / norm;
+            for (int64_t j = 0; j < inner; j++) w[i * inner + j] = v.data[i * inner + j] * s;
+        }
+        *shape = v.shape;
+        return w;
+    }
+    // [Cout][Cin][K] -> packed [Cin][K][Cout_w], Cout_w = Cout rounded up to 4 (+ zero pad)
+    ConvW make_conv(const std::vector<float>& w, int Cout, int Cin, int K, const std::vector<float>* bias, int tc_mode = 0) {
+        ConvW c; c.Cin = Cin; c.Cout = (Cout + 3) / 4 * 4; c.Cout_w = c.Cout; c.K = K;
+        std::vector<float> p((size_t)Cin * K * c.Cout_w, 0.f);
+        for (int co = 0; co < Cout; co++)
+            for (int ci = 0; ci < Cin; ci++)
+                for (int j = 0; j < K; j++) p[((size_t)ci * K + j) * c.Cout_w + co] = w[((size_t)co * Cin + ci) * K + j];
+        c.w = upload(p);
+        std::vector<float> b(c.Cout, 0.f);
+        if (bias) for (int co = 0; co < Cout; co++) b[co] = (*bias)[co];
+        c.b = upload(b);
+        if (tc_mode) c.tc = tc_pack_weights(*this_uploader(), w, Cout, Cin, K);
+        return c;
+    }
+    // uploader functor handed to tc_conv.cuh
+    std::function<float*(const std::vector<float>&)>* this_uploader() {
+        if (!uploader_) uploader_.reset(new std::function<float*(const std::vector<float>&)>([this](const std::vector<float>& v) { return upload(v); }));
+        return uploader_.get();
+    }
+    std::unique_ptr<std::function<float*(const std::vector<float>&)>> uploader_;
+
+    ConvW conv_from(const std::string& name, bool wn = false, int tc_mode = 0) {
+        std::vector<int64_t> shp;
+        std::vector<float> w;
+        if (wn) w = fold_wn(name, &shp);
+        else { const HostTensor& t = W(name + ".weight"); w = t.data; shp = t.shape; }
+        BV2_CHECK(shp.size() == 3 || shp.size() == 2, "conv weight rank " + name);
+        int Cout = (int)shp[0], Cin = (int)shp[1], K = shp.size() == 3 ? (int)shp[2] : 1;
+        const std::vector<float>* b = host.count(name + ".bias") ? &W(name + ".bias").data : nullptr;
+        return make_conv(w, Cout, Cin, K, b, tc_mode);
+    }
+    LnW ln_from(const std::string& name) {
+        LnW l; l.C = (int)W(name + ".gamma").numel(); l.g = upload(W(name + ".gamma").data); l.b = upload(W(name + ".beta").data);
+        return l;
+    }
+    EncoderW encoder_from(const std::string& name, int n_layers, int kernel, std::vector<float>& gw, std::vector<float>& gb) {
+        EncoderW e; e.kernel = kernel;
+        const int H = cfg.hidden_channels, dk = H / cfg.n_heads;
+        e.g_off = append_gproj(name + ".spk_emb_linear", gw, gb);
+        for (int i = 0; i < n_layers; i++) {
+            EncLayerW L;
+            std::string a = name + ".attn_layers." + std::to_string(i);
+            // fused QKV projection; 1/sqrt(dk) of attentions.py:280 folded into the q rows
+            std::vector<float> w((size_t)3 * H * H), b(3 * H);
+            const float qs = 1.f / std::sqrt((float)dk);
+            const char* nm[3] = {".conv_q", ".conv_k", ".conv_v"};
+            for (int p = 0; p < 3; p++) {
+                const HostTensor& wt = W(a + nm[p] + ".weight");
+                const HostTensor& bt = W(a + nm[p] + ".bias");
+                float s = p == 0 ? qs : 1.f;
+                for (int i2 = 0; i2 < H * H; i2++) w[(size_t)p * H * H + i2] = wt.data[i2] * s;
+                for (int i2 = 0; i2 < H; i2++) b[p * H + i2] = bt.data[i2] * s;
+            }
+            L.qkv = make_conv(w, 3 * H, H, 1, &b);
+            L.o = conv_from(a + ".conv_o");
+            L.relk = upload(W(a + ".emb_rel_k").data);
+            L.relv = upload(W(a + ".emb_rel_v").data);
+            L.n1 = ln_from(name + ".norm_layers_1." + std::to_string(i));
+            L.f1 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_1");
+            L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2");
+            L.n2 = ln_from(name + ".norm_layers_2." + std::to_string(i));
+            e.layers.push_back(L);
+        }
+        return e;
+    }
+    DdsW dds_from(const std::string& name, int n_layers) {
+        DdsW d;
+        for (int i = 0; i < n_layers; i++) {
+            std::string s = std::to_string(i);
+            d.sep_w.push_back(upload(W(name + ".convs_sep." + s + ".weight").data));  // [C][1][3]
+            d.sep_b.push_back(upload(W(name + ".convs_sep." + s + ".bias").data));
+            d.c1.push_back(conv_from(name + ".convs_1x1." + s));
+            d.n1.push_back(ln_from(name + ".norms_1." + s));
+            d.n2.push_back(ln_from(name + ".norms_2." + s));
+        }
+        return d;
+    }
+    int append_gproj(const std::string& name, std::vector<float>& gw, std::vector<float>& gb, bool wn = false) {
+        std::vector<int64_t> shp; std::vector<float> w;
+        if (wn) w = fold_wn(name, &shp); else { w = W(name + ".weight").data; shp = W(name + ".weight").shape; }
+        BV2_CHECK((int)shp[1] == cfg.gin_channels, "gproj Cin " + name);
+        int off = (int)gb.size();
+        gw.insert(gw.end(), w.begin(), w.end());
+        const auto& b = W(name + ".bias").data;
+        gb.insert(gb.end(), b.begin(), b.end());
+        return off;
+    }
+
+    void finalize();
+
+    // ---------------------------------------------------------------- launch helpers
+    void conv(const ConvW& cw, const Act& x, const Act& y, cudaStream_t s, ConvArgs extra = ConvArgs(), int cin_off = 0,
+              int cout_off = 0) {
+        ConvArgs a = extra;
+        a.x = x.p; a.Cin_total = x.C; a.cin_off = cin_off; a.Cin = cw.Cin;
+        a.w = cw.w; a.Cout_w = cw.Cout_w; a.bias = cw.b;
+        a.y = y.p; a.Cout_total = y.C; a.cout_off = cout_off; a.Cout = cw.Cout;
+        a.T = x.T; a.B = x.B; a.K = cw.K;
+        if (extra.dil == 0) a.dil = 1;
+        a.pad = (cw.K - 1) / 2 * a.dil;
+        BV2_CHECK(x.T == y.T && x.B == y.B, "conv T/B mismatch");
+        launch_conv1d(a, s);
+        launches++;
+    }
+    void layernorm(const LnW& w, const Act& x, const float* add, const Act& y, cudaStream_t s, int gelu, const float* post_res,
+                   const int* lens, int out_mask) {
+        LnArgs a; a.x = x.p; a.add = add; a.gamma = w.g; a.beta = w.b; a.y = y.p; a.post_res = post_res; a.C = x.C; a.T = x.T;
+        a.B = x.B; a.gelu = gelu; a.relu_in = 0; a.out_mask = out_mask; a.lens = lens; a.eps = 1e-5f;
+        BV2_CHECK(w.C == x.C, "LN C");
+        launch_layernorm(a, s);
+        launches++;
+    }
+    static dim3 grid_tcb(int T, int C, int B) { return dim3(cdiv(T, 128), C / 4, B); }
+
+    void debug(const std::string& name, const Act& a, int c4 = 1) { dbg[name] = DebugBuf{a.p, a.B, a.C, a.T, c4}; }
+    void debug_plain(const std::string& name, const float* p, int B, int C, int T) { dbg[name] = DebugBuf{p, B, C, T, 0}; }
+
+    // ---------------------------------------------------------------- stages
+    void run_gproj(const float* g, int B, float* out, cudaStream_t s) {
+        dim3 grid(cdiv(gproj_n, 8), B);
+        k_linear_g<<<grid, 256, 0, s>>>(gproj_w, gproj_b, g, out, gproj_n, cfg.gin_channels);
+        BV2_CUDA(cudaGetLastError()); launches++;
+    }
+    void run_encoder(const EncoderW& E, Act x, const int* lens, const float* gproj, cudaStream_t s, bool tc);
+    void run_dds(const DdsW& D, Act x, const int* lens, cudaStream_t s);
+    void run_text_encoder(int B, int T, const int64_t* x, const int64_t* tone, const int64_t* lang, const float* bert,
+                          const float* ja, const float* en, const int* lens, const float* gproj, Act& h, Act& stats, cudaStream_t s);
+    void run_durations(Act h, const int* lens, const float* gproj, const float* noise_w, float nsw, float* z, Act& dp_out, int* zch,
+                       cudaStream_t s);
+    void run_flow(Act z, const int* lens, const float* gproj, cudaStream_t s);
+    void run_generator(Act z, const int* lens_or_null, const float* gdec, int g_stride, float* o, cudaStream_t s);
+    int* lens_to_device(const int64_t* x_lengths_dev, int B, Arena& ar, cudaStream_t s);
+};
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_i64_to_i32(const long long* __restrict__ a, int* __restrict__ b, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = (int)a[i];
+}
+__global__ void k_scale_copy(const float* __restrict__ a, float* __restrict__ b, float s, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = a[i] * s;
+}
+
+int* bv2_engine::lens_to_device(const int64_t* xl, int B, Arena& ar, cudaStream_t s) {
+    int* lens = reinterpret_cast<int*>(ar.alloc(B));
+    k_i64_to_i32<<<cdiv(B, 128), 128, 0, s>>>(reinterpret_cast<const long long*>(xl), lens, B);
+    BV2_CUDA(cudaGetLastError()); launches++;
+    return lens;
+}
+
+void bv2_engine::finalize() {
+    const bv2_config& c = cfg;
+    const int H = c.hidden_channels, I = c.inter_channels;
+    BV2_CHECK(H % 4 == 0 && I % 8 == 0 && c.filter_channels % 4 == 0 && c.gin_channels % 4 == 0, "channel multiples of 4");
+    BV2_CHECK(H / c.n_heads == 96, "head dim 96 is the only instantiated attention kernel");
+    BV2_CHECK(c.window_size <= 5, "window");
+    BV2_CHECK(c.sdp_num_bins == 10 && c.sdp_kernel == 3, "sdp spline bins/kernel");
+    std::vector<float> gw, gb;
+    // ---- enc_p (reference models.py:333-375)
+    emb = upload(W("enc_p.emb.weight").data);
+    temb = upload(W("enc_p.tone_emb.weight").data);
+    lemb = upload(W("enc_p.language_emb.weight").data);
+    {
+        // three 1024->H projections concatenated along Cin (one K=3*1024 contraction)
+        const char* nm[3] = {"enc_p.bert_proj", "enc_p.ja_bert_proj", "enc_p.en_bert_proj"};
+        const int D = c.bert_dim;
+        std::vector<float> w((size_t)H * 3 * D), b(H, 0.f);
+        for (int p = 0; p < 3; p++) {
+            const HostTensor& wt = W(std::string(nm[p]) + ".weight");
+            const HostTensor& bt = W(std::string(nm[p]) + ".bias");
+            for (int co = 0; co < H; co++) {
+                for (int ci = 0; ci < D; ci++) w[(size_t)co * 3 * D + p * D + ci] = wt.data[(size_t)co * D + ci];
+                b[co] += bt.data[co];
+            }
+        }
+        bert_proj = make_conv(w, H, 3 * D, 1, &b);
+    }
+    enc_p = encoder_from("enc_p.encoder", c.n_layers, c.kernel_size, gw, gb);
+    enc_proj = conv_from("enc_p.proj");
+    // ---- sdp (reference models.py:148-195); flows[1] is the dropped "useless vflow" (:247)
+    sdp_pre = conv_from("sdp.pre");
+    sdp_proj = conv_from("sdp.proj");
+    sdp_dds = dds_from("sdp.convs", c.sdp_dds_layers);
+    goff_sdp = append_gproj("sdp.cond", gw, gb);
+    sdp_flows.resize(2 * c.sdp_n_flows + 1);
+    for (int i = 2; i <= c.sdp_n_flows; i++) {
+        std::string f = "sdp.flows." + std::to_string(2 * i - 1);
+        ConvFlowW cf;
+        cf.pre_w = upload(W(f + ".pre.weight").data);
+        cf.pre_b = upload(W(f + ".pre.bias").data);
+        cf.dds = dds_from(f + ".convs", c.sdp_dds_layers);
+        cf.proj = conv_from(f + ".proj");
+        sdp_flows[2 * i - 1] = cf;
+    }
+    for (int i = 0; i < 2; i++) { ea_m[i] = W("sdp.flows.0.m").data[i]; ea_logs[i] = W("sdp.flows.0.logs").data[i]; }
+    dconst = (float)std::log(std::exp(1.0 - 1e-3) - 1.0);  // transforms.py:69
+    // ---- dp (reference models.py:259-299)
+    dp_c1 = conv_from("dp.conv_1"); dp_c2 = conv_from("dp.conv_2"); dp_proj = conv_from("dp.proj");
+    dp_n1 = ln_from("dp.norm_1"); dp_n2 = ln_from("dp.norm_2");
+    goff_dp = append_gproj("dp.cond", gw, gb);
+    // ---- flow (reference models.py:82-145 / 403-445): Flip folded into pre/post channel order
+    const int half = I / 2, n = c.n_flow_layer;
+    flows.resize(n);
+    const int tc = c.generator_precision ? 1 : 0;
+    for (int i = 0; i < n; i++) {
+        CouplingW& fl = flows[i];
+        std::string f = "flow.flows." + std::to_string(2 * i);
+        fl.s = ((n - 1 - i) % 2 == 0) ? 1 : 0;
+        const HostTensor& pw = W(f + ".pre.weight");   // [H][half][1]
+        const HostTensor& pb = W(f + ".pre.bias");
+        const HostTensor& qw = W(f + ".post.weight");  // [half][H][1]
+        const HostTensor& qb = W(f + ".post.bias");
+        BV2_CHECK((int)qw.shape[0] == half, "mean_only coupling expected");
+        std::vector<float> w1(pw.data), w2(qw.data), b2(qb.data);
+        if (fl.s) {
+            for (int co = 0; co < H; co++)
+                for (int ci = 0; ci < half; ci++) w1[(size_t)co * half + ci] = pw.data[(size_t)co * half + (half - 1 - ci)];
+            for (int co = 0; co < half; co++) {
+                for (int ci = 0; ci < H; ci++) w2[(size_t)co * H + ci] = qw.data[(size_t)(half - 1 - co) * H + ci];
+                b2[co] = qb.data[half - 1 - co];
+            }
+        }
+        fl.pre = make_conv(w1, H, half, 1, &pb.data);
+        fl.post = make_conv(w2, half, H, 1, &b2);
+        if (c.use_transformer_flow) {
+            fl.enc = encoder_from(f + ".enc", c.n_layers_trans_flow, c.flow_kernel_size, gw, gb);
+        } else {
+            const int L = c.wn_layers;
+            fl.wn_g_off = append_gproj(f + ".enc.cond_layer", gw, gb, true);
+            for (int l = 0; l < L; l++) {
+                fl.wn_in.push_back(conv_from(f + ".enc.in_layers." + std::to_string(l), true));
+                std::vector<int64_t> shp;
+                std::vector<float> w = fold_wn(f + ".enc.res_skip_layers." + std::to_string(l), &shp);
+                const auto& b = W(f + ".enc.res_skip_layers." + std::to_string(l) + ".bias").data;
+                if (l < L - 1) {
+                    std::vector<float> wr(w.begin(), w.begin() + (size_t)H * H), ws(w.begin() + (size_t)H * H, w.end());
+                    std::vector<float> br(b.begin(), b.begin() + H), bs(b.begin() + H, b.end());
+                    fl.wn_res.push_back(make_conv(wr, H, H, 1, &br));
+                    fl.wn_skip.push_back(make_conv(ws, H, H, 1, &bs));
+                } else {
+                    fl.wn_skip.push_back(make_conv(w, H, H, 1, &b));
+                }
+            }
+        }
+    }
+    // ---- dec (reference models.py:490-564)
+    conv_pre = conv_from("dec.conv_pre");
+    goff_dec = append_gproj("dec.cond", gw, gb);
+    int ch = c.upsample_initial_channel;
+    for (int i = 0; i < c.n_ups; i++) {
+        std::vector<int64_t> shp;
+        std::vector<float> w = fold_wn("dec.ups." + std::to_string(i), &shp);  // [Cin][Cout][K]
+        UpW u; u.Cin = (int)shp[0]; u.Cout = (int)shp[1]; u.K = (int)shp[2]; u.u = c.upsample_rates[i];
+        BV2_CHECK(u.K % u.u == 0 && u.K <= 16 && u.Cin == ch && u.Cout == ch / 2 && (u.K - u.u) % 2 == 0, "upsample config");
+        std::vector<float> p((size_t)u.Cin * u.K * u.Cout);
+        for (int ci = 0; ci < u.Cin; ci++)
+            for (int co = 0; co < u.Cout; co++)
+                for (int j = 0; j < u.K; j++) p[((size_t)ci * u.K + j) * u.Cout + co] = w[((size_t)ci * u.Cout + co) * u.K + j];
+        u.w = upload(p); u.b = upload(W("dec.ups." + std::to_string(i) + ".bias").data);
+        ups.push_back(u);
+        ch /= 2;
+        for (int j = 0; j < c.n_resblock_kernels; j++) {
+            ResBlockW rb; rb.k = c.resblock_kernel_sizes[j];
+            std::string r = "dec.resblocks." + std::to_string(i * c.n_resblock_kernels + j);
+            for (int d = 0; d < c.n_dilations; d++) {
+                rb.dil.push_back(c.resblock_dilation_sizes[j][d]);
+                rb.c1.push_back(conv_from(r + ".convs1." + std::to_string(d), true, tc));
+                rb.c2.push_back(conv_from(r + ".convs2." + std::to_string(d), true, tc));
+            }
+            resblocks.push_back(rb);
+        }
+    }
+    BV2_CHECK(ch == 16, "conv_post kernel instantiated for 16 input channels");
+    conv_post_w = upload(W("dec.conv_post.weight").data);  // [1][16][7]
+    emb_g = upload(W("emb_g.weight").data);
+    gproj_n = (int)gb.size();
+    gproj_w = upload(gw); gproj_b = upload(gb);
+    BV2_CUDA(cudaMallocHost(&h_ylen, 4096 * sizeof(long long)));
+    host.clear();
+    finalized = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// attentions.Encoder.forward (reference attentions.py:103-120)
+void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const float* gproj, cudaStream_t s, bool tc) {
+    const int B = x.B, T = x.T, H = x.C, Fc = cfg.filter_channels, nh = cfg.n_heads;
+    const size_t mark = ws.used();
+    Act qkv = ws.act(B, 3 * H, T), att = ws.act(B, H, T), y = ws.act(B, H, T), f = ws.act(B, Fc, T);
+    const int nl = (int)E.layers.size();
+    for (int i = 0; i < nl; i++) {
+        const EncLayerW& L = E.layers[i];
+        if (i == cfg.cond_layer_idx) {
+            k_add_bvec_mask<<<grid_tcb(T, H, B), 128, 0, s>>>(x.p, gproj + E.g_off, gproj_n, H, T, lens);
+            BV2_CUDA(cudaGetLastError()); launches++;
+        }
+        conv(L.qkv, x, qkv, s);
+        {
+            dim3 grid(cdiv(T, 16), nh, B);
+            k_attention_rel<96><<<grid, 128, 0, s>>>(qkv.p, L.relk, L.relv, att.p, H, T, lens, cfg.window_size);
+            BV2_CUDA(cudaGetLastError()); launches++;
+        }
+        conv(L.o, att, y, s);
+        layernorm(L.n1, x, y.p, x, s, 0, nullptr, lens, 0);
+        ConvArgs a1; a1.in_mask = 1; a1.act = 1; a1.lens = lens;
+        conv(L.f1, x, f, s, a1);
+        ConvArgs a2; a2.in_mask = 1; a2.out_mask = 1; a2.lens = lens;
+        conv(L.f2, f, y, s, a2);
+        layernorm(L.n2, x, y.p, x, s, 0, nullptr, lens, i == nl - 1 ? 1 : 0);
+    }
+    (void)tc;
+    ws.release(mark);
+}
+
+// modules.DDSConv.forward without the optional g add (reference modules.py:118-130)
+void bv2_engine::run_dds(const DdsW& D, Act x, const int* lens, cudaStream_t s) {
+    const int B = x.B, T = x.T, C = x.C;
+    const size_t mark = ws.used();
+    Act y = ws.act(B, C, T), y2 = ws.act(B, C, T);
+    const int nl = (int)D.c1.size();
+    int dil = 1;
+    for (int i = 0; i < nl; i++) {
+        k_dwconv3_c4<<<grid_tcb(T, C, B), 128, 0, s>>>(x.p, D.sep_w[i], D.sep_b[i], y.p, C, T, dil, lens);
+        BV2_CUDA(cudaGetLastError()); launches++;
+        layernorm(D.n1[i], y, nullptr, y, s, 1, nullptr, lens, 0);
+        conv(D.c1[i], y, y2, s);
+        layernorm(D.n2[i], y2, nullptr, x, s, 1, x.p, lens, i == nl - 1 ? 1 : 0);
+        dil *= cfg.sdp_kernel;
+    }
+    ws.release(mark);
+}
+
+// TextEncoder.forward (reference models.py:377-400)
+void bv2_engine::run_text_encoder(int B, int T, const int64_t* x, const int64_t* tone, const int64_t* lang, const float* bert,
+                                  const float* ja, const float* en, const int* lens, const float* gproj, Act& h, Act& stats,
+                                  cudaStream_t s) {
+    const int H = cfg.hidden_channels, D = cfg.bert_dim;
+    Act bc = ws.act(B, 3 * D, T);
+    const float* srcs[3] = {bert, ja, en};
+    for (int p = 0; p < 3; p++) {
+        k_plain_to_c4<<<grid_tcb(T, D, B), 128, 0, s>>>(srcs[p], D, (long long)D * T, T, bc.p, 3 * D, p * D, T, nullptr, 1.f);
+        BV2_CUDA(cudaGetLastError()); launches++;
+    }
+    Act proj = ws.act(B, H, T);
+    conv(bert_proj, bc, proj, s);
+    k_embed_sum<<<grid_tcb(T, H, B), 128, 0, s>>>(proj.p, reinterpret_cast<const long long*>(x), reinterpret_cast<const long long*>(tone),
+                                                  reinterpret_cast<const long long*>(lang), emb, temb, lemb, h.p, H, T, lens,
+                                                  std::sqrt((float)H));
+    BV2_CUDA(cudaGetLastError()); launches++;
+    run_encoder(enc_p, h, lens, gproj, s, false);
+    ConvArgs a; a.out_mask = 1; a.lens = lens;
+    conv(enc_proj, h, stats, s, a);
+}
+
+// StochasticDurationPredictor(reverse) + DurationPredictor (reference models.py:197-204,245-256, 285-299)
+void bv2_engine::run_durations(Act h, const int* lens, const float* gproj, const float* noise_w, float nsw, float* z, Act& dp_out,
+                               int* zch_out, cudaStream_t s) {
+    const int B = h.B, T = h.T, Cf = cfg.sdp_filter;
+    // ---- SDP conditioning
+    Act c = ws.act(B, Cf, T), cond = ws.act(B, Cf, T);
+    ConvArgs a0; a0.bias_b = gproj + goff_sdp; a0.bias_b_stride = gproj_n;
+    conv(sdp_pre, h, c, s, a0);
+    run_dds(sdp_dds, c, lens, s);
+    ConvArgs a1; a1.out_mask = 1; a1.lens = lens;
+    conv(sdp_proj, c, cond, s, a1);
+    debug("sdp_cond", cond);
+    {
+        size_t n = (size_t)B * 2 * T;
+        k_scale_copy<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(noise_w, z, nsw, n);
+        BV2_CUDA(cudaGetLastError()); launches++;
+    }
+    Act hh = ws.act(B, Cf, T), pp = ws.act(B, 32, T);
+    int sflip = 0;
+    for (int i = cfg.sdp_n_flows; i >= 2; i--) {
+        sflip ^= 1;  // Flip
+        const ConvFlowW& cf = sdp_flows[2 * i - 1];
+        const int x0ch = sflip ? 1 : 0;
+        k_flow_pre<<<grid_tcb(T, Cf, B), 128, 0, s>>>(z, x0ch, cf.pre_w, cf.pre_b, cond.p, hh.p, Cf, T);
+        BV2_CUDA(cudaGetLastError()); launches++;
+        run_dds(cf.dds, hh, lens, s);
+        conv(cf.proj, hh, pp, s);
+        dim3 grid(cdiv(T, 128), B);
+        k_spline_inverse<10><<<grid, 128, 0, s>>>(pp.p, 32, z, 1 - x0ch, T, lens, 1.f / std::sqrt((float)Cf), cfg.sdp_tail_bound, dconst);
+        BV2_CUDA(cudaGetLastError()); launches++;
+    }
+    sflip ^= 1;  // final Flip before ElementwiseAffine
+    *zch_out = sflip ? 1 : 0;  // physical channel holding logical channel 0
+    // ---- DP
+    const int Cd = cfg.dp_filter;
+    Act xg = ws.act(B, h.C, T), d1 = ws.act(B, Cd, T), d2 = ws.act(B, Cd, T);
+    BV2_CUDA(cudaMemcpyAsync(xg.p, h.p, h.elems() * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    k_add_bvec_mask<<<grid_tcb(T, h.C, B), 128, 0, s>>>(xg.p, gproj + goff_dp, gproj_n, h.C, T, lens);
+    BV2_CUDA(cudaGetLastError()); launches++;
+    ConvArgs r; r.act = 1;
+    conv(dp_c1, xg, d1, s, r);
+    layernorm(dp_n1, d1, nullptr, d1, s, 0, nullptr, lens, 0);
+    ConvArgs r2; r2.act = 1; r2.in_mask = 1; r2.lens = lens;
+    conv(dp_c2, d1, d2, s, r2);
+    layernorm(dp_n2, d2, nullptr, d2, s, 0, nullptr, lens, 0);
+    ConvArgs r3; r3.in_mask = 1; r3.out_mask = 1; r3.lens = lens;
+    conv(dp_proj, d2, dp_out, s, r3);
+}
+
+// {Transformer,Residual}CouplingBlock reverse (reference models.py:142-145, 442-445; modules.py:437-456, 561-580)
+void bv2_engine::run_flow(Act z, const int* lens, const float* gproj, cudaStream_t s) {
+    const int B = z.B, F = z.T, H = cfg.hidden_channels, half = cfg.inter_channels / 2;
+    const size_t mark = ws.used();
+    Act h = ws.act(B, H, F);
+    for (int i = cfg.n_flow_layer - 1; i >= 0; i--) {
+        CouplingW& fl = flows[i];
+        const int in_off = fl.s ? half : 0, out_off = fl.s ? 0 : half;
+        ConvArgs a; a.out_mask = 1; a.lens = lens;
+        conv(fl.pre, z, h, s, a, in_off, 0);
+        Act m_in = h;
+        if (cfg.use_transformer_flow) {
+            run_encoder(fl.enc, h, lens, gproj, s, cfg.generator_precision != 0);
+        } else {
+            const int L = cfg.wn_layers;
+            Act xin = ws.act(B, 2 * H, F), acts = ws.act(B, H, F), out = ws.act(B, H, F);
+            for (int l = 0; l < L; l++) {
+                conv(fl.wn_in[l], h, xin, s);
+                k_wn_gate<<<grid_tcb(F, H, B), 128, 0, s>>>(xin.p, gproj + fl.wn_g_off + 2 * H * l, gproj_n, acts.p, H, F);
+                BV2_CUDA(cudaGetLastError()); launches++;
+                if (l < L - 1) {
+                    ConvArgs ar; ar.res_mode = 1; ar.res = h.p; ar.res_C_total = H; ar.out_mask = 1; ar.lens = lens;
+                    conv(fl.wn_res[l], acts, h, s, ar);
+                }
+                ConvArgs as; as.accumulate = l > 0 ? 1 : 0;
+                conv(fl.wn_skip[l], acts, out, s, as);
+            }
+            m_in = out;
+        }
+        ConvArgs p; p.in_mask = cfg.use_transformer_flow ? 0 : 1; p.res_mode = 2; p.res = z.p; p.res_C_total = z.C; p.res_c_off = out_off;
+        p.out_mask = 1; p.lens = lens;
+        conv(fl.post, m_in, z, s, p, 0, out_off);
+    }
+    if (cfg.n_flow_layer % 2 == 1) {
+        Act t = ws.act(B, z.C, F);
+        k_flip_c4<<<grid_tcb(F, z.C, B), 128, 0, s>>>(z.p, t.p, z.C, F);
+        BV2_CUDA(cudaMemcpyAsync(z.p, t.p, z.elems() * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        launches++;
+    }
+    ws.release(mark);
+}
+
+// Generator.forward (reference models.py:538-557) + ResBlock1.forward (modules.py:296-309)
+void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_stride, float* o, cudaStream_t s) {
+    const int B = z.B, F = z.T;
+    int ch = cfg.upsample_initial_channel, L = F;
+    Act x = ws.act(B, ch, L);
+    ConvArgs a; a.bias_b = gdec; a.bias_b_stride = g_stride;
+    if (lens) { a.in_mask = 1; a.lens = lens; }
+    conv(conv_pre, z, x, s, a);
+    const int nk = cfg.n_resblock_kernels, nd = cfg.n_dilations;
+    const bool tc = cfg.generator_precision != 0;
+    for (int i = 0; i < cfg.n_ups; i++) {
+        const UpW& u = ups[i];
+        const int Lo = L * u.u;
+        Act xu = ws.act(B, u.Cout, Lo), xt = ws.act(B, u.Cout, Lo), ra = ws.act(B, u.Cout, Lo), rb = ws.act(B, u.Cout, Lo),
+            S = ws.act(B, u.Cout, Lo);
+        ConvTArgs t; t.x = x.p; t.Cin = u.Cin; t.Tin = L; t.w = u.w; t.bias = u.b; t.y = xu.p; t.Cout = u.Cout; t.Tout = Lo;
+        t.K = u.K; t.u = u.u; t.p = (u.K - u.u) / 2; t.B = B; t.in_slope = 0.1f;
+        dim3 grid(cdiv(Lo, 128), cdiv(u.Cout, 64), B);
+        k_convT_c4<<<grid, 256, 0, s>>>(t);
+        BV2_CUDA(cudaGetLastError()); launches++;
+        for (int j = 0; j < nk; j++) {
+            const ResBlockW& R = resblocks[i * nk + j];
+            Act cur = xu;
+            for (int d = 0; d < nd; d++) {
+                const bool last = d == nd - 1;
+                Act nxt = last ? S : (cur.p == ra.p ? rb : ra);
+                if (tc) {
+                    TcEpi e1; e1.in_slope = 0.1f;
+                    tc_conv1d(R.c1[d].tc, R.c1[d].b, cur, xt, R.dil[d], e1, s, num_sms); launches++;
+                    TcEpi e2; e2.in_slope = 0.1f; e2.res = cur.p;
+                    if (last) { e2.accumulate = j > 0; e2.out_scale = (j == nk - 1) ? 1.f / nk : 1.f; }
+                    tc_conv1d(R.c2[d].tc, R.c2[d].b, xt, nxt, 1, e2, s, num_sms); launches++;
+                } else {
+                    ConvArgs c1; c1.in_slope = 0.1f; c1.dil = R.dil[d];
+                    conv(R.c1[d], cur, xt, s, c1);
+                    ConvArgs c2; c2.in_slope = 0.1f; c2.res_mode = 1; c2.res = cur.p; c2.res_C_total = u.Cout;
+                    if (last) { c2.accumulate = j > 0; c2.out_scale = (j == nk - 1) ? 1.f / nk : 1.f; }
+                    conv(R.c2[d], xt, nxt, s, c2);
+                }
+                cur = nxt;
+            }
+        }
+        if (i == 0) debug("gen_stage0", S);
+        x = S; L = Lo; ch = u.Cout;
+    }
+    dim3 grid(cdiv(L, 256), B);
+    k_conv_post_tanh<16, 7><<<grid, 256, 0, s>>>(x.p, conv_post_w, o, L, 0.01f);
+    BV2_CUDA(cudaGetLastError()); launches++;
+}
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+#define BV2_API_BEGIN(e)                                  \
+    if (!(e)) return BV2_ERR_ARG;                         \
+    std::lock_guard<std::mutex> _lk((e)->mu);             \
+    try {                                                 \
+        BV2_CUDA(cudaSetDevice((e)->device));
+#define BV2_API_END(e)                                    \
+    }                                                     \
+    catch (const bv2::Error& ex) { (e)->err = ex.what(); return ex.code; } \
+    catch (const std::exception& ex) { (e)->err = ex.what(); return BV2_ERR_INTERNAL; } \
+    return BV2_OK;
+
+static size_t ws_bytes_for(const bv2_config& c, int B, int T, int F) {
+    // generous upper bounds; every buffer is bump-allocated per call
+    size_t tok = (size_t)B * T, frm = (size_t)B * std::max(F, 1);
+    size_t enc = tok * (3 * c.bert_dim + 16 * c.hidden_channels + c.filter_channels + 2 * c.dp_filter + 64) * 4;
+    size_t flow = frm * (12 * c.hidden_channels + c.filter_channels + 4 * c.inter_channels) * 4;
+    size_t gen = frm * ((size_t)c.upsample_initial_channel + 5ull * 8192 * 5) * 4;  // 5 buffers of C*L per stage
+    return enc + flow + gen + (64u << 20);
+}
+
+extern "C" {
+
+const char* bv2_version(void) { return "bv2-b200 0.1 (sm_100a)"; }
+
+int bv2_create(bv2_engine** out, const bv2_config* cfg, int cuda_device) {
+    if (!out || !cfg) return BV2_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || cuda_device < 0 || cuda_device >= n) return BV2_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cuda_device) != cudaSuccess) return BV2_ERR_CUDA;
+    if (prop.major != 10) return BV2_ERR_CUDA;  // sm_100a only: no fallback path exists
+    bv2_engine* e = new bv2_engine();
+    e->cfg = *cfg;
+    e->device = cuda_device;
+    e->num_sms = prop.multiProcessorCount;
+    *out = e;
+    return BV2_OK;
+}
+
+int bv2_set_weight(bv2_engine* e, const char* key, const void* host_ptr, const int64_t* shape, int ndim, int dtype) {
+    if (!e || !key || !host_ptr || ndim < 0 || ndim > 4) return BV2_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (e->finalized) { e->err = "set_weight after finalize"; return BV2_ERR_STATE; }
+    if (std::strncmp(key, "enc_q.", 6) == 0) return BV2_OK;
+    HostTensor t;
+    int64_t n = 1;
+    for (int i = 0; i < ndim; i++) { t.shape.push_back(shape[i]); n *= shape[i]; }
+    t.data.resize((size_t)n);
+    if (dtype == 0) std::memcpy(t.data.data(), host_ptr, (size_t)n * 4);
+    else if (dtype == 1) { const __half* h = static_cast<const __half*>(host_ptr); for (int64_t i = 0; i < n; i++) t.data[i] = __half2float(h[i]); }
+    else { e->err = "dtype"; return BV2_ERR_ARG; }
+    e->host[key] = std::move(t);
+    return BV2_OK;
+}
+
+int bv2_finalize(bv2_engine* e) {
+    BV2_API_BEGIN(e)
+    BV2_CHECK(!e->finalized, "already finalized");
+    e->finalize();
+    BV2_API_END(e)
+}
+
+int bv2_infer_begin(bv2_engine* e, int B, int T, const int64_t* x, const int64_t* x_lengths, const int64_t* sid,
+                    const int64_t* tone, const int64_t* language, const float* bert, const float* ja_bert,
+                    const float* en_bert, const float* noise_w, float noise_scale_w, float length_scale, float sdp_ratio,
+                    const float* w_ceil_override, void* stream, int64_t* y_lengths_host, int32_t* f_max) {
+    BV2_API_BEGIN(e)
+    BV2_CHECK(e->finalized, "not finalized");
+    BV2_CHECK(B >= 1 && B <= 4096 && T >= 1 && x && x_lengths && sid && tone && language && bert && ja_bert && en_bert && noise_w &&
+                  y_lengths_host && f_max, "infer_begin args");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bv2_config& c = e->cfg;
+    const int H = c.hidden_channels, I = c.inter_channels;
+    e->dbg.clear();
+    e->ws.ensure(ws_bytes_for(c, B, T, 0));
+    e->ws.reset();
+    e->persist.ensure((size_t)B * T * (2 * I + 8) * 4 + (size_t)B * (e->gproj_n + c.gin_channels + 16) * 4 + (1 << 20));
+    e->persist.reset();
+    auto& st = e->st;
+    st.active = false; st.B = B; st.T = T;
+    st.lens = e->lens_to_device(x_lengths, B, e->persist, s);
+    float* g = e->persist.alloc((size_t)B * c.gin_channels);
+    st.gproj = e->persist.alloc((size_t)B * e->gproj_n);
+    k_gather_rows<<<B, 128, 0, s>>>(e->emb_g, reinterpret_cast<const long long*>(sid), g, c.gin_channels);
+    BV2_CUDA(cudaGetLastError()); e->launches++;
+    e->run_gproj(g, B, st.gproj, s);
+    Act h = e->ws.act(B, H, T);
+    Act stats; stats.B = B; stats.C = 2 * I; stats.T = T; stats.p = e->persist.alloc(stats.elems());
+    st.stats = stats.p;
+    e->run_text_encoder(B, T, x, tone, language, bert, ja_bert, en_bert, st.lens, st.gproj, h, stats, s);
+    e->debug("x", h); e->debug("stats", stats);
+    float* z = e->ws.alloc((size_t)B * 2 * T);
+    Act dp = e->ws.act(B, 4, T);
+    int zch = 0;
+    e->run_durations(h, st.lens, st.gproj, noise_w, noise_scale_w, z, dp, &zch, s);
+    float* lsdp = e->ws.alloc((size_t)B * T); float* ldp = e->ws.alloc((size_t)B * T);
+    st.w_ceil = e->persist.alloc((size_t)B * T);
+    st.cum = reinterpret_cast<int*>(e->persist.alloc((size_t)B * T));
+    st.ylen = reinterpret_cast<long long*>(e->persist.alloc(2 * (size_t)B + 2));
+    k_durations<<<B, 1024, 0, s>>>(z, zch, e->ea_m[0], e->ea_logs[0], dp.p, sdp_ratio, length_scale, st.lens, T, lsdp, ldp, st.w_ceil,
+                                   st.cum, st.ylen, w_ceil_override);
+    BV2_CUDA(cudaGetLastError()); e->launches++;
+    e->debug_plain("logw_sdp", lsdp, B, 1, T); e->debug_plain("logw_dp", ldp, B, 1, T); e->debug_plain("w_ceil", st.w_ceil, B, 1, T);
+    BV2_CHECK(B <= 4096, "B");
+    BV2_CUDA(cudaMemcpyAsync(e->h_ylen, st.ylen, (size_t)B * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    BV2_CUDA(cudaStreamSynchronize(s));
+    int fm = 1;
+    for (int b = 0; b < B; b++) { y_lengths_host[b] = e->h_ylen[b]; fm = std::max<long long>(fm, e->h_ylen[b]); }
+    *f_max = fm; st.F = fm;
+    st.ylen32 = e->lens_to_device(reinterpret_cast<const int64_t*>(st.ylen), B, e->persist, s);
+    st.active = true;
+    BV2_API_END(e)
+}
+
+int bv2_infer_finish(bv2_engine* e, const float* noise_z, int64_t noise_ld, float noise_scale, int32_t max_len, float* o,
+                     float* attn, float* y_mask, float* z_out, float* z_p, float* m_p, float* logs_p, void* stream) {
+    BV2_API_BEGIN(e)
+    auto& st = e->st;
+    BV2_CHECK(st.active, "infer_finish without infer_begin");
+    BV2_CHECK(noise_z && o && noise_ld >= st.F, "infer_finish args");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bv2_config& c = e->cfg;
+    const int B = st.B, T = st.T, F = st.F, I = c.inter_channels;
+    e->ws.ensure(ws_bytes_for(c, B, T, F));
+    e->ws.reset();
+    float* m_tmp = m_p ? m_p : e->ws.alloc((size_t)B * I * F);
+    float* l_tmp = logs_p ? logs_p : e->ws.alloc((size_t)B * I * F);
+    float* zp_tmp = z_p ? z_p : e->ws.alloc((size_t)B * I * F);
+    Act z = e->ws.act(B, I, F);
+    {
+        dim3 grid(cdiv(F, 128), I / 4, B);
+        k_expand_prior<<<grid, 128, 0, s>>>(st.stats, st.cum, st.ylen, st.lens, noise_z, (long long)I * noise_ld, (int)noise_ld, noise_scale,
+                                            I, T, F, m_tmp, l_tmp, zp_tmp, z.p, y_mask);
+        BV2_CUDA(cudaGetLastError()); e->launches++;
+    }
+    if (attn) {
+        dim3 grid(cdiv(T, 128), F, B);
+        k_attn_path<<<grid, 128, 0, s>>>(st.cum, st.ylen, st.lens, attn, T, F);
+        BV2_CUDA(cudaGetLastError()); e->launches++;
+    }
+    e->run_flow(z, st.ylen32, st.gproj, s);
+    e->debug("z", z);
+    if (z_out) {
+        k_c4_to_plain<<<bv2_engine::grid_tcb(F, I, B), 128, 0, s>>>(z.p, I, 0, F, z_out, I, F);
+        BV2_CUDA(cudaGetLastError()); e->launches++;
+    }
+    int Fg = F;
+    Act zg = z;
+    if (max_len > 0 && max_len < F) {
+        Fg = max_len;
+        zg = e->ws.act(B, I, Fg);
+        // slice [:, :, :max_len] (reference models.py:1073): c4 rows are contiguous per (b, cg)
+        BV2_CUDA(cudaMemcpy2DAsync(zg.p, (size_t)Fg * 16, z.p, (size_t)F * 16, (size_t)Fg * 16, (size_t)B * I / 4, cudaMemcpyDeviceToDevice, s));
+    }
+    e->run_generator(zg, st.ylen32, st.gproj + e->goff_dec, e->gproj_n, o, s);
+    st.active = false;
+    BV2_API_END(e)
+}
+
+int bv2_text_encoder(bv2_engine* e, int B, int T, const int64_t* x, const int64_t* x_lengths, const int64_t* sid,
+                     const int64_t* tone, const int64_t* language, const float* bert, const float* ja_bert, const float* en_bert,
+                     float* x_out, float* m_out, float* logs_out, void* stream) {
+    BV2_API_BEGIN(e)
+    BV2_CHECK(e->finalized, "not finalized");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bv2_config& c = e->cfg;
+    const int H = c.hidden_channels, I = c.inter_channels;
+    e->dbg.clear(); e->st.active = false;
+    e->ws.ensure(ws_bytes_for(c, B, T, 0)); e->ws.reset();
+    int* lens = e->lens_to_device(x_lengths, B, e->ws, s);
+    float* g = e->ws.alloc((size_t)B * c.gin_channels);
+    float* gp = e->ws.alloc((size_t)B * e->gproj_n);
+    k_gather_rows<<<B, 128, 0, s>>>(e->emb_g, reinterpret_cast<const long long*>(sid), g, c.gin_channels);
+    e->launches++;
+    e->run_gproj(g, B, gp, s);
+    Act h = e->ws.act(B, H, T), stats = e->ws.act(B, 2 * I, T);
+    e->run_text_encoder(B, T, x, tone, language, bert, ja_bert, en_bert, lens, gp, h, stats, s);
+    k_c4_to_plain<<<bv2_engine::grid_tcb(T, H, B), 128, 0, s>>>(h.p, H, 0, T, x_out, H, T);
+    k_c4_to_plain<<<bv2_engine::grid_tcb(T, I, B), 128, 0, s>>>(stats.p, 2 * I, 0, T, m_out, I, T);
+    k_c4_to_plain<<<bv2_engine::grid_tcb(T, I, B), 128, 0, s>>>(stats.p, 2 * I, I, T, logs_out, I, T);
+    BV2_CUDA(cudaGetLastError()); e->launches += 3;
+    BV2_API_END(e)
+}
+
+int bv2_duration(bv2_engine* e, int B, int T, const float* x, const int64_t* x_lengths, const int64_t* sid, const float* noise_w,
+                 float noise_scale_w, float* logw_sdp, float* logw_dp, void* stream) {
+    BV2_API_BEGIN(e)
+    BV2_CHECK(e->finalized, "not finalized");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bv2_config& c = e->cfg;
+    const int H = c.hidden_channels;
+    e->dbg.clear(); e->st.active = false;
+    e->ws.ensure(ws_bytes_for(c, B, T, 0)); e->ws.reset();
+    int* lens = e->lens_to_device(x_lengths, B, e->ws, s);
+    float* g = e->ws.alloc((size_t)B * c.gin_channels);
+    float* gp = e->ws.alloc((size_t)B * e->gproj_n);
+    k_gather_rows<<<B, 128, 0, s>>>(e->emb_g, reinterpret_cast<const long long*>(sid), g, c.gin_channels);
+    e->launches++;
+    e->run_gproj(g, B, gp, s);
+    Act h = e->ws.act(B, H, T);
+    k_plain_to_c4<<<bv2_engine::grid_tcb(T, H, B), 128, 0, s>>>(x, H, (long long)H * T, T, h.p, H, 0, T, nullptr, 1.f);
+    e->launches++;
+    float* z = e->ws.alloc((size_t)B * 2 * T);
+    Act dp = e->ws.act(B, 4, T);
+    int zch = 0;
+    e->run_durations(h, lens, gp, noise_w, noise_scale_w, z, dp, &zch, s);
+    float* wc = e->ws.alloc((size_t)B * T);
+    int* cum = reinterpret_cast<int*>(e->ws.alloc((size_t)B * T));
+    long long* yl = reinterpret_cast<long long*>(e->ws.alloc(2 * (size_t)B + 2));
+    k_durations<<<B, 1024, 0, s>>>(z, zch, e->ea_m[0], e->ea_logs[0], dp.p, 0.5f, 1.f, lens, T, logw_sdp, logw_dp, wc, cum, yl, nullptr);
+    BV2_CUDA(cudaGetLastError()); e->launches++;
+    BV2_API_END(e)
+}
+
+int bv2_flow_reverse(bv2_engine* e, int B, int F, const float* z_p, const int64_t* y_lengths, const int64_t* sid, float* z_out,
+                     void* stream) {
+    BV2_API_BEGIN(e)
+    BV2_CHECK(e->finalized, "not finalized");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bv2_config& c = e->cfg;
+    const int I = c.inter_channels;
+    e->dbg.clear(); e->st.active = false;
+    e->ws.ensure(ws_bytes_for(c, B, 1, F)); e->ws.reset();
+    int* lens = e->lens_to_device(y_lengths, B, e->ws, s);
+    float* g = e->ws.alloc((size_t)B * c.gin_channels);
+    float* gp = e->ws.alloc((size_t)B * e->gproj_n);
+    k_gather_rows<<<B, 128, 0, s>>>(e->emb_g, reinterpret_cast<const long long*>(sid), g, c.gin_channels);
+    e->launches++;
+    e->run_gproj(g, B, gp, s);
+    Act z = e->ws.act(B, I, F);
+    k_plain_to_c4<<<bv2_engine::grid_tcb(F, I, B), 128, 0, s>>>(z_p, I, (long long)I * F, F, z.p, I, 0, F, nullptr, 1.f);
+    e->launches++;
+    e->run_flow(z, lens, gp, s);
+    k_c4_to_plain<<<bv2_engine::grid_tcb(F, I, B), 128, 0, s>>>(z.p, I, 0, F, z_out, I, F);
+    BV2_CUDA(cudaGetLastError()); e->launches++;
+    BV2_API_END(e)
+}
+
+int bv2_generator(bv2_engine* e, int B, int F, const float* z_in, const float* g, float* o, void* stream) {
+    BV2_API_BEGIN(e)
+    BV2_CHECK(e->finalized, "not finalized");
+    BV2_CHECK(B >= 1 && F >= 1 && z_in && g && o, "generator args");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const bv2_config& c = e->cfg;
+    const int I = c.inter_channels;
+    e->dbg.clear(); e->st.active = false;
+    e->ws.ensure(ws_bytes_for(c, B, 1, F)); e->ws.reset();
+    float* gp = e->ws.alloc((size_t)B * e->gproj_n);
+    e->run_gproj(g, B, gp, s);
+    Act z = e->ws.act(B, I, F);
+    k_plain_to_c4<<<bv2_engine::grid_tcb(F, I, B), 128, 0, s>>>(z_in, I, (long long)I * F, F, z.p, I, 0, F, nullptr, 1.f);
+    BV2_CUDA(cudaGetLastError()); e->launches++;
+    e->run_generator(z, nullptr, gp + e->goff_dec, e->gproj_n, o, s);
+    BV2_API_END(e)
+}
+
+int64_t bv2_debug_read(bv2_engine* e, const char* name, float* host_out, int64_t capacity) {
+    if (!e || !name || !host_out) return BV2_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    try {
+        BV2_CUDA(cudaSetDevice(e->device));
+        auto it = e->dbg.find(name);
+        if (it == e->dbg.end()) { e->err = std::string("no debug buffer ") + name; return BV2_ERR_ARG; }
+        const DebugBuf& d = it->second;
+        int64_t n = (int64_t)d.B * d.C * d.T;
+        if (n > capacity) { e->err = "capacity"; return BV2_ERR_ARG; }
+        BV2_CUDA(cudaDeviceSynchronize());
+        if (!d.c4) {
+            BV2_CUDA(cudaMemcpy(host_out, d.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        } else {
+            float* tmp = nullptr;
+            BV2_CUDA(cudaMalloc(&tmp, (size_t)n * 4));
+            k_c4_to_plain<<<bv2_engine::grid_tcb(d.T, d.C, d.B), 128>>>(d.p, d.C, 0, d.T, tmp, d.C, d.T);
+            cudaError_t er = cudaMemcpy(host_out, tmp, (size_t)n * 4, cudaMemcpyDeviceToHost);
+            cudaFree(tmp);
+            BV2_CUDA(er);
+        }
+        return n;
+    } catch (const bv2::Error& ex) { e->err = ex.what(); return ex.code; }
+}
+
+int64_t bv2_launch_count(const bv2_engine* e) { return e ? e->launches : 0; }
+int64_t bv2_workspace_bytes(const bv2_engine* e) { return e ? (int64_t)(e->ws.cap() + e->persist.cap()) : 0; }
+const char* bv2_last_error(const bv2_engine* e) { return e ? e->err.c_str() : "null engine"; }
+void bv2_destroy(bv2_engine* e) { delete e; }
+
+}  // extern "C"

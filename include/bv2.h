@@ -1,0 +1,116 @@
+/* libbv2 -- C ABI of the Blackwell-native VITS2 inference engine (Bert-VITS2 v2.3 `SynthesizerTrn.infer`).
+ *
+ * The reference has no FFI/plugin layer: its seam is the Python class `models.SynthesizerTrn`
+ * (reference models.py:811-1074) constructed by `infer.get_net_g` (reference infer.py:84-104) and driven by
+ * `infer.infer` / `infer_multilang` (reference infer.py:302-318, 407-423).  This header is what a ctypes
+ * binding behind that class binds (bert_vits2_b200/engine.py; INTEGRATION.md shows the reference-side stub).
+ *
+ * Conventions: every function returns 0 on success or a negative bv2_status; nothing throws or aborts across
+ * the ABI; `bv2_last_error` returns a thread-unsafe, engine-owned message for the last failure.  The caller
+ * owns every input/output buffer (device pointers unless noted, fp32 contiguous, reference tensor layouts
+ * [B,C,T]); the engine owns weights and workspace.  Work is enqueued on the caller's `stream`
+ * (a cudaStream_t passed as void*); the only host synchronisation is inside bv2_infer_begin (one read-back of
+ * y_lengths, the same data-dependent length the reference syncs on at models.py:1058 / commons.py:120-121).
+ * One engine per device; concurrent callers are serialised by an internal mutex (ctypes drops the GIL).
+ * There is NO CPU fallback: creation fails if no sm_100 device is present.
+ */
+#ifndef BV2_H_
+#define BV2_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bv2_engine bv2_engine;
+
+typedef enum {
+    BV2_OK = 0,
+    BV2_ERR_ARG = -1,      /* bad argument / unsupported configuration (reference raises ValueError) */
+    BV2_ERR_STATE = -2,    /* call order violated (weights missing, not finalized, begin/finish mismatch) */
+    BV2_ERR_CUDA = -3,     /* CUDA runtime error */
+    BV2_ERR_INTERNAL = -4
+} bv2_status;
+
+#define BV2_MAX_UPS 8
+#define BV2_MAX_RESBLOCK_KERNELS 4
+#define BV2_MAX_DILATIONS 4
+
+/* `hps.model` + ctor args of reference models.SynthesizerTrn.__init__ (models.py:816-841). */
+typedef struct {
+    int32_t n_vocab, num_tones, num_languages, bert_dim;
+    int32_t inter_channels, hidden_channels, filter_channels, n_heads, n_layers, kernel_size, window_size;
+    int32_t gin_channels, n_speakers;
+    int32_t n_flow_layer, n_layers_trans_flow, use_transformer_flow, flow_kernel_size, wn_layers;
+    int32_t upsample_initial_channel, n_ups;
+    int32_t upsample_rates[BV2_MAX_UPS], upsample_kernel_sizes[BV2_MAX_UPS];
+    int32_t n_resblock_kernels, n_dilations;
+    int32_t resblock_kernel_sizes[BV2_MAX_RESBLOCK_KERNELS];
+    int32_t resblock_dilation_sizes[BV2_MAX_RESBLOCK_KERNELS][BV2_MAX_DILATIONS];
+    int32_t sdp_filter, sdp_kernel, sdp_n_flows, sdp_dds_layers, sdp_num_bins;
+    float sdp_tail_bound;
+    int32_t dp_filter, dp_kernel, cond_layer_idx;
+    int32_t generator_precision; /* 0 = fp32 SIMT convs, 1 = TF32 tcgen05 implicit-GEMM convs (fp32 accumulate) */
+} bv2_config;
+
+/* replaces: models.SynthesizerTrn(...).to(device) (reference infer.py:95-101) */
+int bv2_create(bv2_engine** out, const bv2_config* cfg, int cuda_device);
+
+/* replaces: load_state_dict for one entry of `G_*.pth["model"]` (reference utils.py:65-120).
+ * `key` is the reference state_dict key (weight-norm as weight_g/weight_v); host_ptr is HOST memory;
+ * dtype: 0 = fp32, 1 = fp16 (compress_model.py:49-52 checkpoints).  Unknown keys (enc_q.*) are ignored. */
+int bv2_set_weight(bv2_engine* e, const char* key, const void* host_ptr, const int64_t* shape, int ndim, int dtype);
+
+/* folds weight-norm (incl. ConvTranspose dim-0 = in_channels), folds Flip into coupling weights,
+ * packs and uploads.  replaces: net_g.eval() + the per-call weight-norm re-evaluation of the reference. */
+int bv2_finalize(bv2_engine* e);
+
+/* ---- whole path: SynthesizerTrn.infer (reference models.py:1026-1074), split at the data-dependent length.
+ * begin: emb_g -> enc_p -> sdp/dp -> durations.  Inputs as the reference passes them (int64 ids, fp32 feats).
+ *   noise_w [B,2,T] replaces torch.randn at models.py:249.  w_ceil_override (optional, [B,T] fp32) teacher-forces
+ *   durations for parity harnesses.  Writes y_lengths_host[B] (HOST) and *f_max = max(y_lengths).            */
+int bv2_infer_begin(bv2_engine* e, int B, int T, const int64_t* x, const int64_t* x_lengths, const int64_t* sid,
+                    const int64_t* tone, const int64_t* language, const float* bert, const float* ja_bert,
+                    const float* en_bert, const float* noise_w, float noise_scale_w, float length_scale,
+                    float sdp_ratio, const float* w_ceil_override, void* stream, int64_t* y_lengths_host,
+                    int32_t* f_max);
+
+/* finish: length regulation -> prior sample -> flow reverse -> Generator.  noise_z [B,inter,>=F] with row stride
+ * noise_ld replaces torch.randn_like at models.py:1071.  Outputs (caller-allocated, any may be NULL except o):
+ *   o [B,1,Fg*hop] with Fg = min(F, max_len), attn [B,1,F,T], y_mask [B,1,F], z/z_p/m_p/logs_p [B,inter,F]. */
+int bv2_infer_finish(bv2_engine* e, const float* noise_z, int64_t noise_ld, float noise_scale, int32_t max_len,
+                     float* o, float* attn, float* y_mask, float* z, float* z_p, float* m_p, float* logs_p,
+                     void* stream);
+
+/* ---- per-stage entry points (parity tests + microbenchmarks; same kernels as the whole path) ---------------
+ * text encoder: outputs x [B,H,T], m_p/logs_p [B,inter,T] (reference models.py:377-400)                       */
+int bv2_text_encoder(bv2_engine* e, int B, int T, const int64_t* x, const int64_t* x_lengths, const int64_t* sid,
+                     const int64_t* tone, const int64_t* language, const float* bert, const float* ja_bert,
+                     const float* en_bert, float* x_out, float* m_out, float* logs_out, void* stream);
+/* duration predictors on a given encoder output x [B,H,T]: logw_sdp/logw_dp [B,1,T]
+ * (reference models.py:197-204,245-256 and 285-299)                                                         */
+int bv2_duration(bv2_engine* e, int B, int T, const float* x, const int64_t* x_lengths, const int64_t* sid,
+                 const float* noise_w, float noise_scale_w, float* logw_sdp, float* logw_dp, void* stream);
+/* flow reverse on z_p [B,inter,F] -> z (reference models.py:142-145 / 442-445)                               */
+int bv2_flow_reverse(bv2_engine* e, int B, int F, const float* z_p, const int64_t* y_lengths, const int64_t* sid,
+                     float* z, void* stream);
+/* Generator: z [B,inter,F], g [B,gin] -> o [B,1,F*hop] (reference models.py:538-557)                          */
+int bv2_generator(bv2_engine* e, int B, int F, const float* z, const float* g, float* o, void* stream);
+
+/* Debug tap: copy a named internal stage buffer of the LAST call (converted to [B,C,T]) to HOST memory.
+ * Returns the number of floats written, or a negative status.                                               */
+int64_t bv2_debug_read(bv2_engine* e, const char* name, float* host_out, int64_t capacity);
+
+/* Counters: kernels launched by the engine since creation / bytes of workspace in use. */
+int64_t bv2_launch_count(const bv2_engine* e);
+int64_t bv2_workspace_bytes(const bv2_engine* e);
+
+const char* bv2_last_error(const bv2_engine* e);
+const char* bv2_version(void);
+void bv2_destroy(bv2_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BV2_H_ */
