@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the SynthesizerTrn.infer hot path (BASELINE.json metric: audio-sec/s at 44.1 kHz).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+A "step" is one whole infer() over one batch of synthetic get_text() outputs (config 2 of BASELINE.json:
+B=1, 256-phoneme ZH utterance, 44.1 kHz, full path: enc_p -> SDP/DP -> length regulation -> flow -> Generator).
+Synthetic seeded weights of the reference architecture (no network for checkpoints): bert_vits2_b200.synth.
+
+  value   whole-job audio-seconds per second with the inputs resident in HBM (device-timed, CUDA events,
+          barrier + synchronize on both sides, max over ranks)
+  e2e     the same through the public drop-in API SynthesizerTrn.infer() from pinned HOST buffers: H2D of the
+          step's inputs and D2H of the waveform inside the timed region
+  roofline  Generator stage (>99 % of FLOPs): algorithmic layer-boundary bytes (6 830 852 B per
+          frame) / device time of the stage measured with CUDA events inside the timed steps, against the
+          measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle port of the reference (oracle/vits2_oracle.py; /root/reference does not exist on
+          the GPU box) on the host cores, bounded sample of the same workload
+
+Multi-GPU (--gpus N under torchrun): utterances shard embarrassingly; every rank runs the same per-GPU
+workload (weak scaling) and the waveforms are gathered to rank 0 with one NCCL gather inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from bert_vits2_b200 import synth  # noqa: E402
+from bert_vits2_b200.spec import ModelConfig  # noqa: E402
+
+SR, HOP = 44100, 512
+GEN_BYTES_PER_FRAME = 6_830_852      # SURVEY.md §8d, layer-boundary algorithmic bytes, fp32 activations
+GEN_FLOP_PER_FRAME = 651_608_576
+INFER_KW = dict(sdp_ratio=0.5, noise_scale=0.6, noise_scale_w=0.9, length_scale=1.0)  # webui defaults (webui.py:443-454)
+WORKLOAD = dict(B=1, T=256, languages=[0])  # BASELINE.json configs[1]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_cores():
+    """Usable host threads: affinity mask capped by the cgroup CPU quota (os.cpu_count() ignores both)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return n
+
+
+def cpu_oracle_rate(cfg, sd, budget_s=20.0, max_iters=5):
+    """Bounded CPU sample of the same workload: the first CPU_T phonemes of the config-2 utterance through the whole
+    path (audio-s/s is a rate, so a shorter utterance of the same kind is a fair sample)."""
+    from oracle import vits2_oracle as O
+    CPU_T = 64
+    avail = host_cores()
+    # pick the thread count that serves the reference best on this host (all threads can be far slower than a subset
+    # on many-core boxes because the path is ~12 k small ATen ops): probe on a 16-phoneme utterance
+    pin = synth.synthetic_inputs(cfg, [16], [0], seed=3)
+    pnw, pnz = synth.synthetic_noise(cfg, 1, 16, 1024, seed=3)
+    best, cores = None, avail
+    for n_thr in sorted({min(avail, 8), min(avail, 32), avail}):
+        torch.set_num_threads(n_thr)
+        O.infer(sd, cfg, **pin, noise_w=pnw, noise_z=pnz, **INFER_KW)
+        c0 = time.perf_counter()
+        O.infer(sd, cfg, **pin, noise_w=pnw, noise_z=pnz, **INFER_KW)
+        dt = time.perf_counter() - c0
+        if best is None or dt < best:
+            best, cores = dt, n_thr
+        if dt > 5.0:
+            break
+    torch.set_num_threads(cores)
+    inp = synth.synthetic_inputs(cfg, [CPU_T], [0], seed=2)
+    nw, nz = synth.synthetic_noise(cfg, 1, CPU_T, 4096, seed=2)
+    secs, n, audio = 0.0, 0, 0.0
+    t_start = time.perf_counter()
+    for i in range(max_iters + 1):
+        c0 = time.perf_counter()
+        oo, _, ym, _ = O.infer(sd, cfg, **inp, noise_w=nw, noise_z=nz, **INFER_KW)
+        dt = time.perf_counter() - c0
+        if i:
+            secs += dt; n += 1; audio += float(ym.sum()) * HOP / SR
+        if time.perf_counter() - t_start > budget_s and n >= 1:
+            break
+    return {"value": audio / secs, "unit": "audio-s/s", "cores": cores, "cores_available": avail, "kind": "port",
+            "sample": f"{n} x first {CPU_T} phonemes of the config2 utterance ({audio / n:.2f} s audio each) after 1 warm-up, "
+                      f"torch CPU fp32 oracle port of the reference, weight-norm re-evaluated per call"}, secs / n
+
+
+def make_case(cfg, rank):
+    wl = WORKLOAD
+    inp = synth.synthetic_inputs(cfg, [wl["T"]] * wl["B"], wl["languages"] * wl["B"], seed=2 + rank)
+    nw, nz = synth.synthetic_noise(cfg, wl["B"], wl["T"], 4096, seed=2 + rank)
+    return inp, nw, nz
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host threads, same config/metric."""
+    if rank != 0:
+        return
+    from oracle import vits2_oracle as O
+    cfg = ModelConfig()
+    sd = synth.synthetic_state_dict(cfg, 0)
+    steps, warm = max(1, min(args.steps, 5)), 1
+    cb, sec_per = cpu_oracle_rate(cfg, sd, budget_s=60.0, max_iters=steps)
+    v, cores = cb["value"], cb["cores"]
+    audio = v * sec_per
+    frames = int(round(audio * SR / HOP))
+    secs = sec_per * steps
+    line = {
+        "impl": "reference", "metric": "audio-sec/s (real-time factor) at 44.1kHz", "value": v, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * secs / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config2: B=1, T=256 ZH phonemes, full SynthesizerTrn.infer path (transformer flow)", "frames": frames,
+                   "audio_seconds_per_step": audio, "sample": cb["sample"]},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("BV2_PRECISION", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--cpu-baseline-steps", type=int, default=3)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from bert_vits2_b200.models import SynthesizerTrn
+    cfg = ModelConfig()
+    sd = synth.synthetic_state_dict(cfg, 0)
+    net = SynthesizerTrn(cfg.n_vocab, 1025, 32, 192, 192, 768, 2, 6, 3, 0.1, "1", [3, 7, 11], [[1, 3, 5]] * 3, [8, 8, 2, 2, 2], 512,
+                         [16, 16, 8, 2, 2], n_speakers=cfg.n_speakers, gin_channels=512, init_seed=None, precision=args.precision)
+    net.load_state_dict(sd, strict=False)
+    net = net.to(dev).eval()
+    eng = net._engine(dev)
+    eng.set_profiling(True)
+    inp, nw, nz = make_case(cfg, rank)
+    B, T = inp["x"].shape
+    d_inp = {k: v.to(dev) for k, v in inp.items()}
+    d_nw, d_nz = nw.to(dev), nz.to(dev)
+    h_inp = {k: v.pin_memory() for k, v in inp.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    gather_buf = None
+
+    def gather_wave(o):
+        # the ONLY exchange step of the path: final waveform batch to rank 0 over NVLink (NCCL)
+        nonlocal gather_buf
+        if world == 1:
+            return
+        if rank == 0 and (gather_buf is None or gather_buf[0].shape != o.shape):
+            gather_buf = [torch.empty_like(o) for _ in range(world)]
+        dist.gather(o, gather_buf if rank == 0 else None, dst=0)
+
+    def step_resident():
+        ylen, F = eng.infer_begin(d_inp["x"], d_inp["x_lengths"], d_inp["sid"], d_inp["tone"], d_inp["language"], d_inp["bert"],
+                                  d_inp["ja_bert"], d_inp["en_bert"], d_nw, INFER_KW["noise_scale_w"], INFER_KW["length_scale"],
+                                  INFER_KW["sdp_ratio"])
+        o, attn, y_mask, aux = eng.infer_finish(B, T, F, d_nz, INFER_KW["noise_scale"])
+        gather_wave(o)
+        return int(ylen.sum()), o
+
+    def step_e2e():
+        dd = {k: v.to(dev, non_blocking=True) for k, v in h_inp.items()}
+        o, attn, y_mask, aux = net.infer(dd["x"], dd["x_lengths"], dd["sid"], dd["tone"], dd["language"], dd["bert"], dd["ja_bert"],
+                                         dd["en_bert"], **INFER_KW)
+        gather_wave(o)
+        wav = o[:, 0].cpu()  # D2H of the step's result, as infer.py:315-318 does
+        return int(net.last_y_lengths.sum()), wav
+
+    # ---------------- device-resident value
+    for _ in range(args.warmup):
+        step_resident()
+    l0 = eng.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    frames, gen_ms = 0, []
+    for _ in range(args.steps):
+        f, o = step_resident()
+        frames += f
+        gen_ms.append(eng.stage_ms("generator"))  # blocks on this step's generator end event only
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launch_count - l0
+    flow_ms, enc_ms = eng.stage_ms("flow"), eng.stage_ms("encoder_duration")
+    # ---------------- end to end through the public API with host buffers
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    frames_e = 0
+    for _ in range(args.steps):
+        f, wav = step_e2e()
+        frames_e += f
+    t1.record()
+    barrier()
+    ms_e = t0.elapsed_time(t1)
+    h2d = sum(v.numel() * v.element_size() for v in h_inp.values())
+    d2h = wav.numel() * wav.element_size()
+    # ---------------- max over ranks
+    stats = torch.tensor([ms, ms_e, float(frames), float(frames_e)], device=dev, dtype=torch.float64)
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, ms_e = float(mx[0]), float(mx[1]); frames, frames_e = float(sm[2]), float(sm[3])
+    if rank == 0:
+        audio = frames * HOP / SR
+        value = audio / (ms * 1e-3)
+        e2e_v = (frames_e * HOP / SR) / (ms_e * 1e-3)
+        hbm, how = peaks()
+        fpu = frames / (args.steps * world)  # frames per utterance-step on one GPU
+        g_ms = float(np.mean(gen_ms))
+        ach = GEN_BYTES_PER_FRAME * fpu / (g_ms * 1e-3) / 1e9
+        line = {
+            "metric": "audio-sec/s (real-time factor) at 44.1kHz", "value": value, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": "config2: B=1, T=256 ZH phonemes per GPU, full SynthesizerTrn.infer path (transformer flow)",
+                       "global_batch": world * B, "frames_per_utterance": fpu, "audio_seconds_per_step": audio / args.steps,
+                       "parallelism": f"dp{world} (utterance sharding, NCCL gather of waveforms)" if world > 1 else "single GPU",
+                       "precision": args.precision,
+                       "l2": "no explicit flush: each step streams ~0.7 GB of fp32 activations (> 126 MB L2)"},
+            "e2e": {"value": e2e_v, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "Generator stage (conv_pre .. conv_post+tanh, 98 convolutions)", "achieved": ach, "peak": hbm,
+                         "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": how, "stage_ms": g_ms,
+                         "tensor_tflops": GEN_FLOP_PER_FRAME * fpu / (g_ms * 1e-3) / 1e12},
+            "stage_ms": {"encoder_duration": enc_ms, "flow": flow_ms, "generator": g_ms},
+        }
+        # CPU baseline on rank 0 at N=1 only: bounded sample of the same workload
+        if world == 1 and args.cpu_baseline_steps > 0:
+            line["cpu_baseline"], _ = cpu_oracle_rate(cfg, sd, budget_s=20.0, max_iters=args.cpu_baseline_steps)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,8 @@ SYMBOLS = {
     "bv2_flow_reverse": (C.c_int, [P, C.c_int, C.c_int, F32P, I64P, I64P, F32P, C.c_void_p]),
     "bv2_generator": (C.c_int, [P, C.c_int, C.c_int, F32P, F32P, F32P, C.c_void_p]),
     "bv2_debug_read": (C.c_int64, [P, C.c_char_p, C.c_void_p, C.c_int64]),
+    "bv2_set_profiling": (C.c_int, [P, C.c_int]),
+    "bv2_stage_ms": (C.c_float, [P, C.c_char_p]),
     "bv2_launch_count": (C.c_int64, [P]),
     "bv2_workspace_bytes": (C.c_int64, [P]),
     "bv2_last_error": (C.c_char_p, [P]),

@@ -102,10 +102,25 @@ struct bv2_engine {
         float* gproj = nullptr; float* w_ceil = nullptr;
     } st;
     long long* h_ylen = nullptr;  // pinned
+    bool profiling = false;
+    struct StageEv { cudaEvent_t a = nullptr, b = nullptr; bool rec = false; };
+    std::map<std::string, StageEv> stage_ev;
+    void stage_begin(const char* n, cudaStream_t s) {
+        if (!profiling) return;
+        StageEv& ev = stage_ev[n];
+        if (!ev.a) { BV2_CUDA(cudaEventCreate(&ev.a)); BV2_CUDA(cudaEventCreate(&ev.b)); }
+        BV2_CUDA(cudaEventRecord(ev.a, s)); ev.rec = false;
+    }
+    void stage_end(const char* n, cudaStream_t s) {
+        if (!profiling) return;
+        StageEv& ev = stage_ev[n];
+        BV2_CUDA(cudaEventRecord(ev.b, s)); ev.rec = true;
+    }
 
     ~bv2_engine() {
         for (void* p : dev_allocs) cudaFree(p);
         if (h_ylen) cudaFreeHost(h_ylen);
+        for (auto& kv : stage_ev) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
     }
 
     // ---------------------------------------------------------------- weights
@@ -717,6 +732,7 @@ int bv2_infer_begin(bv2_engine* e, int B, int T, const int64_t* x, const int64_t
     e->persist.reset();
     auto& st = e->st;
     st.active = false; st.B = B; st.T = T;
+    e->stage_begin("encoder_duration", s);
     st.lens = e->lens_to_device(x_lengths, B, e->persist, s);
     float* g = e->persist.alloc((size_t)B * c.gin_channels);
     st.gproj = e->persist.alloc((size_t)B * e->gproj_n);
@@ -740,7 +756,7 @@ int bv2_infer_begin(bv2_engine* e, int B, int T, const int64_t* x, const int64_t
                                    st.cum, st.ylen, w_ceil_override);
     BV2_CUDA(cudaGetLastError()); e->launches++;
     e->debug_plain("logw_sdp", lsdp, B, 1, T); e->debug_plain("logw_dp", ldp, B, 1, T); e->debug_plain("w_ceil", st.w_ceil, B, 1, T);
-    BV2_CHECK(B <= 4096, "B");
+    e->stage_end("encoder_duration", s);
     BV2_CUDA(cudaMemcpyAsync(e->h_ylen, st.ylen, (size_t)B * sizeof(long long), cudaMemcpyDeviceToHost, s));
     BV2_CUDA(cudaStreamSynchronize(s));
     int fm = 1;
@@ -777,7 +793,9 @@ int bv2_infer_finish(bv2_engine* e, const float* noise_z, int64_t noise_ld, floa
         k_attn_path<<<grid, 128, 0, s>>>(st.cum, st.ylen, st.lens, attn, T, F);
         BV2_CUDA(cudaGetLastError()); e->launches++;
     }
+    e->stage_begin("flow", s);
     e->run_flow(z, st.ylen32, st.gproj, s);
+    e->stage_end("flow", s);
     e->debug("z", z);
     if (z_out) {
         k_c4_to_plain<<<bv2_engine::grid_tcb(F, I, B), 128, 0, s>>>(z.p, I, 0, F, z_out, I, F);
@@ -791,7 +809,9 @@ int bv2_infer_finish(bv2_engine* e, const float* noise_z, int64_t noise_ld, floa
         // slice [:, :, :max_len] (reference models.py:1073): c4 rows are contiguous per (b, cg)
         BV2_CUDA(cudaMemcpy2DAsync(zg.p, (size_t)Fg * 16, z.p, (size_t)F * 16, (size_t)Fg * 16, (size_t)B * I / 4, cudaMemcpyDeviceToDevice, s));
     }
+    e->stage_begin("generator", s);
     e->run_generator(zg, st.ylen32, st.gproj + e->goff_dec, e->gproj_n, o, s);
+    e->stage_end("generator", s);
     st.active = false;
     BV2_API_END(e)
 }
@@ -889,7 +909,9 @@ int bv2_generator(bv2_engine* e, int B, int F, const float* z_in, const float* g
     Act z = e->ws.act(B, I, F);
     k_plain_to_c4<<<bv2_engine::grid_tcb(F, I, B), 128, 0, s>>>(z_in, I, (long long)I * F, F, z.p, I, 0, F, nullptr, 1.f);
     BV2_CUDA(cudaGetLastError()); e->launches++;
+    e->stage_begin("generator", s);
     e->run_generator(z, nullptr, gp + e->goff_dec, e->gproj_n, o, s);
+    e->stage_end("generator", s);
     BV2_API_END(e)
 }
 
@@ -916,6 +938,25 @@ int64_t bv2_debug_read(bv2_engine* e, const char* name, float* host_out, int64_t
         }
         return n;
     } catch (const bv2::Error& ex) { e->err = ex.what(); return ex.code; }
+}
+
+int bv2_set_profiling(bv2_engine* e, int enable) {
+    if (!e) return BV2_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->profiling = enable != 0;
+    return BV2_OK;
+}
+
+float bv2_stage_ms(bv2_engine* e, const char* stage) {
+    if (!e || !stage) return -1.f;
+    std::lock_guard<std::mutex> lk(e->mu);
+    auto it = e->stage_ev.find(stage);
+    if (it == e->stage_ev.end() || !it->second.rec) return -1.f;
+    cudaSetDevice(e->device);
+    if (cudaEventSynchronize(it->second.b) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, it->second.a, it->second.b) != cudaSuccess) return -1.f;
+    return ms;
 }
 
 int64_t bv2_launch_count(const bv2_engine* e) { return e ? e->launches : 0; }

@@ -1,26 +1,290 @@
-// tcgen05 (TF32, fp32 accumulate in TMEM) implicit-GEMM Conv1d on the c4 layout.  [placeholder: filled in next]
+// tcgen05 (5th-gen tensor core) implicit-GEMM Conv1d on the c4 activation layout, TF32 operands, fp32 accumulate
+// in TMEM.  Replaces the 90 dilated MRF convolutions of the HiFi-GAN Generator (reference modules.py:296-309 via
+// models.py:546-552) = 96 % of the MACs of SynthesizerTrn.infer.
+//
+// GEMM view of one CTA tile:  D[128 time steps, N = Cout] += sum_{tap j} sum_{ci}  A_j[t, ci] * W_j[ci, co]
+//   A_j[t, ci] = act(x[ci][t0 + t + j*dil - pad])  -- a time-shifted view of ONE staged activation tile.
+// With the c4 layout a tile chunk is staged as [KC/4 channel groups][R = 128 + (K-1)*dil rows][4 ch] fp32, i.e. the
+// K-major / no-swizzle UMMA canonical layout with SBO = 128 B (8 rows x 16 B) and LBO = R*16 B, so tap j is just the
+// smem-descriptor start address advanced by j*dil*16 bytes: the im2col matrix is never materialised and each
+// activation byte is fetched from HBM/L2 once per conv instead of K times.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (cp.async.bulk, mbarrier complete_tx), warp 1 = TMEM allocator +
+// single-thread tcgen05.mma issuer, warps 2-5 = operand prologue (leaky-relu + round-to-nearest TF32 in smem, zero
+// fill of the conv padding rows, fence.proxy.async) and TMEM epilogue (tcgen05.ld -> +bias, +residual, MRF
+// accumulate/scale -> coalesced 16-byte stores).
 #pragma once
+#include <cstring>
 #include <functional>
 #include <vector>
 #include "common.cuh"
 
 namespace bv2 {
 
-struct TcConvW { float* w = nullptr; int Cin = 0, Cout = 0, K = 0; };
+struct TcConvW {
+    float* w = nullptr;  // packed [nchunks][K][KC/4][Cout][4], TF32-rounded (RN)
+    int Cin = 0, Cout = 0, K = 0, KC = 0, nchunks = 0;
+};
 struct TcEpi {
-    float in_slope = 1.f;
-    const float* res = nullptr;
-    int accumulate = 0;
+    float in_slope = 1.f;        // leaky-relu slope applied to the conv INPUT (1 = identity)
+    const float* res = nullptr;  // residual, c4 [B][Cout/4][T][4]
+    int accumulate = 0;          // y = (y_old + v) * out_scale
     float out_scale = 1.f;
 };
 
+inline float tf32_rn_host(float x) {
+    uint32_t u; std::memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return x;
+    u = (u + 0x1000u) & 0xffffe000u;  // round to nearest, ties away (== cvt.rna.tf32.f32)
+    float r; std::memcpy(&r, &u, 4);
+    return r;
+}
+
+// w: [Cout][Cin][K] fp32 (weight-norm already folded)
 inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>& up, const std::vector<float>& w, int Cout, int Cin, int K) {
-    (void)up; (void)w;
     TcConvW t; t.Cin = Cin; t.Cout = Cout; t.K = K;
+    t.KC = Cin >= 32 ? 32 : Cin;
+    if (Cin % t.KC != 0 || t.KC % 8 != 0 || Cout % 16 != 0 || Cout > 256 || Cout < 16)
+        throw Error(-2, "tc_conv: unsupported channel counts " + std::to_string(Cin) + "->" + std::to_string(Cout));
+    t.nchunks = Cin / t.KC;
+    std::vector<float> p((size_t)Cin * K * Cout);
+    const int ncg = t.KC / 4;
+    for (int c = 0; c < t.nchunks; c++)
+        for (int j = 0; j < K; j++)
+            for (int g = 0; g < ncg; g++)
+                for (int n = 0; n < Cout; n++)
+                    for (int e = 0; e < 4; e++) {
+                        int ci = c * t.KC + g * 4 + e;
+                        p[((((size_t)c * K + j) * ncg + g) * Cout + n) * 4 + e] = tf32_rn_host(w[((size_t)n * Cin + ci) * K + j]);
+                    }
+    t.w = up(p);
     return t;
 }
-inline void tc_conv1d(const TcConvW&, const float*, const Act&, const Act&, int, const TcEpi&, cudaStream_t, int) {
-    throw Error(-4, "tcgen05 conv path not built");
+
+struct TcParams {
+    const float* x; float* y; const float* w; const float* bias; const float* res;
+    int Cin, N, T, B, K, dil, pad, KC, nchunks, R, nws;
+    uint32_t a_stage_bytes, w_stage_bytes, tmem_cols, idesc;
+    float in_slope, out_scale; int accumulate;
+};
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+}  // namespace tc
+
+__global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * 128, b = blockIdx.y;
+    uint8_t* sA = smem;
+    uint8_t* sW = smem + 2 * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)p.nws * p.w_stage_bytes);
+    // barrier map: [0,2) a_full, [2,4) a_ready, [4,6) a_empty, [6,6+nws) w_full, [6+nws,6+2nws) w_empty, last acc_full
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    const int B_AFULL = 0, B_AREADY = 2, B_AEMPTY = 4, B_WFULL = 6, B_WEMPTY = 6 + p.nws, B_ACC = 6 + 2 * p.nws;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACC + 1);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) { mbar_init(BAR(B_AFULL + i), 1); mbar_init(BAR(B_AREADY + i), 128); mbar_init(BAR(B_AEMPTY + i), 1); }
+        for (int i = 0; i < p.nws; i++) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
+        mbar_init(BAR(B_ACC), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int R = p.R, ncg = p.KC / 4;
+    // rows r of the staged tile map to t = t0 - pad + r; rows outside [0, T) are the conv's zero padding
+    const int r_lo = max(0, p.pad - t0);
+    const int r_hi = min(R, p.T - (t0 - p.pad));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer: activation chunk c+1 is requested before the weight tiles of chunk c
+            const uint32_t row_bytes = (uint32_t)(r_hi - r_lo) * 16u;
+            auto load_a = [&](int c) {
+                const int sa = c & 1;
+                mbar_wait(BAR(B_AEMPTY + sa), ((c >> 1) & 1) ^ 1);
+                mbar_expect_tx(BAR(B_AFULL + sa), row_bytes * ncg);
+                const float* src = p.x + (((size_t)b * (p.Cin / 4) + (size_t)c * ncg) * p.T + (t0 - p.pad + r_lo)) * 4;
+                uint32_t dst = smem_u32(sA + (size_t)sa * p.a_stage_bytes) + (uint32_t)r_lo * 16u;
+                for (int g = 0; g < ncg; g++) bulk_g2s(dst + (uint32_t)g * R * 16u, src + (size_t)g * p.T * 4, row_bytes, BAR(B_AFULL + sa));
+            };
+            load_a(0);
+            int wi = 0;
+            for (int c = 0; c < p.nchunks; c++) {
+                if (c + 1 < p.nchunks) load_a(c + 1);
+                for (int j = 0; j < p.K; j++, wi++) {
+                    const int sw = wi % p.nws;
+                    mbar_wait(BAR(B_WEMPTY + sw), ((wi / p.nws) & 1) ^ 1);
+                    mbar_expect_tx(BAR(B_WFULL + sw), p.w_stage_bytes);
+                    bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), p.w + ((size_t)c * p.K + j) * p.KC * p.N, p.w_stage_bytes,
+                             BAR(B_WFULL + sw));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer: K taps x KC/8 tcgen05.mma (M=128, N=Cout, K=8 tf32) per activation chunk
+            const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)p.N * 16u;
+            int wi = 0;
+            for (int c = 0; c < p.nchunks; c++) {
+                const int sa = c & 1;
+                mbar_wait(BAR(B_AREADY + sa), (c >> 1) & 1);
+                fence_after();
+                const uint32_t a_base = smem_u32(sA + (size_t)sa * p.a_stage_bytes);
+                for (int j = 0; j < p.K; j++, wi++) {
+                    const int sw = wi % p.nws;
+                    mbar_wait(BAR(B_WFULL + sw), (wi / p.nws) & 1);
+                    fence_after();
+                    const uint32_t w_base = smem_u32(sW + (size_t)sw * p.w_stage_bytes);
+                    for (int kk = 0; kk < p.KC / 8; kk++) {
+                        uint64_t ad = make_desc(a_base + ((uint32_t)(2 * kk) * R + (uint32_t)(j * p.dil)) * 16u, a_lbo, 128u);
+                        uint64_t bd = make_desc(w_base + (uint32_t)(2 * kk) * b_lbo, b_lbo, 128u);
+                        umma_tf32(tmem, ad, bd, p.idesc, (c | j | kk) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(BAR(B_WEMPTY + sw));
+                }
+                umma_commit(BAR(B_AEMPTY + sa));
+            }
+            umma_commit(BAR(B_ACC));
+        }
+    } else {
+        // ===== operand prologue on the staged tile (generic proxy), then hand over to the async proxy
+        const int tid2 = threadIdx.x - 64;
+        const float slope = p.in_slope;
+        for (int c = 0; c < p.nchunks; c++) {
+            const int sa = c & 1;
+            mbar_wait(BAR(B_AFULL + sa), (c >> 1) & 1);
+            float4* A = reinterpret_cast<float4*>(sA + (size_t)sa * p.a_stage_bytes);
+            for (int g = 0; g < ncg; g++) {
+                float4* Ag = A + (size_t)g * R;
+                for (int r = tid2; r < R; r += 128) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r >= r_lo && r < r_hi) {
+                        v = Ag[r];
+                        v.x = to_tf32(lrelu(v.x, slope)); v.y = to_tf32(lrelu(v.y, slope));
+                        v.z = to_tf32(lrelu(v.z, slope)); v.w = to_tf32(lrelu(v.w, slope));
+                    }
+                    Ag[r] = v;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(BAR(B_AREADY + sa));
+        }
+        // ===== epilogue: TMEM -> registers -> (+bias, +residual, MRF accumulate/scale) -> c4 global
+        mbar_wait(BAR(B_ACC), 0);
+        fence_after();
+        const int q = warp & 3;
+        const int t = t0 + q * 32 + lane;
+        const bool ok = t < p.T;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        const size_t cstride = (size_t)p.T;  // float4 stride between channel groups
+        float4* y4 = reinterpret_cast<float4*>(p.y) + (size_t)b * (p.N / 4) * p.T + t;
+        const float4* r4 = p.res ? reinterpret_cast<const float4*>(p.res) + (size_t)b * (p.N / 4) * p.T + t : nullptr;
+        for (int col = 0; col < p.N; col += 16) {
+            uint32_t v[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(trow + (uint32_t)col));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (ok) {
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const int cg = col / 4 + g;
+                    const float4 bz = *reinterpret_cast<const float4*>(p.bias + cg * 4);
+                    float4 o = make_float4(__uint_as_float(v[4 * g]) + bz.x, __uint_as_float(v[4 * g + 1]) + bz.y,
+                                           __uint_as_float(v[4 * g + 2]) + bz.z, __uint_as_float(v[4 * g + 3]) + bz.w);
+                    if (r4) { float4 r = r4[cg * cstride]; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+                    if (p.accumulate) { float4 a = y4[cg * cstride]; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+                    o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale;
+                    y4[cg * cstride] = o;
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const Act& y, int dil, const TcEpi& e, cudaStream_t st, int num_sms) {
+    (void)num_sms;
+    BV2_CHECK(w.w && x.C == w.Cin && y.C == w.Cout && x.T == y.T && x.B == y.B, "tc_conv1d shapes");
+    TcParams p{};
+    p.x = x.p; p.y = y.p; p.w = w.w; p.bias = bias; p.res = e.res;
+    p.Cin = w.Cin; p.N = w.Cout; p.T = x.T; p.B = x.B; p.K = w.K; p.dil = dil; p.pad = (w.K - 1) / 2 * dil;
+    p.KC = w.KC; p.nchunks = w.nchunks; p.R = 128 + (w.K - 1) * dil;
+    p.a_stage_bytes = (uint32_t)(p.KC * p.R * 4);
+    p.w_stage_bytes = (uint32_t)(p.KC * p.N * 4);
+    const uint32_t budget = 200 * 1024;
+    int nws = (int)((budget - 2 * p.a_stage_bytes - 512) / p.w_stage_bytes);
+    p.nws = std::max(2, std::min(nws, 8));
+    uint32_t cols = 32; while ((int)cols < p.N) cols <<= 1;
+    p.tmem_cols = cols;
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
+    p.in_slope = e.in_slope; p.out_scale = e.out_scale; p.accumulate = e.accumulate;
+    const size_t smem = 2 * (size_t)p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + (size_t)(7 + 2 * p.nws) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(cdiv(p.T, 128), p.B);
+    k_tc_conv1d<<<grid, 192, smem, st>>>(p);
+    BV2_CUDA(cudaGetLastError());
 }
 
 }  // namespace bv2

@@ -101,6 +101,12 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.bv2_launch_count(self._h))
 
+    def set_profiling(self, on: bool = True):
+        self._check(self.lib.bv2_set_profiling(self._h, int(on)))
+
+    def stage_ms(self, stage: str) -> float:
+        return float(self.lib.bv2_stage_ms(self._h, stage.encode()))
+
     # ---- whole path ---------------------------------------------------------------------------------
     def infer_begin(self, x, x_lengths, sid, tone, language, bert, ja_bert, en_bert, noise_w, noise_scale_w, length_scale,
                     sdp_ratio, w_ceil_override=None):

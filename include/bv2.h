@@ -102,6 +102,12 @@ int bv2_generator(bv2_engine* e, int B, int F, const float* z, const float* g, f
  * Returns the number of floats written, or a negative status.                                               */
 int64_t bv2_debug_read(bv2_engine* e, const char* name, float* host_out, int64_t capacity);
 
+/* Stage timing (CUDA events recorded on the caller's stream around "encoder_duration", "flow", "generator"):
+ * enable with bv2_set_profiling(e, 1); bv2_stage_ms blocks on the stage's end event and returns the duration of
+ * the stage in the LAST call, or a negative value if it was not recorded. */
+int bv2_set_profiling(bv2_engine* e, int enable);
+float bv2_stage_ms(bv2_engine* e, const char* stage);
+
 /* Counters: kernels launched by the engine since creation / bytes of workspace in use. */
 int64_t bv2_launch_count(const bv2_engine* e);
 int64_t bv2_workspace_bytes(const bv2_engine* e);

@@ -1,0 +1,113 @@
+// Standalone hardware probe for the tcgen05 implicit-GEMM conv (bert_vits2_b200/csrc/tc_conv.cuh):
+// validates the smem-descriptor scheme (tap = start-address shift) against a CPU conv on TF32-rounded operands.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tests/cuda/tc_probe tests/cuda/tc_probe.cu
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+#include "../../bert_vits2_b200/csrc/tc_conv.cuh"
+
+using namespace bv2;
+
+static std::vector<void*> g_allocs;
+static float* up(const std::vector<float>& v) {
+    void* p; cudaMalloc(&p, v.size() * 4); cudaMemcpy(p, v.data(), v.size() * 4, cudaMemcpyHostToDevice); g_allocs.push_back(p);
+    return (float*)p;
+}
+
+static int run_case(int Cin, int Cout, int K, int dil, int T, int B, float slope, bool res, bool acc, float scale, int iters) {
+    std::mt19937 rng(Cin * 131 + Cout * 17 + K * 7 + dil + T);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    std::vector<float> x((size_t)B * Cin * T), w((size_t)Cout * Cin * K), bias(Cout), r((size_t)B * Cout * T), y0((size_t)B * Cout * T);
+    for (auto& v : x) v = nd(rng);
+    for (auto& v : w) v = nd(rng) / std::sqrt((float)(Cin * K));
+    for (auto& v : bias) v = nd(rng);
+    for (auto& v : r) v = nd(rng);
+    for (auto& v : y0) v = nd(rng);
+    // c4 layouts
+    auto to_c4 = [&](const std::vector<float>& s, int C) {
+        std::vector<float> d(s.size());
+        for (int b = 0; b < B; b++) for (int c = 0; c < C; c++) for (int t = 0; t < T; t++)
+            d[(((size_t)b * (C / 4) + c / 4) * T + t) * 4 + (c & 3)] = s[((size_t)b * C + c) * T + t];
+        return d;
+    };
+    std::function<float*(const std::vector<float>&)> upf = up;
+    TcConvW tw = tc_pack_weights(upf, w, Cout, Cin, K);
+    Act ax; ax.B = B; ax.C = Cin; ax.T = T; ax.p = up(to_c4(x, Cin));
+    Act ay; ay.B = B; ay.C = Cout; ay.T = T; ay.p = up(to_c4(y0, Cout));
+    float* dres = up(to_c4(r, Cout));
+    float* dbias = up(bias);
+    TcEpi e; e.in_slope = slope; e.res = res ? dres : nullptr; e.accumulate = acc; e.out_scale = scale;
+    tc_conv1d(tw, dbias, ax, ay, dil, e, 0, 148);
+    cudaError_t er = cudaDeviceSynchronize();
+    if (er != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(er)); return 1; }
+    std::vector<float> got((size_t)B * Cout * T);
+    cudaMemcpy(got.data(), ay.p, got.size() * 4, cudaMemcpyDeviceToHost);
+    // CPU reference on tf32-rounded operands
+    const int pad = (K - 1) / 2 * dil;
+    double maxerr = 0, maxref = 0;
+    std::vector<float> xa(x.size());
+    for (size_t i = 0; i < x.size(); i++) { float v = x[i]; v = v > 0 ? v : v * slope; xa[i] = tf32_rn_host(v); }
+    std::vector<float> wr(w.size());
+    for (size_t i = 0; i < w.size(); i++) wr[i] = tf32_rn_host(w[i]);
+    for (int b = 0; b < B; b++)
+        for (int co = 0; co < Cout; co++)
+            for (int t = 0; t < T; t += (T > 400 ? 7 : 1)) {
+                double s = bias[co];
+                for (int ci = 0; ci < Cin; ci++)
+                    for (int j = 0; j < K; j++) {
+                        int tt = t + j * dil - pad;
+                        if (tt >= 0 && tt < T) s += (double)xa[((size_t)b * Cin + ci) * T + tt] * wr[((size_t)co * Cin + ci) * K + j];
+                    }
+                if (res) s += r[((size_t)b * Cout + co) * T + t];
+                if (acc) s += y0[((size_t)b * Cout + co) * T + t];
+                s *= scale;
+                double g = got[(((size_t)b * (Cout / 4) + co / 4) * T + t) * 4 + (co & 3)];
+                maxerr = std::max(maxerr, std::fabs(g - s)); maxref = std::max(maxref, std::fabs(s));
+            }
+    float ms = 0;
+    if (iters > 0) {
+        cudaEvent_t a, c; cudaEventCreate(&a); cudaEventCreate(&c);
+        e.accumulate = 0;
+        for (int i = 0; i < 3; i++) tc_conv1d(tw, dbias, ax, ay, dil, e, 0, 148);
+        cudaEventRecord(a);
+        for (int i = 0; i < iters; i++) tc_conv1d(tw, dbias, ax, ay, dil, e, 0, 148);
+        cudaEventRecord(c); cudaEventSynchronize(c); cudaEventElapsedTime(&ms, a, c); ms /= iters;
+    }
+    double flop = 2.0 * B * T * (double)Cin * Cout * K;
+    double bytes = 4.0 * B * T * (Cin + Cout * (1 + (res ? 1 : 0)));
+    bool ok = maxerr < 2e-3 * std::max(1.0, maxref);
+    printf("%s Cin=%3d Cout=%3d K=%2d dil=%d T=%6d B=%d slope=%.2f res=%d acc=%d : maxerr %.3e (ref max %.2f)", ok ? "PASS" : "FAIL", Cin, Cout, K,
+           dil, T, B, slope, (int)res, (int)acc, maxerr, maxref);
+    if (iters > 0) printf("  | %.3f ms  %.1f TFLOP/s  %.0f GB/s", ms, flop / ms * 1e-9, bytes / ms * 1e-6);
+    printf("\n");
+    fflush(stdout);
+    return ok ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+    int fails = 0;
+    bool perf = argc > 1;
+    try {
+        // functional: K=1 first (no tap shift), then taps with shifts not multiple of 8 rows
+        fails += run_case(16, 16, 1, 1, 300, 1, 1.f, false, false, 1.f, 0);
+        fails += run_case(64, 64, 1, 1, 300, 2, 1.f, false, false, 1.f, 0);
+        fails += run_case(16, 16, 3, 1, 300, 1, 0.1f, false, false, 1.f, 0);
+        fails += run_case(32, 32, 7, 3, 1000, 2, 0.1f, true, false, 1.f, 0);
+        fails += run_case(64, 64, 11, 5, 700, 1, 0.1f, true, true, 1.f / 3, 0);
+        fails += run_case(128, 128, 3, 1, 256, 1, 0.1f, false, false, 1.f, 0);
+        fails += run_case(256, 256, 11, 5, 500, 1, 0.1f, true, false, 1.f, 0);
+        fails += run_case(256, 256, 7, 1, 128, 3, 0.1f, false, true, 1.f, 0);
+        fails += run_case(192, 192, 5, 1, 333, 1, 1.f, false, false, 1.f, 0);
+        if (perf) {
+            // Generator MRF shapes at F=1024 frames
+            int F = 1024;
+            int Cs[5] = {256, 128, 64, 32, 16}; int Ls[5] = {8, 64, 128, 256, 512};
+            for (int s = 0; s < 5; s++)
+                for (int k : {3, 7, 11})
+                    for (int d : {1, 5}) fails += run_case(Cs[s], Cs[s], k, d, Ls[s] * F, 1, 0.1f, true, false, 1.f, 10);
+        }
+    } catch (const std::exception& ex) { printf("exception: %s\n", ex.what()); return 2; }
+    printf("%s (%d failing)\n", fails ? "PROBE FAILED" : "PROBE OK", fails);
+    return fails ? 1 : 0;
+}
