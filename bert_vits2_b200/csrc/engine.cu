@@ -36,7 +36,7 @@ struct CouplingW {
     std::vector<ConvW> wn_in, wn_res, wn_skip; int wn_g_off = 0;  // WN flow
 };
 struct ResBlockW { std::vector<ConvW> c1, c2; int k = 3; std::vector<int> dil; };
-struct UpW { float* w = nullptr; float* b = nullptr; int Cin = 0, Cout = 0, K = 0, u = 0; };
+struct UpW { float* w = nullptr; float* b = nullptr; int Cin = 0, Cout = 0, K = 0, u = 0; TcConvW tc; };
 
 struct DebugBuf { const float* p; int B, C, T; int c4; };
 
@@ -188,7 +188,7 @@ struct bv2_engine {
         LnW l; l.C = (int)W(name + ".gamma").numel(); l.g = upload(W(name + ".gamma").data); l.b = upload(W(name + ".beta").data);
         return l;
     }
-    EncoderW encoder_from(const std::string& name, int n_layers, int kernel, std::vector<float>& gw, std::vector<float>& gb) {
+    EncoderW encoder_from(const std::string& name, int n_layers, int kernel, std::vector<float>& gw, std::vector<float>& gb, int tc_mode = 0) {
         EncoderW e; e.kernel = kernel;
         const int H = cfg.hidden_channels, dk = H / cfg.n_heads;
         e.g_off = append_gproj(name + ".spk_emb_linear", gw, gb);
@@ -206,13 +206,13 @@ struct bv2_engine {
                 for (int i2 = 0; i2 < H * H; i2++) w[(size_t)p * H * H + i2] = wt.data[i2] * s;
                 for (int i2 = 0; i2 < H; i2++) b[p * H + i2] = bt.data[i2] * s;
             }
-            L.qkv = make_conv(w, 3 * H, H, 1, &b);
-            L.o = conv_from(a + ".conv_o");
+            L.qkv = make_conv(w, 3 * H, H, 1, &b, tc_mode);
+            L.o = conv_from(a + ".conv_o", false, tc_mode);
             L.relk = upload(W(a + ".emb_rel_k").data);
             L.relv = upload(W(a + ".emb_rel_v").data);
             L.n1 = ln_from(name + ".norm_layers_1." + std::to_string(i));
-            L.f1 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_1");
-            L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2");
+            L.f1 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_1", false, tc_mode);
+            L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2", false, tc_mode);
             L.n2 = ln_from(name + ".norm_layers_2." + std::to_string(i));
             e.layers.push_back(L);
         }
@@ -245,7 +245,18 @@ struct bv2_engine {
 
     // ---------------------------------------------------------------- launch helpers
     void conv(const ConvW& cw, const Act& x, const Act& y, cudaStream_t s, ConvArgs extra = ConvArgs(), int cin_off = 0,
-              int cout_off = 0) {
+              int cout_off = 0, bool allow_tc = false) {
+        if (allow_tc && cw.tc.w) {
+            TcEpi e;
+            e.in_slope = extra.in_slope; e.in_mask = extra.in_mask; e.relu = extra.act == 1; e.res_mode = extra.res_mode; e.res = extra.res;
+            e.res_C_total = extra.res_C_total; e.res_c_off = extra.res_c_off; e.accumulate = extra.accumulate; e.out_scale = extra.out_scale;
+            e.out_mask = extra.out_mask; e.lens = extra.lens; e.bias_b = extra.bias_b; e.bias_b_stride = extra.bias_b_stride;
+            e.cin_off = cin_off; e.cout_off = cout_off; e.dil = extra.dil ? extra.dil : 1;
+            BV2_CHECK(x.T == y.T && x.B == y.B, "conv T/B mismatch");
+            tc_conv1d(cw.tc, cw.b, x, y, e, s, num_sms);
+            launches++;
+            return;
+        }
         ConvArgs a = extra;
         a.x = x.p; a.Cin_total = x.C; a.cin_off = cin_off; a.Cin = cw.Cin;
         a.w = cw.w; a.Cout_w = cw.Cout_w; a.bias = cw.b;
@@ -376,31 +387,31 @@ void bv2_engine::finalize() {
                 b2[co] = qb.data[half - 1 - co];
             }
         }
-        fl.pre = make_conv(w1, H, half, 1, &pb.data);
-        fl.post = make_conv(w2, half, H, 1, &b2);
+        fl.pre = make_conv(w1, H, half, 1, &pb.data, tc);
+        fl.post = make_conv(w2, half, H, 1, &b2, tc);
         if (c.use_transformer_flow) {
-            fl.enc = encoder_from(f + ".enc", c.n_layers_trans_flow, c.flow_kernel_size, gw, gb);
+            fl.enc = encoder_from(f + ".enc", c.n_layers_trans_flow, c.flow_kernel_size, gw, gb, tc);
         } else {
             const int L = c.wn_layers;
             fl.wn_g_off = append_gproj(f + ".enc.cond_layer", gw, gb, true);
             for (int l = 0; l < L; l++) {
-                fl.wn_in.push_back(conv_from(f + ".enc.in_layers." + std::to_string(l), true));
+                fl.wn_in.push_back(conv_from(f + ".enc.in_layers." + std::to_string(l), true, tc));
                 std::vector<int64_t> shp;
                 std::vector<float> w = fold_wn(f + ".enc.res_skip_layers." + std::to_string(l), &shp);
                 const auto& b = W(f + ".enc.res_skip_layers." + std::to_string(l) + ".bias").data;
                 if (l < L - 1) {
                     std::vector<float> wr(w.begin(), w.begin() + (size_t)H * H), ws(w.begin() + (size_t)H * H, w.end());
                     std::vector<float> br(b.begin(), b.begin() + H), bs(b.begin() + H, b.end());
-                    fl.wn_res.push_back(make_conv(wr, H, H, 1, &br));
-                    fl.wn_skip.push_back(make_conv(ws, H, H, 1, &bs));
+                    fl.wn_res.push_back(make_conv(wr, H, H, 1, &br, tc));
+                    fl.wn_skip.push_back(make_conv(ws, H, H, 1, &bs, tc));
                 } else {
-                    fl.wn_skip.push_back(make_conv(w, H, H, 1, &b));
+                    fl.wn_skip.push_back(make_conv(w, H, H, 1, &b, tc));
                 }
             }
         }
     }
     // ---- dec (reference models.py:490-564)
-    conv_pre = conv_from("dec.conv_pre");
+    conv_pre = conv_from("dec.conv_pre", false, tc);
     goff_dec = append_gproj("dec.cond", gw, gb);
     int ch = c.upsample_initial_channel;
     for (int i = 0; i < c.n_ups; i++) {
@@ -413,6 +424,7 @@ void bv2_engine::finalize() {
             for (int co = 0; co < u.Cout; co++)
                 for (int j = 0; j < u.K; j++) p[((size_t)ci * u.K + j) * u.Cout + co] = w[((size_t)ci * u.Cout + co) * u.K + j];
         u.w = upload(p); u.b = upload(W("dec.ups." + std::to_string(i) + ".bias").data);
+        if (tc) u.tc = tc_pack_upsample(*this_uploader(), w, u.Cin, u.Cout, u.K, u.u);
         ups.push_back(u);
         ch /= 2;
         for (int j = 0; j < c.n_resblock_kernels; j++) {
@@ -449,21 +461,20 @@ void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const fl
             k_add_bvec_mask<<<grid_tcb(T, H, B), 128, 0, s>>>(x.p, gproj + E.g_off, gproj_n, H, T, lens);
             BV2_CUDA(cudaGetLastError()); launches++;
         }
-        conv(L.qkv, x, qkv, s);
+        conv(L.qkv, x, qkv, s, ConvArgs(), 0, 0, tc);
         {
             dim3 grid(cdiv(T, 16), nh, B);
             k_attention_rel<96><<<grid, 128, 0, s>>>(qkv.p, L.relk, L.relv, att.p, H, T, lens, cfg.window_size);
             BV2_CUDA(cudaGetLastError()); launches++;
         }
-        conv(L.o, att, y, s);
+        conv(L.o, att, y, s, ConvArgs(), 0, 0, tc);
         layernorm(L.n1, x, y.p, x, s, 0, nullptr, lens, 0);
         ConvArgs a1; a1.in_mask = 1; a1.act = 1; a1.lens = lens;
-        conv(L.f1, x, f, s, a1);
+        conv(L.f1, x, f, s, a1, 0, 0, tc);
         ConvArgs a2; a2.in_mask = 1; a2.out_mask = 1; a2.lens = lens;
-        conv(L.f2, f, y, s, a2);
+        conv(L.f2, f, y, s, a2, 0, 0, tc);
         layernorm(L.n2, x, y.p, x, s, 0, nullptr, lens, i == nl - 1 ? 1 : 0);
     }
-    (void)tc;
     ws.release(mark);
 }
 
@@ -559,13 +570,14 @@ void bv2_engine::run_durations(Act h, const int* lens, const float* gproj, const
 // {Transformer,Residual}CouplingBlock reverse (reference models.py:142-145, 442-445; modules.py:437-456, 561-580)
 void bv2_engine::run_flow(Act z, const int* lens, const float* gproj, cudaStream_t s) {
     const int B = z.B, F = z.T, H = cfg.hidden_channels, half = cfg.inter_channels / 2;
+    const bool tcf = cfg.generator_precision != 0;
     const size_t mark = ws.used();
     Act h = ws.act(B, H, F);
     for (int i = cfg.n_flow_layer - 1; i >= 0; i--) {
         CouplingW& fl = flows[i];
         const int in_off = fl.s ? half : 0, out_off = fl.s ? 0 : half;
         ConvArgs a; a.out_mask = 1; a.lens = lens;
-        conv(fl.pre, z, h, s, a, in_off, 0);
+        conv(fl.pre, z, h, s, a, in_off, 0, tcf);
         Act m_in = h;
         if (cfg.use_transformer_flow) {
             run_encoder(fl.enc, h, lens, gproj, s, cfg.generator_precision != 0);
@@ -573,21 +585,21 @@ void bv2_engine::run_flow(Act z, const int* lens, const float* gproj, cudaStream
             const int L = cfg.wn_layers;
             Act xin = ws.act(B, 2 * H, F), acts = ws.act(B, H, F), out = ws.act(B, H, F);
             for (int l = 0; l < L; l++) {
-                conv(fl.wn_in[l], h, xin, s);
+                conv(fl.wn_in[l], h, xin, s, ConvArgs(), 0, 0, tcf);
                 k_wn_gate<<<grid_tcb(F, H, B), 128, 0, s>>>(xin.p, gproj + fl.wn_g_off + 2 * H * l, gproj_n, acts.p, H, F);
                 BV2_CUDA(cudaGetLastError()); launches++;
                 if (l < L - 1) {
                     ConvArgs ar; ar.res_mode = 1; ar.res = h.p; ar.res_C_total = H; ar.out_mask = 1; ar.lens = lens;
-                    conv(fl.wn_res[l], acts, h, s, ar);
+                    conv(fl.wn_res[l], acts, h, s, ar, 0, 0, tcf);
                 }
                 ConvArgs as; as.accumulate = l > 0 ? 1 : 0;
-                conv(fl.wn_skip[l], acts, out, s, as);
+                conv(fl.wn_skip[l], acts, out, s, as, 0, 0, tcf);
             }
             m_in = out;
         }
         ConvArgs p; p.in_mask = cfg.use_transformer_flow ? 0 : 1; p.res_mode = 2; p.res = z.p; p.res_C_total = z.C; p.res_c_off = out_off;
         p.out_mask = 1; p.lens = lens;
-        conv(fl.post, m_in, z, s, p, 0, out_off);
+        conv(fl.post, m_in, z, s, p, 0, out_off, tcf);
     }
     if (cfg.n_flow_layer % 2 == 1) {
         Act t = ws.act(B, z.C, F);
@@ -605,9 +617,9 @@ void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_
     Act x = ws.act(B, ch, L);
     ConvArgs a; a.bias_b = gdec; a.bias_b_stride = g_stride;
     if (lens) { a.in_mask = 1; a.lens = lens; }
-    conv(conv_pre, z, x, s, a);
-    const int nk = cfg.n_resblock_kernels, nd = cfg.n_dilations;
     const bool tc = cfg.generator_precision != 0;
+    conv(conv_pre, z, x, s, a, 0, 0, tc);
+    const int nk = cfg.n_resblock_kernels, nd = cfg.n_dilations;
     for (int i = 0; i < cfg.n_ups; i++) {
         const UpW& u = ups[i];
         const int Lo = L * u.u;
@@ -615,9 +627,14 @@ void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_
             S = ws.act(B, u.Cout, Lo);
         ConvTArgs t; t.x = x.p; t.Cin = u.Cin; t.Tin = L; t.w = u.w; t.bias = u.b; t.y = xu.p; t.Cout = u.Cout; t.Tout = Lo;
         t.K = u.K; t.u = u.u; t.p = (u.K - u.u) / 2; t.B = B; t.in_slope = 0.1f;
-        dim3 grid(cdiv(Lo, 128), cdiv(u.Cout, 64), B);
-        k_convT_c4<<<grid, 256, 0, s>>>(t);
-        BV2_CUDA(cudaGetLastError()); launches++;
+        if (tc) {
+            TcEpi eu; eu.in_slope = 0.1f;
+            tc_conv1d(u.tc, u.b, x, xu, eu, s, num_sms); launches++;
+        } else {
+            dim3 grid(cdiv(Lo, 128), cdiv(u.Cout, 64), B);
+            k_convT_c4<<<grid, 256, 0, s>>>(t);
+            BV2_CUDA(cudaGetLastError()); launches++;
+        }
         for (int j = 0; j < nk; j++) {
             const ResBlockW& R = resblocks[i * nk + j];
             Act cur = xu;
@@ -625,11 +642,11 @@ void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_
                 const bool last = d == nd - 1;
                 Act nxt = last ? S : (cur.p == ra.p ? rb : ra);
                 if (tc) {
-                    TcEpi e1; e1.in_slope = 0.1f;
-                    tc_conv1d(R.c1[d].tc, R.c1[d].b, cur, xt, R.dil[d], e1, s, num_sms); launches++;
-                    TcEpi e2; e2.in_slope = 0.1f; e2.res = cur.p;
+                    TcEpi e1; e1.in_slope = 0.1f; e1.dil = R.dil[d];
+                    tc_conv1d(R.c1[d].tc, R.c1[d].b, cur, xt, e1, s, num_sms); launches++;
+                    TcEpi e2; e2.in_slope = 0.1f; e2.res = cur.p; e2.res_mode = 1;
                     if (last) { e2.accumulate = j > 0; e2.out_scale = (j == nk - 1) ? 1.f / nk : 1.f; }
-                    tc_conv1d(R.c2[d].tc, R.c2[d].b, xt, nxt, 1, e2, s, num_sms); launches++;
+                    tc_conv1d(R.c2[d].tc, R.c2[d].b, xt, nxt, e2, s, num_sms); launches++;
                 } else {
                     ConvArgs c1; c1.in_slope = 0.1f; c1.dil = R.dil[d];
                     conv(R.c1[d], cur, xt, s, c1);

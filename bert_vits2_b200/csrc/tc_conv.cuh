@@ -24,12 +24,24 @@ namespace bv2 {
 struct TcConvW {
     float* w = nullptr;  // packed [nchunks][K][KC/4][Cout][4], TF32-rounded (RN)
     int Cin = 0, Cout = 0, K = 0, KC = 0, nchunks = 0;
+    int ups_u = 0, ups_cout = 0;  // polyphase ConvTranspose1d: Cout = ups_u * ups_cout columns (phase-major)
 };
 struct TcEpi {
     float in_slope = 1.f;        // leaky-relu slope applied to the conv INPUT (1 = identity)
-    const float* res = nullptr;  // residual, c4 [B][Cout/4][T][4]
-    int accumulate = 0;          // y = (y_old + v) * out_scale
+    int in_mask = 0;             // input rows t >= lens[b] read as zero
+    int relu = 0;
+    int res_mode = 0;            // 1: v += res ; 2: v = res - v
+    const float* res = nullptr;  // residual, c4, res_C_total channels, first channel res_c_off
+    int res_C_total = 0, res_c_off = 0;
+    int accumulate = 0;          // v += y_old
     float out_scale = 1.f;
+    int out_mask = 0;            // v *= (t < lens[b])
+    const int* lens = nullptr;
+    const float* bias_b = nullptr;  // per-batch bias row (speaker conditioning)
+    int bias_b_stride = 0;
+    int cin_off = 0, cout_off = 0;  // channel windows inside x / y (multiples of 4)
+    int dil = 1;
+    int ntile = 0;               // N tile (0 = auto)
 };
 
 inline float tf32_rn_host(float x) {
@@ -44,7 +56,7 @@ inline float tf32_rn_host(float x) {
 inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>& up, const std::vector<float>& w, int Cout, int Cin, int K) {
     TcConvW t; t.Cin = Cin; t.Cout = Cout; t.K = K;
     t.KC = Cin >= 32 ? 32 : Cin;
-    if (Cin % t.KC != 0 || t.KC % 8 != 0 || Cout % 16 != 0 || Cout > 256 || Cout < 16)
+    if (Cin % t.KC != 0 || t.KC % 8 != 0 || Cout % 16 != 0 || Cout < 16)
         throw Error(-2, "tc_conv: unsupported channel counts " + std::to_string(Cin) + "->" + std::to_string(Cout));
     t.nchunks = Cin / t.KC;
     std::vector<float> p((size_t)Cin * K * Cout);
@@ -61,11 +73,39 @@ inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>&
     return t;
 }
 
+// ConvTranspose1d(Cin->Cout, K, stride u, padding (K-u)/2) as a polyphase stride-1 conv (reference models.py:543-545):
+//   out[t*u + r][co] = sum_m sum_ci x[t + floor((r+p)/u) - m][ci] * w[ci][co][(r+p)%u + m*u]
+// -> an ordinary conv over input-rate time with Kp taps (union of the per-phase offsets), N = u*Cout columns ordered
+// (r, co), structural zeros where a phase does not use a tap.  wT: [Cin][Cout][K] (weight-norm folded).
+inline TcConvW tc_pack_upsample(std::function<float*(const std::vector<float>&)>& up, const std::vector<float>& wT, int Cin, int Cout, int K, int u) {
+    const int p = (K - u) / 2, taps = K / u;
+    int omin = 1 << 30, omax = -(1 << 30);
+    for (int r = 0; r < u; r++)
+        for (int m = 0; m < taps; m++) { int o = (r + p) / u - m; omin = std::min(omin, o); omax = std::max(omax, o); }
+    int half = std::max(-omin, omax);
+    const int Kp = 2 * half + 1;  // symmetric so that pad = (Kp-1)/2
+    std::vector<float> w((size_t)u * Cout * Cin * Kp, 0.f);  // [N = u*Cout][Cin][Kp]
+    for (int r = 0; r < u; r++)
+        for (int m = 0; m < taps; m++) {
+            const int o = (r + p) / u - m, j = (r + p) % u + m * u, tap = o + half;
+            for (int co = 0; co < Cout; co++)
+                for (int ci = 0; ci < Cin; ci++)
+                    w[(((size_t)(r * Cout + co)) * Cin + ci) * Kp + tap] = wT[((size_t)ci * Cout + co) * K + j];
+        }
+    TcConvW t = tc_pack_weights(up, w, u * Cout, Cin, Kp);
+    t.ups_u = u; t.ups_cout = Cout;
+    return t;
+}
+
 struct TcParams {
-    const float* x; float* y; const float* w; const float* bias; const float* res;
-    int Cin, N, T, B, K, dil, pad, KC, nchunks, R, nws;
+    const float* x; float* y; const float* w; const float* bias; const float* res; const float* bias_b; const int* lens;
+    int Cin_total, cin_off, Cout_total, cout_off, res_C_total, res_c_off, bias_b_stride;
+    int Ncols_total;  // packed weight row length (all N tiles)
+    int nt;           // columns of this launch's N tile
+    int T, B, K, dil, pad, KC, nchunks, R, nws, MT;
     uint32_t a_stage_bytes, w_stage_bytes, tmem_cols, idesc;
-    float in_slope, out_scale; int accumulate;
+    float in_slope, out_scale;
+    int accumulate, relu, res_mode, in_mask, out_mask, ups_u, ups_cout;
 };
 
 namespace tc {
@@ -86,7 +126,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             long long now = clock64();
             if (t0 == 0) t0 = now;
             else if (now - t0 > 4000000000ll) {  // ~2 s
-                printf("bv2 tc_conv: mbarrier wait timeout (block %d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
+                printf("bv2 tc_conv: mbarrier wait timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+                       threadIdx.x, bar, parity);
                 __trap();
             }
         }
@@ -124,11 +165,14 @@ __device__ __forceinline__ float to_tf32(float x) {
 
 }  // namespace tc
 
+// grid: (M blocks of MT*128 time steps, N tiles, B)
 __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t0 = blockIdx.x * 128, b = blockIdx.y;
+    const int MT = p.MT;
+    const int t0 = blockIdx.x * 128 * MT, n0 = blockIdx.y * p.nt, b = blockIdx.z;
+    const int nt = p.nt;
     uint8_t* sA = smem;
     uint8_t* sW = smem + 2 * p.a_stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)p.nws * p.w_stage_bytes);
@@ -154,9 +198,11 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
     const uint32_t tmem = *tmem_slot;
 
     const int R = p.R, ncg = p.KC / 4;
+    const int len = p.lens ? p.lens[b] : p.T;
     // rows r of the staged tile map to t = t0 - pad + r; rows outside [0, T) are the conv's zero padding
     const int r_lo = max(0, p.pad - t0);
     const int r_hi = min(R, p.T - (t0 - p.pad));
+    const int r_mask_hi = p.in_mask ? min(r_hi, len - (t0 - p.pad)) : r_hi;  // rows >= this read as zero (x * x_mask)
 
     if (warp == 0) {
         if (lane == 0) {
@@ -166,27 +212,30 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
                 const int sa = c & 1;
                 mbar_wait(BAR(B_AEMPTY + sa), ((c >> 1) & 1) ^ 1);
                 mbar_expect_tx(BAR(B_AFULL + sa), row_bytes * ncg);
-                const float* src = p.x + (((size_t)b * (p.Cin / 4) + (size_t)c * ncg) * p.T + (t0 - p.pad + r_lo)) * 4;
+                const float* src = p.x + (((size_t)b * (p.Cin_total / 4) + p.cin_off / 4 + (size_t)c * ncg) * p.T + (t0 - p.pad + r_lo)) * 4;
                 uint32_t dst = smem_u32(sA + (size_t)sa * p.a_stage_bytes) + (uint32_t)r_lo * 16u;
                 for (int g = 0; g < ncg; g++) bulk_g2s(dst + (uint32_t)g * R * 16u, src + (size_t)g * p.T * 4, row_bytes, BAR(B_AFULL + sa));
             };
             load_a(0);
             int wi = 0;
+            const uint32_t wrow = (uint32_t)nt * 16u;
             for (int c = 0; c < p.nchunks; c++) {
                 if (c + 1 < p.nchunks) load_a(c + 1);
                 for (int j = 0; j < p.K; j++, wi++) {
                     const int sw = wi % p.nws;
                     mbar_wait(BAR(B_WEMPTY + sw), ((wi / p.nws) & 1) ^ 1);
                     mbar_expect_tx(BAR(B_WFULL + sw), p.w_stage_bytes);
-                    bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), p.w + ((size_t)c * p.K + j) * p.KC * p.N, p.w_stage_bytes,
-                             BAR(B_WFULL + sw));
+                    const float* src = p.w + (((size_t)c * p.K + j) * ncg * p.Ncols_total + n0) * 4;
+                    const uint32_t dst = smem_u32(sW + (size_t)sw * p.w_stage_bytes);
+                    for (int g = 0; g < ncg; g++) bulk_g2s(dst + (uint32_t)g * wrow, src + (size_t)g * p.Ncols_total * 4, wrow, BAR(B_WFULL + sw));
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // ===== MMA issuer: K taps x KC/8 tcgen05.mma (M=128, N=Cout, K=8 tf32) per activation chunk
-            const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)p.N * 16u;
+            // ===== MMA issuer: per weight tile, MT x KC/8 tcgen05.mma (M=128, N=nt, K=8 tf32); the MT accumulators
+            // (TMEM column blocks) share the weight tile, dividing its L2->smem traffic per FLOP by MT
+            const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)nt * 16u;
             int wi = 0;
             for (int c = 0; c < p.nchunks; c++) {
                 const int sa = c & 1;
@@ -198,10 +247,12 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
                     mbar_wait(BAR(B_WFULL + sw), (wi / p.nws) & 1);
                     fence_after();
                     const uint32_t w_base = smem_u32(sW + (size_t)sw * p.w_stage_bytes);
-                    for (int kk = 0; kk < p.KC / 8; kk++) {
-                        uint64_t ad = make_desc(a_base + ((uint32_t)(2 * kk) * R + (uint32_t)(j * p.dil)) * 16u, a_lbo, 128u);
-                        uint64_t bd = make_desc(w_base + (uint32_t)(2 * kk) * b_lbo, b_lbo, 128u);
-                        umma_tf32(tmem, ad, bd, p.idesc, (c | j | kk) != 0 ? 1u : 0u);
+                    for (int mt = 0; mt < MT; mt++) {
+                        for (int kk = 0; kk < p.KC / 8; kk++) {
+                            uint64_t ad = make_desc(a_base + ((uint32_t)(2 * kk) * R + (uint32_t)(mt * 128 + j * p.dil)) * 16u, a_lbo, 128u);
+                            uint64_t bd = make_desc(w_base + (uint32_t)(2 * kk) * b_lbo, b_lbo, 128u);
+                            umma_tf32(tmem + (uint32_t)(mt * nt), ad, bd, p.idesc, (c | j | kk) != 0 ? 1u : 0u);
+                        }
                     }
                     umma_commit(BAR(B_WEMPTY + sw));
                 }
@@ -221,7 +272,7 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
                 float4* Ag = A + (size_t)g * R;
                 for (int r = tid2; r < R; r += 128) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r >= r_lo && r < r_hi) {
+                    if (r >= r_lo && r < r_mask_hi) {
                         v = Ag[r];
                         v.x = to_tf32(lrelu(v.x, slope)); v.y = to_tf32(lrelu(v.y, slope));
                         v.z = to_tf32(lrelu(v.z, slope)); v.w = to_tf32(lrelu(v.w, slope));
@@ -232,34 +283,48 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(BAR(B_AREADY + sa));
         }
-        // ===== epilogue: TMEM -> registers -> (+bias, +residual, MRF accumulate/scale) -> c4 global
+        // ===== epilogue: TMEM -> registers -> fused pointwise tail -> c4 global (16-byte stores, coalesced across a warp)
         mbar_wait(BAR(B_ACC), 0);
         fence_after();
         const int q = warp & 3;
-        const int t = t0 + q * 32 + lane;
-        const bool ok = t < p.T;
-        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-        const size_t cstride = (size_t)p.T;  // float4 stride between channel groups
-        float4* y4 = reinterpret_cast<float4*>(p.y) + (size_t)b * (p.N / 4) * p.T + t;
-        const float4* r4 = p.res ? reinterpret_cast<const float4*>(p.res) + (size_t)b * (p.N / 4) * p.T + t : nullptr;
-        for (int col = 0; col < p.N; col += 16) {
-            uint32_t v[16];
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                         : "r"(trow + (uint32_t)col));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (ok) {
+        const size_t cstride = (size_t)p.T;
+        for (int mt = 0; mt < MT; mt++) {
+            const int t = t0 + mt * 128 + q * 32 + lane;
+            const bool ok = t < p.T;
+            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt);
+            const float msk = (p.out_mask && t >= len) ? 0.f : 1.f;
+            for (int col = 0; col < nt; col += 16) {
+                uint32_t v[16];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                               "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(trow + (uint32_t)col));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (!ok) continue;
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    const int cg = col / 4 + g;
-                    const float4 bz = *reinterpret_cast<const float4*>(p.bias + cg * 4);
+                    const int n = n0 + col + 4 * g;  // global output column of this 4-channel group
+                    int co = n, tt = t;
+                    size_t tstride = cstride;
+                    if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; tstride = cstride * p.ups_u; }
+                    const float4 bz = *reinterpret_cast<const float4*>(p.bias + co);
                     float4 o = make_float4(__uint_as_float(v[4 * g]) + bz.x, __uint_as_float(v[4 * g + 1]) + bz.y,
                                            __uint_as_float(v[4 * g + 2]) + bz.z, __uint_as_float(v[4 * g + 3]) + bz.w);
-                    if (r4) { float4 r = r4[cg * cstride]; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
-                    if (p.accumulate) { float4 a = y4[cg * cstride]; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
-                    o.x *= p.out_scale; o.y *= p.out_scale; o.z *= p.out_scale; o.w *= p.out_scale;
-                    y4[cg * cstride] = o;
+                    if (p.bias_b) {
+                        const float4 b2 = *reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + co);
+                        o.x += b2.x; o.y += b2.y; o.z += b2.z; o.w += b2.w;
+                    }
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (p.res_mode) {
+                        const float4 r = reinterpret_cast<const float4*>(p.res)[((size_t)b * (p.res_C_total / 4) + (p.res_c_off + co) / 4) * tstride + tt];
+                        if (p.res_mode == 1) { o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+                        else { o.x = r.x - o.x; o.y = r.y - o.y; o.z = r.z - o.z; o.w = r.w - o.w; }
+                    }
+                    float4* yp = reinterpret_cast<float4*>(p.y) + ((size_t)b * (p.Cout_total / 4) + (p.cout_off + co) / 4) * tstride + tt;
+                    if (p.accumulate) { const float4 a = *yp; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+                    const float s = p.out_scale * msk;
+                    o.x *= s; o.y *= s; o.z *= s; o.w *= s;
+                    *yp = o;
                 }
             }
         }
@@ -271,29 +336,67 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
     }
 }
 
-inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const Act& y, int dil, const TcEpi& e, cudaStream_t st, int num_sms) {
-    (void)num_sms;
-    BV2_CHECK(w.w && x.C == w.Cin && y.C == w.Cout && x.T == y.T && x.B == y.B, "tc_conv1d shapes");
+// x: c4 input [B][x.C/4][T][4]; y: c4 output ([B][y.C/4][T*max(1,ups_u)][4]).  Channel windows via e.cin_off/e.cout_off.
+inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const Act& y, const TcEpi& e, cudaStream_t st, int num_sms) {
+    const int u = w.ups_u ? w.ups_u : 1;
+    BV2_CHECK(w.w && x.B == y.B && y.T == x.T * u, "tc_conv1d shapes");
+    BV2_CHECK(e.cin_off % 4 == 0 && e.cout_off % 4 == 0 && e.cin_off + w.Cin <= x.C, "tc_conv1d channel window");
     TcParams p{};
-    p.x = x.p; p.y = y.p; p.w = w.w; p.bias = bias; p.res = e.res;
-    p.Cin = w.Cin; p.N = w.Cout; p.T = x.T; p.B = x.B; p.K = w.K; p.dil = dil; p.pad = (w.K - 1) / 2 * dil;
-    p.KC = w.KC; p.nchunks = w.nchunks; p.R = 128 + (w.K - 1) * dil;
+    p.x = x.p; p.y = y.p; p.w = w.w; p.bias = bias; p.res = e.res; p.bias_b = e.bias_b; p.lens = e.lens;
+    p.Cin_total = x.C; p.cin_off = e.cin_off; p.Cout_total = y.C; p.cout_off = e.cout_off;
+    p.res_C_total = e.res_C_total ? e.res_C_total : y.C; p.res_c_off = e.res_c_off; p.bias_b_stride = e.bias_b_stride;
+    p.Ncols_total = w.Cout;
+    p.T = x.T; p.B = x.B; p.K = w.K; p.dil = e.dil; p.pad = (w.K - 1) / 2 * e.dil;
+    p.KC = w.KC; p.nchunks = w.nchunks;
+    // ---- N tile: largest divisor of Cout that is a multiple of 16 and <= 256 (or the caller's request)
+    int nt = e.ntile;
+    if (!nt) {
+        // largest N tile (multiple of 16, divisor of Cout, <= 256) that still yields >= num_sms CTAs; never below 64
+        const int mtiles = cdiv(x.T, 128) * x.B;
+        int best = 0;
+        for (int c = std::min(w.Cout, 256); c >= 16; c -= 16) {
+            if (w.Cout % c) continue;
+            if (!best) best = c;
+            if (c < 64 && best) break;
+            best = c;
+            if ((long long)mtiles * (w.Cout / c) >= num_sms) break;
+        }
+        nt = best;
+    }
+    BV2_CHECK(nt >= 16 && nt <= 256 && nt % 16 == 0 && w.Cout % nt == 0, "tc_conv1d N tile");
+    if (w.ups_u) BV2_CHECK(w.ups_cout % 4 == 0, "ups cout");
+    p.nt = nt;
+    const int ntiles = w.Cout / nt;
+    // ---- M tiles per CTA: share each weight tile across MT accumulators while the grid still fills the chip
+    int MT = 1;
+    const int halo = (w.K - 1) * e.dil;
+    while (MT < 4) {
+        const int m2 = MT * 2;
+        if (m2 * nt > 512) break;
+        if ((long long)cdiv(p.T, 128 * m2) * ntiles * p.B < 2ll * num_sms) break;
+        if (2ull * p.KC * (m2 * 128 + halo) * 4 + 2ull * p.KC * nt * 4 > 200u * 1024) break;
+        MT = m2;
+    }
+    p.MT = MT;
+    p.R = MT * 128 + halo;
     p.a_stage_bytes = (uint32_t)(p.KC * p.R * 4);
-    p.w_stage_bytes = (uint32_t)(p.KC * p.N * 4);
+    p.w_stage_bytes = (uint32_t)(p.KC * nt * 4);
     const uint32_t budget = 200 * 1024;
     int nws = (int)((budget - 2 * p.a_stage_bytes - 512) / p.w_stage_bytes);
     p.nws = std::max(2, std::min(nws, 8));
-    uint32_t cols = 32; while ((int)cols < p.N) cols <<= 1;
+    uint32_t cols = 32; while ((int)cols < MT * nt) cols <<= 1;
     p.tmem_cols = cols;
-    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
-    p.in_slope = e.in_slope; p.out_scale = e.out_scale; p.accumulate = e.accumulate;
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((128u >> 4) << 24);
+    p.in_slope = e.in_slope; p.out_scale = e.out_scale; p.accumulate = e.accumulate; p.relu = e.relu; p.res_mode = e.res ? (e.res_mode ? e.res_mode : 1) : 0;
+    p.in_mask = e.in_mask; p.out_mask = e.out_mask; p.ups_u = w.ups_u; p.ups_cout = w.ups_cout;
+    if (p.in_mask || p.out_mask) BV2_CHECK(e.lens != nullptr, "mask needs lens");
     const size_t smem = 2 * (size_t)p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + (size_t)(7 + 2 * p.nws) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {
         BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    dim3 grid(cdiv(p.T, 128), p.B);
+    dim3 grid(cdiv(p.T, 128 * MT), ntiles, p.B);
     k_tc_conv1d<<<grid, 192, smem, st>>>(p);
     BV2_CUDA(cudaGetLastError());
 }

@@ -37,8 +37,8 @@ static int run_case(int Cin, int Cout, int K, int dil, int T, int B, float slope
     Act ay; ay.B = B; ay.C = Cout; ay.T = T; ay.p = up(to_c4(y0, Cout));
     float* dres = up(to_c4(r, Cout));
     float* dbias = up(bias);
-    TcEpi e; e.in_slope = slope; e.res = res ? dres : nullptr; e.accumulate = acc; e.out_scale = scale;
-    tc_conv1d(tw, dbias, ax, ay, dil, e, 0, 148);
+    TcEpi e; e.in_slope = slope; e.res = res ? dres : nullptr; e.res_mode = 1; e.accumulate = acc; e.out_scale = scale; e.dil = dil;
+    tc_conv1d(tw, dbias, ax, ay, e, 0, 148);
     cudaError_t er = cudaDeviceSynchronize();
     if (er != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(er)); return 1; }
     std::vector<float> got((size_t)B * Cout * T);
@@ -69,9 +69,9 @@ static int run_case(int Cin, int Cout, int K, int dil, int T, int B, float slope
     if (iters > 0) {
         cudaEvent_t a, c; cudaEventCreate(&a); cudaEventCreate(&c);
         e.accumulate = 0;
-        for (int i = 0; i < 3; i++) tc_conv1d(tw, dbias, ax, ay, dil, e, 0, 148);
+        for (int i = 0; i < 3; i++) tc_conv1d(tw, dbias, ax, ay, e, 0, 148);
         cudaEventRecord(a);
-        for (int i = 0; i < iters; i++) tc_conv1d(tw, dbias, ax, ay, dil, e, 0, 148);
+        for (int i = 0; i < iters; i++) tc_conv1d(tw, dbias, ax, ay, e, 0, 148);
         cudaEventRecord(c); cudaEventSynchronize(c); cudaEventElapsedTime(&ms, a, c); ms /= iters;
     }
     double flop = 2.0 * B * T * (double)Cin * Cout * K;
@@ -82,6 +82,60 @@ static int run_case(int Cin, int Cout, int K, int dil, int T, int B, float slope
     if (iters > 0) printf("  | %.3f ms  %.1f TFLOP/s  %.0f GB/s", ms, flop / ms * 1e-9, bytes / ms * 1e-6);
     printf("\n");
     fflush(stdout);
+    return ok ? 0 : 1;
+}
+
+static int run_ups(int Cin, int Cout, int K, int u, int T, int B, int iters) {
+    std::mt19937 rng(Cin * 13 + Cout + K + u + T);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    const int To = T * u, p = (K - u) / 2;
+    std::vector<float> x((size_t)B * Cin * T), w((size_t)Cin * Cout * K), bias(Cout);
+    for (auto& v : x) v = nd(rng);
+    for (auto& v : w) v = nd(rng) / std::sqrt((float)(Cin * K / u));
+    for (auto& v : bias) v = nd(rng);
+    std::vector<float> xc(x.size());
+    for (int b = 0; b < B; b++) for (int c = 0; c < Cin; c++) for (int t = 0; t < T; t++)
+        xc[(((size_t)b * (Cin / 4) + c / 4) * T + t) * 4 + (c & 3)] = x[((size_t)b * Cin + c) * T + t];
+    std::function<float*(const std::vector<float>&)> upf = up;
+    TcConvW tw = tc_pack_upsample(upf, w, Cin, Cout, K, u);
+    Act ax; ax.B = B; ax.C = Cin; ax.T = T; ax.p = up(xc);
+    std::vector<float> y0((size_t)B * Cout * To, 0.f);
+    Act ay; ay.B = B; ay.C = Cout; ay.T = To; ay.p = up(y0);
+    float* dbias = up(bias);
+    TcEpi e; e.in_slope = 0.1f;
+    tc_conv1d(tw, dbias, ax, ay, e, 0, 148);
+    cudaError_t er = cudaDeviceSynchronize();
+    if (er != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(er)); return 1; }
+    std::vector<float> got(y0.size());
+    cudaMemcpy(got.data(), ay.p, got.size() * 4, cudaMemcpyDeviceToHost);
+    double maxerr = 0, maxref = 0;
+    for (int b = 0; b < B; b++)
+        for (int co = 0; co < Cout; co += 3)
+            for (int n = 0; n < To; n += (To > 2000 ? 13 : 1)) {
+                double s = bias[co];
+                for (int i = 0; i < T; i++) {
+                    int j = n + p - i * u;
+                    if (j < 0 || j >= K) continue;
+                    for (int ci = 0; ci < Cin; ci++) {
+                        float xv = x[((size_t)b * Cin + ci) * T + i]; xv = xv > 0 ? xv : 0.1f * xv;
+                        s += (double)tf32_rn_host(xv) * tf32_rn_host(w[((size_t)ci * Cout + co) * K + j]);
+                    }
+                }
+                double g = got[(((size_t)b * (Cout / 4) + co / 4) * To + n) * 4 + (co & 3)];
+                maxerr = std::max(maxerr, std::fabs(g - s)); maxref = std::max(maxref, std::fabs(s));
+            }
+    float ms = 0;
+    if (iters > 0) {
+        cudaEvent_t a, c; cudaEventCreate(&a); cudaEventCreate(&c);
+        for (int i = 0; i < 3; i++) tc_conv1d(tw, dbias, ax, ay, e, 0, 148);
+        cudaEventRecord(a);
+        for (int i = 0; i < iters; i++) tc_conv1d(tw, dbias, ax, ay, e, 0, 148);
+        cudaEventRecord(c); cudaEventSynchronize(c); cudaEventElapsedTime(&ms, a, c); ms /= iters;
+    }
+    bool ok = maxerr < 2e-3 * std::max(1.0, maxref);
+    printf("%s UPS Cin=%3d Cout=%3d K=%2d u=%d T=%6d B=%d (Kp=%d) : maxerr %.3e (ref max %.2f)", ok ? "PASS" : "FAIL", Cin, Cout, K, u, T, B, tw.K, maxerr, maxref);
+    if (iters > 0) printf("  | %.3f ms", ms);
+    printf("\n"); fflush(stdout);
     return ok ? 0 : 1;
 }
 
@@ -99,6 +153,23 @@ int main(int argc, char** argv) {
         fails += run_case(256, 256, 11, 5, 500, 1, 0.1f, true, false, 1.f, 0);
         fails += run_case(256, 256, 7, 1, 128, 3, 0.1f, false, true, 1.f, 0);
         fails += run_case(192, 192, 5, 1, 333, 1, 1.f, false, false, 1.f, 0);
+        fails += run_case(192, 768, 5, 1, 1573, 1, 1.f, false, false, 1.f, perf ? 10 : 0);   // flow FFN conv_1 (N tiles)
+        fails += run_case(768, 192, 5, 1, 1573, 1, 1.f, false, false, 1.f, perf ? 10 : 0);   // flow FFN conv_2
+        fails += run_case(192, 576, 1, 1, 1573, 2, 1.f, false, false, 1.f, perf ? 10 : 0);   // fused QKV
+        fails += run_case(96, 192, 1, 1, 700, 1, 1.f, false, false, 1.f, 0);
+        fails += run_case(192, 512, 7, 1, 1573, 1, 1.f, false, false, 1.f, perf ? 10 : 0);   // conv_pre
+        fails += run_ups(512, 256, 16, 8, 300, 1, 0);
+        fails += run_ups(256, 128, 16, 8, 257, 2, 0);
+        fails += run_ups(128, 64, 8, 2, 1000, 1, 0);
+        fails += run_ups(64, 32, 2, 2, 900, 1, 0);
+        fails += run_ups(32, 16, 2, 2, 1111, 1, 0);
+        if (perf) {
+            fails += run_ups(512, 256, 16, 8, 1573, 1, 10);
+            fails += run_ups(256, 128, 16, 8, 1573 * 8, 1, 10);
+            fails += run_ups(128, 64, 8, 2, 1573 * 64, 1, 10);
+            fails += run_ups(64, 32, 2, 2, 1573 * 128, 1, 10);
+            fails += run_ups(32, 16, 2, 2, 1573 * 256, 1, 10);
+        }
         if (perf) {
             // Generator MRF shapes at F=1024 frames
             int F = 1024;
