@@ -154,7 +154,7 @@ struct bv2_engine {
         return w;
     }
     // [Cout][Cin][K] -> packed [Cin][K][Cout_w], Cout_w = Cout rounded up to 4 (+ zero pad)
-    ConvW make_conv(const std::vector<float>& w, int Cout, int Cin, int K, const std::vector<float>* bias, int tc_mode = 0) {
+    ConvW make_conv(const std::vector<float>& w, int Cout, int Cin, int K, const std::vector<float>* bias, int tc_mode = 0, int tc_nt = 0) {
         ConvW c; c.Cin = Cin; c.Cout = (Cout + 3) / 4 * 4; c.Cout_w = c.Cout; c.K = K;
         std::vector<float> p((size_t)Cin * K * c.Cout_w, 0.f);
         for (int co = 0; co < Cout; co++)
@@ -164,7 +164,7 @@ struct bv2_engine {
         std::vector<float> b(c.Cout, 0.f);
         if (bias) for (int co = 0; co < Cout; co++) b[co] = (*bias)[co];
         c.b = upload(b);
-        if (tc_mode) c.tc = tc_pack_weights(*this_uploader(), w, Cout, Cin, K);
+        if (tc_mode) c.tc = tc_pack_weights(*this_uploader(), w, Cout, Cin, K, tc_nt);
         return c;
     }
     // uploader functor handed to tc_conv.cuh
@@ -174,7 +174,7 @@ struct bv2_engine {
     }
     std::unique_ptr<std::function<float*(const std::vector<float>&)>> uploader_;
 
-    ConvW conv_from(const std::string& name, bool wn = false, int tc_mode = 0) {
+    ConvW conv_from(const std::string& name, bool wn = false, int tc_mode = 0, int tc_nt = 0) {
         std::vector<int64_t> shp;
         std::vector<float> w;
         if (wn) w = fold_wn(name, &shp);
@@ -182,7 +182,7 @@ struct bv2_engine {
         BV2_CHECK(shp.size() == 3 || shp.size() == 2, "conv weight rank " + name);
         int Cout = (int)shp[0], Cin = (int)shp[1], K = shp.size() == 3 ? (int)shp[2] : 1;
         const std::vector<float>* b = host.count(name + ".bias") ? &W(name + ".bias").data : nullptr;
-        return make_conv(w, Cout, Cin, K, b, tc_mode);
+        return make_conv(w, Cout, Cin, K, b, tc_mode, tc_nt);
     }
     LnW ln_from(const std::string& name) {
         LnW l; l.C = (int)W(name + ".gamma").numel(); l.g = upload(W(name + ".gamma").data); l.b = upload(W(name + ".beta").data);
@@ -206,13 +206,13 @@ struct bv2_engine {
                 for (int i2 = 0; i2 < H * H; i2++) w[(size_t)p * H * H + i2] = wt.data[i2] * s;
                 for (int i2 = 0; i2 < H; i2++) b[p * H + i2] = bt.data[i2] * s;
             }
-            L.qkv = make_conv(w, 3 * H, H, 1, &b, tc_mode);
-            L.o = conv_from(a + ".conv_o", false, tc_mode);
+            L.qkv = make_conv(w, 3 * H, H, 1, &b, tc_mode, 96);
+            L.o = conv_from(a + ".conv_o", false, tc_mode, 96);
             L.relk = upload(W(a + ".emb_rel_k").data);
             L.relv = upload(W(a + ".emb_rel_v").data);
             L.n1 = ln_from(name + ".norm_layers_1." + std::to_string(i));
-            L.f1 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_1", false, tc_mode);
-            L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2", false, tc_mode);
+            L.f1 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_1", false, tc_mode, 128);
+            L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2", false, tc_mode, 96);
             L.n2 = ln_from(name + ".norm_layers_2." + std::to_string(i));
             e.layers.push_back(L);
         }
@@ -387,31 +387,31 @@ void bv2_engine::finalize() {
                 b2[co] = qb.data[half - 1 - co];
             }
         }
-        fl.pre = make_conv(w1, H, half, 1, &pb.data, tc);
-        fl.post = make_conv(w2, half, H, 1, &b2, tc);
+        fl.pre = make_conv(w1, H, half, 1, &pb.data, tc, 96);
+        fl.post = make_conv(w2, half, H, 1, &b2, tc, 48);
         if (c.use_transformer_flow) {
             fl.enc = encoder_from(f + ".enc", c.n_layers_trans_flow, c.flow_kernel_size, gw, gb, tc);
         } else {
             const int L = c.wn_layers;
             fl.wn_g_off = append_gproj(f + ".enc.cond_layer", gw, gb, true);
             for (int l = 0; l < L; l++) {
-                fl.wn_in.push_back(conv_from(f + ".enc.in_layers." + std::to_string(l), true, tc));
+                fl.wn_in.push_back(conv_from(f + ".enc.in_layers." + std::to_string(l), true, tc, 128));
                 std::vector<int64_t> shp;
                 std::vector<float> w = fold_wn(f + ".enc.res_skip_layers." + std::to_string(l), &shp);
                 const auto& b = W(f + ".enc.res_skip_layers." + std::to_string(l) + ".bias").data;
                 if (l < L - 1) {
                     std::vector<float> wr(w.begin(), w.begin() + (size_t)H * H), ws(w.begin() + (size_t)H * H, w.end());
                     std::vector<float> br(b.begin(), b.begin() + H), bs(b.begin() + H, b.end());
-                    fl.wn_res.push_back(make_conv(wr, H, H, 1, &br, tc));
-                    fl.wn_skip.push_back(make_conv(ws, H, H, 1, &bs, tc));
+                    fl.wn_res.push_back(make_conv(wr, H, H, 1, &br, tc, 96));
+                    fl.wn_skip.push_back(make_conv(ws, H, H, 1, &bs, tc, 96));
                 } else {
-                    fl.wn_skip.push_back(make_conv(w, H, H, 1, &b, tc));
+                    fl.wn_skip.push_back(make_conv(w, H, H, 1, &b, tc, 96));
                 }
             }
         }
     }
     // ---- dec (reference models.py:490-564)
-    conv_pre = conv_from("dec.conv_pre", false, tc);
+    conv_pre = conv_from("dec.conv_pre", false, tc, 128);
     goff_dec = append_gproj("dec.cond", gw, gb);
     int ch = c.upsample_initial_channel;
     for (int i = 0; i < c.n_ups; i++) {

@@ -22,8 +22,8 @@
 namespace bv2 {
 
 struct TcConvW {
-    float* w = nullptr;  // packed [nchunks][K][KC/4][Cout][4], TF32-rounded (RN)
-    int Cin = 0, Cout = 0, K = 0, KC = 0, nchunks = 0;
+    float* w = nullptr;  // packed [Cout/nt N tiles][nchunks][K][KC/4][nt][4], TF32-rounded (RN): one contiguous smem image per stage
+    int Cin = 0, Cout = 0, K = 0, KC = 0, nchunks = 0, nt = 0;
     int ups_u = 0, ups_cout = 0;  // polyphase ConvTranspose1d: Cout = ups_u * ups_cout columns (phase-major)
 };
 struct TcEpi {
@@ -41,7 +41,6 @@ struct TcEpi {
     int bias_b_stride = 0;
     int cin_off = 0, cout_off = 0;  // channel windows inside x / y (multiples of 4)
     int dil = 1;
-    int ntile = 0;               // N tile (0 = auto)
 };
 
 inline float tf32_rn_host(float x) {
@@ -53,22 +52,29 @@ inline float tf32_rn_host(float x) {
 }
 
 // w: [Cout][Cin][K] fp32 (weight-norm already folded)
-inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>& up, const std::vector<float>& w, int Cout, int Cin, int K) {
+// nt = N tile (0: largest divisor of Cout that is a multiple of 16 and <= 256)
+inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>& up, const std::vector<float>& w, int Cout, int Cin, int K, int nt = 0) {
     TcConvW t; t.Cin = Cin; t.Cout = Cout; t.K = K;
-    t.KC = Cin >= 32 ? 32 : Cin;
+    if (!nt) { nt = std::min(Cout, 256); while (Cout % nt || nt % 16) nt -= 16; }
+    // K chunk: 32 channels (16 for wide N tiles so that two CTAs fit in one SM's shared memory)
+    t.KC = Cin >= 32 ? (nt > 128 ? 16 : 32) : Cin;
     if (Cin % t.KC != 0 || t.KC % 8 != 0 || Cout % 16 != 0 || Cout < 16)
         throw Error(-2, "tc_conv: unsupported channel counts " + std::to_string(Cin) + "->" + std::to_string(Cout));
+    if (nt < 16 || nt > 256 || nt % 16 || Cout % nt) throw Error(-2, "tc_conv: bad N tile");
+    t.nt = nt;
     t.nchunks = Cin / t.KC;
     std::vector<float> p((size_t)Cin * K * Cout);
     const int ncg = t.KC / 4;
-    for (int c = 0; c < t.nchunks; c++)
-        for (int j = 0; j < K; j++)
-            for (int g = 0; g < ncg; g++)
-                for (int n = 0; n < Cout; n++)
-                    for (int e = 0; e < 4; e++) {
-                        int ci = c * t.KC + g * 4 + e;
-                        p[((((size_t)c * K + j) * ncg + g) * Cout + n) * 4 + e] = tf32_rn_host(w[((size_t)n * Cin + ci) * K + j]);
-                    }
+    for (int tile = 0; tile < Cout / nt; tile++)
+        for (int c = 0; c < t.nchunks; c++)
+            for (int j = 0; j < K; j++)
+                for (int g = 0; g < ncg; g++)
+                    for (int n = 0; n < nt; n++)
+                        for (int e = 0; e < 4; e++) {
+                            int ci = c * t.KC + g * 4 + e;
+                            p[(((((size_t)tile * t.nchunks + c) * K + j) * ncg + g) * nt + n) * 4 + e] =
+                                tf32_rn_host(w[((size_t)(tile * nt + n) * Cin + ci) * K + j]);
+                        }
     t.w = up(p);
     return t;
 }
@@ -92,7 +98,8 @@ inline TcConvW tc_pack_upsample(std::function<float*(const std::vector<float>&)>
                 for (int ci = 0; ci < Cin; ci++)
                     w[(((size_t)(r * Cout + co)) * Cin + ci) * Kp + tap] = wT[((size_t)ci * Cout + co) * K + j];
         }
-    TcConvW t = tc_pack_weights(up, w, u * Cout, Cin, Kp);
+    int nt = std::min(u * Cout, 256);
+    TcConvW t = tc_pack_weights(up, w, u * Cout, Cin, Kp, nt);
     t.ups_u = u; t.ups_cout = Cout;
     return t;
 }
@@ -100,13 +107,26 @@ inline TcConvW tc_pack_upsample(std::function<float*(const std::vector<float>&)>
 struct TcParams {
     const float* x; float* y; const float* w; const float* bias; const float* res; const float* bias_b; const int* lens;
     int Cin_total, cin_off, Cout_total, cout_off, res_C_total, res_c_off, bias_b_stride;
-    int Ncols_total;  // packed weight row length (all N tiles)
-    int nt;           // columns of this launch's N tile
+    int nt;           // columns per N tile
     int T, B, K, dil, pad, KC, nchunks, R, nws, MT;
     uint32_t a_stage_bytes, w_stage_bytes, tmem_cols, idesc;
     float in_slope, out_scale;
     int accumulate, relu, res_mode, in_mask, out_mask, ups_u, ups_cout;
 };
+
+namespace tc {
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+                   "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+}  // namespace tc
 
 namespace tc {
 
@@ -166,6 +186,10 @@ __device__ __forceinline__ float to_tf32(float x) {
 }  // namespace tc
 
 // grid: (M blocks of MT*128 time steps, N tiles, B)
+//
+// Accumulator-init fusion: before the first MMA the epilogue warps pre-load  bias (+ per-batch bias) (+/- residual)
+// (+ previous output when accumulating)  into the TMEM accumulator with tcgen05.st while the first TMA loads are in
+// flight; every MMA then accumulates, and the tail is only  TMEM -> [relu] -> scale/mask -> store.
 __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -176,16 +200,17 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
     uint8_t* sA = smem;
     uint8_t* sW = smem + 2 * p.a_stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)p.nws * p.w_stage_bytes);
-    // barrier map: [0,2) a_full, [2,4) a_ready, [4,6) a_empty, [6,6+nws) w_full, [6+nws,6+2nws) w_empty, last acc_full
+    // barrier map: [0,2) a_full, [2,4) a_ready, [4,6) a_empty, [6,6+nws) w_full, [6+nws,6+2nws) w_empty, acc_full, acc_init
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    const int B_AFULL = 0, B_AREADY = 2, B_AEMPTY = 4, B_WFULL = 6, B_WEMPTY = 6 + p.nws, B_ACC = 6 + 2 * p.nws;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACC + 1);
+    const int B_AFULL = 0, B_AREADY = 2, B_AEMPTY = 4, B_WFULL = 6, B_WEMPTY = 6 + p.nws, B_ACC = 6 + 2 * p.nws, B_INIT = B_ACC + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_INIT + 1);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) { mbar_init(BAR(B_AFULL + i), 1); mbar_init(BAR(B_AREADY + i), 128); mbar_init(BAR(B_AEMPTY + i), 1); }
         for (int i = 0; i < p.nws; i++) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
         mbar_init(BAR(B_ACC), 1);
+        mbar_init(BAR(B_INIT), 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -218,25 +243,25 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
             };
             load_a(0);
             int wi = 0;
-            const uint32_t wrow = (uint32_t)nt * 16u;
+            const float* wtile = p.w + (size_t)blockIdx.y * p.nchunks * p.K * p.KC * nt;
             for (int c = 0; c < p.nchunks; c++) {
                 if (c + 1 < p.nchunks) load_a(c + 1);
                 for (int j = 0; j < p.K; j++, wi++) {
                     const int sw = wi % p.nws;
                     mbar_wait(BAR(B_WEMPTY + sw), ((wi / p.nws) & 1) ^ 1);
                     mbar_expect_tx(BAR(B_WFULL + sw), p.w_stage_bytes);
-                    const float* src = p.w + (((size_t)c * p.K + j) * ncg * p.Ncols_total + n0) * 4;
-                    const uint32_t dst = smem_u32(sW + (size_t)sw * p.w_stage_bytes);
-                    for (int g = 0; g < ncg; g++) bulk_g2s(dst + (uint32_t)g * wrow, src + (size_t)g * p.Ncols_total * 4, wrow, BAR(B_WFULL + sw));
+                    bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), wtile + ((size_t)c * p.K + j) * p.KC * nt, p.w_stage_bytes,
+                             BAR(B_WFULL + sw));
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // ===== MMA issuer: per weight tile, MT x KC/8 tcgen05.mma (M=128, N=nt, K=8 tf32); the MT accumulators
-            // (TMEM column blocks) share the weight tile, dividing its L2->smem traffic per FLOP by MT
+            // ===== MMA issuer: per weight tile, MT x KC/8 tcgen05.mma (M=128, N=nt, K=8 tf32), always accumulating
             const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)nt * 16u;
             int wi = 0;
+            mbar_wait(BAR(B_INIT), 0);
+            fence_after();
             for (int c = 0; c < p.nchunks; c++) {
                 const int sa = c & 1;
                 mbar_wait(BAR(B_AREADY + sa), (c >> 1) & 1);
@@ -251,7 +276,7 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
                         for (int kk = 0; kk < p.KC / 8; kk++) {
                             uint64_t ad = make_desc(a_base + ((uint32_t)(2 * kk) * R + (uint32_t)(mt * 128 + j * p.dil)) * 16u, a_lbo, 128u);
                             uint64_t bd = make_desc(w_base + (uint32_t)(2 * kk) * b_lbo, b_lbo, 128u);
-                            umma_tf32(tmem + (uint32_t)(mt * nt), ad, bd, p.idesc, (c | j | kk) != 0 ? 1u : 0u);
+                            umma_tf32(tmem + (uint32_t)(mt * nt), ad, bd, p.idesc, 1u);
                         }
                     }
                     umma_commit(BAR(B_WEMPTY + sw));
@@ -261,8 +286,47 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
             umma_commit(BAR(B_ACC));
         }
     } else {
-        // ===== operand prologue on the staged tile (generic proxy), then hand over to the async proxy
         const int tid2 = threadIdx.x - 64;
+        const int q = warp & 3;
+        const size_t cstride = (size_t)p.T;
+        // ===== accumulator init (overlaps the first TMA loads)
+        for (int mt = 0; mt < MT; mt++) {
+            const int t = t0 + mt * 128 + q * 32 + lane;
+            const bool ok = t < p.T;
+            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt);
+            for (int col = 0; col < nt; col += 16) {
+                uint32_t v[16];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const int n = n0 + col + 4 * g;
+                    int co = n, tt = t;
+                    size_t tstride = cstride;
+                    if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; tstride = cstride * p.ups_u; }
+                    float4 o = *reinterpret_cast<const float4*>(p.bias + co);
+                    if (p.bias_b) {
+                        const float4 b2 = *reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + co);
+                        o.x += b2.x; o.y += b2.y; o.z += b2.z; o.w += b2.w;
+                    }
+                    if (ok) {
+                        if (p.res_mode) {
+                            const float4 r = reinterpret_cast<const float4*>(p.res)[((size_t)b * (p.res_C_total / 4) + (p.res_c_off + co) / 4) * tstride + tt];
+                            if (p.res_mode == 1) { o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+                            else { o.x -= r.x; o.y -= r.y; o.z -= r.z; o.w -= r.w; }  // epilogue negates: res - (conv + bias)
+                        }
+                        if (p.accumulate) {
+                            const float4 a = reinterpret_cast<const float4*>(p.y)[((size_t)b * (p.Cout_total / 4) + (p.cout_off + co) / 4) * tstride + tt];
+                            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                        }
+                    }
+                    v[4 * g] = __float_as_uint(o.x); v[4 * g + 1] = __float_as_uint(o.y); v[4 * g + 2] = __float_as_uint(o.z); v[4 * g + 3] = __float_as_uint(o.w);
+                }
+                tmem_st16(trow + (uint32_t)col, v);
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        fence_before();
+        mbar_arrive(BAR(B_INIT));
+        // ===== operand prologue on the staged tile (generic proxy), then hand over to the async proxy
         const float slope = p.in_slope;
         for (int c = 0; c < p.nchunks; c++) {
             const int sa = c & 1;
@@ -283,48 +347,30 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(BAR(B_AREADY + sa));
         }
-        // ===== epilogue: TMEM -> registers -> fused pointwise tail -> c4 global (16-byte stores, coalesced across a warp)
+        // ===== tail: TMEM -> [relu] -> scale/mask -> c4 global (16-byte stores, coalesced across a warp)
         mbar_wait(BAR(B_ACC), 0);
         fence_after();
-        const int q = warp & 3;
-        const size_t cstride = (size_t)p.T;
+        const float sgn = p.res_mode == 2 ? -1.f : 1.f;
         for (int mt = 0; mt < MT; mt++) {
             const int t = t0 + mt * 128 + q * 32 + lane;
             const bool ok = t < p.T;
             const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt);
-            const float msk = (p.out_mask && t >= len) ? 0.f : 1.f;
+            const float s = ((p.out_mask && t >= len) ? 0.f : p.out_scale) * sgn;
             for (int col = 0; col < nt; col += 16) {
                 uint32_t v[16];
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                               "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                             : "r"(trow + (uint32_t)col));
+                tmem_ld16(trow + (uint32_t)col, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (!ok) continue;
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    const int n = n0 + col + 4 * g;  // global output column of this 4-channel group
+                    const int n = n0 + col + 4 * g;
                     int co = n, tt = t;
                     size_t tstride = cstride;
                     if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; tstride = cstride * p.ups_u; }
-                    const float4 bz = *reinterpret_cast<const float4*>(p.bias + co);
-                    float4 o = make_float4(__uint_as_float(v[4 * g]) + bz.x, __uint_as_float(v[4 * g + 1]) + bz.y,
-                                           __uint_as_float(v[4 * g + 2]) + bz.z, __uint_as_float(v[4 * g + 3]) + bz.w);
-                    if (p.bias_b) {
-                        const float4 b2 = *reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + co);
-                        o.x += b2.x; o.y += b2.y; o.z += b2.z; o.w += b2.w;
-                    }
+                    float4 o = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
                     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                    if (p.res_mode) {
-                        const float4 r = reinterpret_cast<const float4*>(p.res)[((size_t)b * (p.res_C_total / 4) + (p.res_c_off + co) / 4) * tstride + tt];
-                        if (p.res_mode == 1) { o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
-                        else { o.x = r.x - o.x; o.y = r.y - o.y; o.z = r.z - o.z; o.w = r.w - o.w; }
-                    }
-                    float4* yp = reinterpret_cast<float4*>(p.y) + ((size_t)b * (p.Cout_total / 4) + (p.cout_off + co) / 4) * tstride + tt;
-                    if (p.accumulate) { const float4 a = *yp; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
-                    const float s = p.out_scale * msk;
                     o.x *= s; o.y *= s; o.z *= s; o.w *= s;
-                    *yp = o;
+                    reinterpret_cast<float4*>(p.y)[((size_t)b * (p.Cout_total / 4) + (p.cout_off + co) / 4) * tstride + tt] = o;
                 }
             }
         }
@@ -338,6 +384,7 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
 
 // x: c4 input [B][x.C/4][T][4]; y: c4 output ([B][y.C/4][T*max(1,ups_u)][4]).  Channel windows via e.cin_off/e.cout_off.
 inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const Act& y, const TcEpi& e, cudaStream_t st, int num_sms) {
+    (void)num_sms;
     const int u = w.ups_u ? w.ups_u : 1;
     BV2_CHECK(w.w && x.B == y.B && y.T == x.T * u, "tc_conv1d shapes");
     BV2_CHECK(e.cin_off % 4 == 0 && e.cout_off % 4 == 0 && e.cin_off + w.Cin <= x.C, "tc_conv1d channel window");
@@ -345,52 +392,31 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     p.x = x.p; p.y = y.p; p.w = w.w; p.bias = bias; p.res = e.res; p.bias_b = e.bias_b; p.lens = e.lens;
     p.Cin_total = x.C; p.cin_off = e.cin_off; p.Cout_total = y.C; p.cout_off = e.cout_off;
     p.res_C_total = e.res_C_total ? e.res_C_total : y.C; p.res_c_off = e.res_c_off; p.bias_b_stride = e.bias_b_stride;
-    p.Ncols_total = w.Cout;
     p.T = x.T; p.B = x.B; p.K = w.K; p.dil = e.dil; p.pad = (w.K - 1) / 2 * e.dil;
     p.KC = w.KC; p.nchunks = w.nchunks;
-    // ---- N tile: largest divisor of Cout that is a multiple of 16 and <= 256 (or the caller's request)
-    int nt = e.ntile;
-    if (!nt) {
-        // largest N tile (multiple of 16, divisor of Cout, <= 256) that still yields >= num_sms CTAs; never below 64
-        const int mtiles = cdiv(x.T, 128) * x.B;
-        int best = 0;
-        for (int c = std::min(w.Cout, 256); c >= 16; c -= 16) {
-            if (w.Cout % c) continue;
-            if (!best) best = c;
-            if (c < 64 && best) break;
-            best = c;
-            if ((long long)mtiles * (w.Cout / c) >= num_sms) break;
-        }
-        nt = best;
-    }
-    BV2_CHECK(nt >= 16 && nt <= 256 && nt % 16 == 0 && w.Cout % nt == 0, "tc_conv1d N tile");
+    const int nt = w.nt;
     if (w.ups_u) BV2_CHECK(w.ups_cout % 4 == 0, "ups cout");
     p.nt = nt;
     const int ntiles = w.Cout / nt;
-    // ---- M tiles per CTA: share each weight tile across MT accumulators while the grid still fills the chip
-    int MT = 1;
+    const int MT = 1;  // weight-tile sharing across M tiles: measured slower than more resident CTAs at these sizes
     const int halo = (w.K - 1) * e.dil;
-    while (MT < 4) {
-        const int m2 = MT * 2;
-        if (m2 * nt > 512) break;
-        if ((long long)cdiv(p.T, 128 * m2) * ntiles * p.B < 2ll * num_sms) break;
-        if (2ull * p.KC * (m2 * 128 + halo) * 4 + 2ull * p.KC * nt * 4 > 200u * 1024) break;
-        MT = m2;
-    }
     p.MT = MT;
     p.R = MT * 128 + halo;
     p.a_stage_bytes = (uint32_t)(p.KC * p.R * 4);
     p.w_stage_bytes = (uint32_t)(p.KC * nt * 4);
-    const uint32_t budget = 200 * 1024;
-    int nws = (int)((budget - 2 * p.a_stage_bytes - 512) / p.w_stage_bytes);
-    p.nws = std::max(2, std::min(nws, 8));
+    // shared memory per CTA is capped (~100 KB) so that two CTAs co-reside per SM: one CTA's accumulator init / tail
+    // overlaps the other's MMA main loop
+    const uint32_t budget = 100 * 1024;
+    int nws = ((int)budget - 2 * (int)p.a_stage_bytes - 512) / (int)p.w_stage_bytes;
+    p.nws = std::max(2, std::min(nws, 6));
     uint32_t cols = 32; while ((int)cols < MT * nt) cols <<= 1;
     p.tmem_cols = cols;
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((128u >> 4) << 24);
     p.in_slope = e.in_slope; p.out_scale = e.out_scale; p.accumulate = e.accumulate; p.relu = e.relu; p.res_mode = e.res ? (e.res_mode ? e.res_mode : 1) : 0;
     p.in_mask = e.in_mask; p.out_mask = e.out_mask; p.ups_u = w.ups_u; p.ups_cout = w.ups_cout;
     if (p.in_mask || p.out_mask) BV2_CHECK(e.lens != nullptr, "mask needs lens");
-    const size_t smem = 2 * (size_t)p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + (size_t)(7 + 2 * p.nws) * 8 + 16;
+    BV2_CHECK(!(p.relu && (p.res_mode || p.accumulate)), "relu cannot be combined with residual/accumulate (accumulator-init fusion)");
+    const size_t smem = 2 * (size_t)p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + (size_t)(8 + 2 * p.nws) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {
         BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

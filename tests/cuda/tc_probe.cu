@@ -52,7 +52,7 @@ static int run_case(int Cin, int Cout, int K, int dil, int T, int B, float slope
     for (size_t i = 0; i < w.size(); i++) wr[i] = tf32_rn_host(w[i]);
     for (int b = 0; b < B; b++)
         for (int co = 0; co < Cout; co++)
-            for (int t = 0; t < T; t += (T > 400 ? 7 : 1)) {
+            for (int t = 0; t < T; t += std::max(1, T / 300)) {
                 double s = bias[co];
                 for (int ci = 0; ci < Cin; ci++)
                     for (int j = 0; j < K; j++) {
@@ -111,7 +111,7 @@ static int run_ups(int Cin, int Cout, int K, int u, int T, int B, int iters) {
     double maxerr = 0, maxref = 0;
     for (int b = 0; b < B; b++)
         for (int co = 0; co < Cout; co += 3)
-            for (int n = 0; n < To; n += (To > 2000 ? 13 : 1)) {
+            for (int n = 0; n < To; n += std::max(1, To / 300)) {
                 double s = bias[co];
                 for (int i = 0; i < T; i++) {
                     int j = n + p - i * u;
