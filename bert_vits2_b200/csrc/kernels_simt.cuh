@@ -69,9 +69,12 @@ struct ConvArgs {
     const int* lens = nullptr;
 };
 
-template <int K>
-__global__ void __launch_bounds__(256) k_conv1d_c4(ConvArgs a) {
-    constexpr int TT = 128, COT = 64, CIT = 8, MAXD = 5;
+// Tile = (16*NI time steps) x (4*CGN output channels), 16*CGN threads, each thread NI x 4 outputs.
+// <8,16>: 128 x 64 tile for long sequences; <1,4>: 16 x 16 tile so that token-rate tensors (T ~ 256) still spread over
+// >= 100 CTAs (the text encoder / duration predictors are latency-bound).
+template <int K, int NI, int CGN>
+__global__ void __launch_bounds__(16 * CGN) k_conv1d_c4(ConvArgs a) {
+    constexpr int TT = 16 * NI, COT = 4 * CGN, CIT = 8, MAXD = 5, NTHR = 16 * CGN;
     constexpr int XW = TT + (K - 1) * MAXD;
     __shared__ float sx[CIT][XW];
     __shared__ __align__(16) float sw[CIT][K][COT];
@@ -79,13 +82,13 @@ __global__ void __launch_bounds__(256) k_conv1d_c4(ConvArgs a) {
     const int b = blockIdx.z, t0 = blockIdx.x * TT, co0 = blockIdx.y * COT;
     const int len = a.lens ? a.lens[b] : a.T;
     const int xw = TT + (K - 1) * a.dil;
-    float acc[8][4];
+    float acc[NI][4];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    for (int i = 0; i < NI; i++) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     const float4* x4 = reinterpret_cast<const float4*>(a.x) + ((size_t)b * (a.Cin_total / 4) + a.cin_off / 4) * a.T;
 
     for (int c0 = 0; c0 < a.Cin; c0 += CIT) {
-        for (int i = tid; i < 2 * xw; i += 256) {
+        for (int i = tid; i < 2 * xw; i += NTHR) {
             int g = i >= xw ? 1 : 0, p = i - g * xw;
             int t = t0 - a.pad + p;
             int cg = c0 / 4 + g;
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(256) k_conv1d_c4(ConvArgs a) {
             }
             sx[g * 4 + 0][p] = v.x; sx[g * 4 + 1][p] = v.y; sx[g * 4 + 2][p] = v.z; sx[g * 4 + 3][p] = v.w;
         }
-        for (int i = tid; i < CIT * K * (COT / 4); i += 256) {
+        for (int i = tid; i < CIT * K * (COT / 4); i += NTHR) {
             int c4i = i % (COT / 4), r = i / (COT / 4);
             int j = r % K, ci = r / K;
             int co = co0 + c4i * 4;
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(256) k_conv1d_c4(ConvArgs a) {
                 const float4 w4 = *reinterpret_cast<const float4*>(&sw[ci][j][cgo * 4]);
                 const float* xr = &sx[ci][tl + j * a.dil];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
+                for (int i = 0; i < NI; i++) {
                     float xv = xr[16 * i];
                     acc[i][0] = fmaf(xv, w4.x, acc[i][0]);
                     acc[i][1] = fmaf(xv, w4.y, acc[i][1]);
@@ -140,7 +143,7 @@ __global__ void __launch_bounds__(256) k_conv1d_c4(ConvArgs a) {
                                    ((size_t)b * (a.res_C_total / 4) + (a.res_c_off + co) / 4) * a.T
                              : nullptr;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < NI; i++) {
         int t = t0 + tl + 16 * i;
         if (t >= a.T) continue;
         float4 v = make_float4(acc[i][0] + bz.x, acc[i][1] + bz.y, acc[i][2] + bz.z, acc[i][3] + bz.w);
@@ -158,15 +161,26 @@ __global__ void __launch_bounds__(256) k_conv1d_c4(ConvArgs a) {
     }
 }
 
+template <int K>
+inline void launch_conv1d_k(const ConvArgs& a, cudaStream_t st) {
+    const long long big_ctas = (long long)cdiv(a.T, 128) * cdiv(a.Cout, 64) * a.B;
+    if (big_ctas >= 96) {
+        dim3 grid(cdiv(a.T, 128), cdiv(a.Cout, 64), a.B);
+        k_conv1d_c4<K, 8, 16><<<grid, 256, 0, st>>>(a);
+    } else {
+        dim3 grid(cdiv(a.T, 16), cdiv(a.Cout, 16), a.B);
+        k_conv1d_c4<K, 1, 4><<<grid, 64, 0, st>>>(a);
+    }
+}
+
 inline void launch_conv1d(const ConvArgs& a, cudaStream_t st) {
-    dim3 grid(cdiv(a.T, 128), cdiv(a.Cout, 64), a.B);
     BV2_CHECK(a.dil <= 5 && a.Cin % 4 == 0 && a.Cout % 4 == 0 && a.cin_off % 4 == 0 && a.cout_off % 4 == 0, "conv1d shape");
     switch (a.K) {
-        case 1: k_conv1d_c4<1><<<grid, 256, 0, st>>>(a); break;
-        case 3: k_conv1d_c4<3><<<grid, 256, 0, st>>>(a); break;
-        case 5: k_conv1d_c4<5><<<grid, 256, 0, st>>>(a); break;
-        case 7: k_conv1d_c4<7><<<grid, 256, 0, st>>>(a); break;
-        case 11: k_conv1d_c4<11><<<grid, 256, 0, st>>>(a); break;
+        case 1: launch_conv1d_k<1>(a, st); break;
+        case 3: launch_conv1d_k<3>(a, st); break;
+        case 5: launch_conv1d_k<5>(a, st); break;
+        case 7: launch_conv1d_k<7>(a, st); break;
+        case 11: launch_conv1d_k<11>(a, st); break;
         default: throw Error(-2, "conv1d: unsupported kernel size " + std::to_string(a.K));
     }
     BV2_CUDA(cudaGetLastError());

@@ -56,8 +56,7 @@ inline float tf32_rn_host(float x) {
 inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>& up, const std::vector<float>& w, int Cout, int Cin, int K, int nt = 0) {
     TcConvW t; t.Cin = Cin; t.Cout = Cout; t.K = K;
     if (!nt) { nt = std::min(Cout, 256); while (Cout % nt || nt % 16) nt -= 16; }
-    // K chunk: 32 channels (16 for wide N tiles so that two CTAs fit in one SM's shared memory)
-    t.KC = Cin >= 32 ? (nt > 128 ? 16 : 32) : Cin;
+    t.KC = Cin >= 32 ? 32 : Cin;
     if (Cin % t.KC != 0 || t.KC % 8 != 0 || Cout % 16 != 0 || Cout < 16)
         throw Error(-2, "tc_conv: unsupported channel counts " + std::to_string(Cin) + "->" + std::to_string(Cout));
     if (nt < 16 || nt > 256 || nt % 16 || Cout % nt) throw Error(-2, "tc_conv: bad N tile");
@@ -384,7 +383,6 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
 
 // x: c4 input [B][x.C/4][T][4]; y: c4 output ([B][y.C/4][T*max(1,ups_u)][4]).  Channel windows via e.cin_off/e.cout_off.
 inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const Act& y, const TcEpi& e, cudaStream_t st, int num_sms) {
-    (void)num_sms;
     const int u = w.ups_u ? w.ups_u : 1;
     BV2_CHECK(w.w && x.B == y.B && y.T == x.T * u, "tc_conv1d shapes");
     BV2_CHECK(e.cin_off % 4 == 0 && e.cout_off % 4 == 0 && e.cin_off + w.Cin <= x.C, "tc_conv1d channel window");
@@ -406,7 +404,8 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     p.w_stage_bytes = (uint32_t)(p.KC * nt * 4);
     // shared memory per CTA is capped (~100 KB) so that two CTAs co-reside per SM: one CTA's accumulator init / tail
     // overlaps the other's MMA main loop
-    const uint32_t budget = 100 * 1024;
+    const long long nctas = (long long)cdiv(p.T, 128 * MT) * ntiles * p.B;
+    const uint32_t budget = (nctas > num_sms && nt <= 128) ? 100 * 1024 : 200 * 1024;
     int nws = ((int)budget - 2 * (int)p.a_stage_bytes - 512) / (int)p.w_stage_bytes;
     p.nws = std::max(2, std::min(nws, 6));
     uint32_t cols = 32; while ((int)cols < MT * nt) cols <<= 1;
