@@ -154,7 +154,7 @@ struct bv2_engine {
         return w;
     }
     // [Cout][Cin][K] -> packed [Cin][K][Cout_w], Cout_w = Cout rounded up to 4 (+ zero pad)
-    ConvW make_conv(const std::vector<float>& w, int Cout, int Cin, int K, const std::vector<float>* bias, int tc_mode = 0, int tc_nt = 0) {
+    ConvW make_conv(const std::vector<float>& w, int Cout, int Cin, int K, const std::vector<float>* bias, int tc_mode = 0, int tc_nt = 0, int tc_kc = 0) {
         ConvW c; c.Cin = Cin; c.Cout = (Cout + 3) / 4 * 4; c.Cout_w = c.Cout; c.K = K;
         std::vector<float> p((size_t)Cin * K * c.Cout_w, 0.f);
         for (int co = 0; co < Cout; co++)
@@ -164,7 +164,7 @@ struct bv2_engine {
         std::vector<float> b(c.Cout, 0.f);
         if (bias) for (int co = 0; co < Cout; co++) b[co] = (*bias)[co];
         c.b = upload(b);
-        if (tc_mode) c.tc = tc_pack_weights(*this_uploader(), w, Cout, Cin, K, tc_nt);
+        if (tc_mode && Cout % 16 == 0) c.tc = tc_pack_weights(*this_uploader(), w, Cout, Cin, K, tc_nt, tc_mode == 2 ? 1 : 0, tc_kc);
         return c;
     }
     // uploader functor handed to tc_conv.cuh
@@ -174,7 +174,7 @@ struct bv2_engine {
     }
     std::unique_ptr<std::function<float*(const std::vector<float>&)>> uploader_;
 
-    ConvW conv_from(const std::string& name, bool wn = false, int tc_mode = 0, int tc_nt = 0) {
+    ConvW conv_from(const std::string& name, bool wn = false, int tc_mode = 0, int tc_nt = 0, int tc_kc = 0) {
         std::vector<int64_t> shp;
         std::vector<float> w;
         if (wn) w = fold_wn(name, &shp);
@@ -182,7 +182,7 @@ struct bv2_engine {
         BV2_CHECK(shp.size() == 3 || shp.size() == 2, "conv weight rank " + name);
         int Cout = (int)shp[0], Cin = (int)shp[1], K = shp.size() == 3 ? (int)shp[2] : 1;
         const std::vector<float>* b = host.count(name + ".bias") ? &W(name + ".bias").data : nullptr;
-        return make_conv(w, Cout, Cin, K, b, tc_mode, tc_nt);
+        return make_conv(w, Cout, Cin, K, b, tc_mode, tc_nt, tc_kc);
     }
     LnW ln_from(const std::string& name) {
         LnW l; l.C = (int)W(name + ".gamma").numel(); l.g = upload(W(name + ".gamma").data); l.b = upload(W(name + ".beta").data);
@@ -206,25 +206,25 @@ struct bv2_engine {
                 for (int i2 = 0; i2 < H * H; i2++) w[(size_t)p * H * H + i2] = wt.data[i2] * s;
                 for (int i2 = 0; i2 < H; i2++) b[p * H + i2] = bt.data[i2] * s;
             }
-            L.qkv = make_conv(w, 3 * H, H, 1, &b, tc_mode, 96);
-            L.o = conv_from(a + ".conv_o", false, tc_mode, 48);
+            L.qkv = make_conv(w, 3 * H, H, 1, &b, tc_mode, tc_mode == 2 ? 32 : 96);
+            L.o = conv_from(a + ".conv_o", false, tc_mode, tc_mode == 2 ? 32 : 48);
             L.relk = upload(W(a + ".emb_rel_k").data);
             L.relv = upload(W(a + ".emb_rel_v").data);
             L.n1 = ln_from(name + ".norm_layers_1." + std::to_string(i));
-            L.f1 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_1", false, tc_mode, 128);
+            L.f1 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_1", false, tc_mode, tc_mode == 2 ? 32 : 128);
             L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2", false, tc_mode, 32);
             L.n2 = ln_from(name + ".norm_layers_2." + std::to_string(i));
             e.layers.push_back(L);
         }
         return e;
     }
-    DdsW dds_from(const std::string& name, int n_layers) {
+    DdsW dds_from(const std::string& name, int n_layers, int tc_mode = 0) {
         DdsW d;
         for (int i = 0; i < n_layers; i++) {
             std::string s = std::to_string(i);
             d.sep_w.push_back(upload(W(name + ".convs_sep." + s + ".weight").data));  // [C][1][3]
             d.sep_b.push_back(upload(W(name + ".convs_sep." + s + ".bias").data));
-            d.c1.push_back(conv_from(name + ".convs_1x1." + s));
+            d.c1.push_back(conv_from(name + ".convs_1x1." + s, false, tc_mode, 32));
             d.n1.push_back(ln_from(name + ".norms_1." + s));
             d.n2.push_back(ln_from(name + ".norms_2." + s));
         }
@@ -323,6 +323,11 @@ void bv2_engine::finalize() {
     BV2_CHECK(c.window_size <= 5, "window");
     BV2_CHECK(c.sdp_num_bins == 10 && c.sdp_kernel == 3, "sdp spline bins/kernel");
     std::vector<float> gw, gb;
+    // Precision policy: stages that feed ceil(durations) never run on the TF32 tensor-core path.  Error-compensated
+    // 3xTF32 was measured (tests/cuda/tc_probe.cu run_x3): the tcgen05 FP32 accumulator truncates, so the error grows
+    // linearly with the reduction length (~6.6e-8 per accumulated product: 1.5e-4 at Cin*K = 2304) and misses the
+    // fp32-class accuracy ceil() needs.  These stages therefore stay on FP32 FMA (SIMT) in both engines.
+    const int x3 = 0;
     // ---- enc_p (reference models.py:333-375)
     emb = upload(W("enc_p.emb.weight").data);
     temb = upload(W("enc_p.tone_emb.weight").data);
@@ -340,14 +345,14 @@ void bv2_engine::finalize() {
                 b[co] += bt.data[co];
             }
         }
-        bert_proj = make_conv(w, H, 3 * D, 1, &b);
+        bert_proj = make_conv(w, H, 3 * D, 1, &b, x3, 32);
     }
-    enc_p = encoder_from("enc_p.encoder", c.n_layers, c.kernel_size, gw, gb);
-    enc_proj = conv_from("enc_p.proj");
+    enc_p = encoder_from("enc_p.encoder", c.n_layers, c.kernel_size, gw, gb, x3);
+    enc_proj = conv_from("enc_p.proj", false, x3, 32);
     // ---- sdp (reference models.py:148-195); flows[1] is the dropped "useless vflow" (:247)
-    sdp_pre = conv_from("sdp.pre");
-    sdp_proj = conv_from("sdp.proj");
-    sdp_dds = dds_from("sdp.convs", c.sdp_dds_layers);
+    sdp_pre = conv_from("sdp.pre", false, x3, 32);
+    sdp_proj = conv_from("sdp.proj", false, x3, 32);
+    sdp_dds = dds_from("sdp.convs", c.sdp_dds_layers, x3);
     goff_sdp = append_gproj("sdp.cond", gw, gb);
     sdp_flows.resize(2 * c.sdp_n_flows + 1);
     for (int i = 2; i <= c.sdp_n_flows; i++) {
@@ -355,14 +360,14 @@ void bv2_engine::finalize() {
         ConvFlowW cf;
         cf.pre_w = upload(W(f + ".pre.weight").data);
         cf.pre_b = upload(W(f + ".pre.bias").data);
-        cf.dds = dds_from(f + ".convs", c.sdp_dds_layers);
-        cf.proj = conv_from(f + ".proj");
+        cf.dds = dds_from(f + ".convs", c.sdp_dds_layers, x3);
+        cf.proj = conv_from(f + ".proj", false, x3, 32);
         sdp_flows[2 * i - 1] = cf;
     }
     for (int i = 0; i < 2; i++) { ea_m[i] = W("sdp.flows.0.m").data[i]; ea_logs[i] = W("sdp.flows.0.logs").data[i]; }
     dconst = (float)std::log(std::exp(1.0 - 1e-3) - 1.0);  // transforms.py:69
     // ---- dp (reference models.py:259-299)
-    dp_c1 = conv_from("dp.conv_1"); dp_c2 = conv_from("dp.conv_2"); dp_proj = conv_from("dp.proj");
+    dp_c1 = conv_from("dp.conv_1", false, x3, 32); dp_c2 = conv_from("dp.conv_2", false, x3, 32); dp_proj = conv_from("dp.proj");
     dp_n1 = ln_from("dp.norm_1"); dp_n2 = ln_from("dp.norm_2");
     goff_dp = append_gproj("dp.cond", gw, gb);
     // ---- flow (reference models.py:82-145 / 403-445): Flip folded into pre/post channel order
@@ -424,7 +429,7 @@ void bv2_engine::finalize() {
             for (int co = 0; co < u.Cout; co++)
                 for (int j = 0; j < u.K; j++) p[((size_t)ci * u.K + j) * u.Cout + co] = w[((size_t)ci * u.Cout + co) * u.K + j];
         u.w = upload(p); u.b = upload(W("dec.ups." + std::to_string(i) + ".bias").data);
-        if (tc) u.tc = tc_pack_upsample(*this_uploader(), w, u.Cin, u.Cout, u.K, u.u);
+        if (tc) u.tc = tc_pack_upsample(*this_uploader(), w, u.Cin, u.Cout, u.K, u.u, i == 0 ? 32 : 16);
         ups.push_back(u);
         ch /= 2;
         for (int j = 0; j < c.n_resblock_kernels; j++) {
@@ -432,8 +437,8 @@ void bv2_engine::finalize() {
             std::string r = "dec.resblocks." + std::to_string(i * c.n_resblock_kernels + j);
             for (int d = 0; d < c.n_dilations; d++) {
                 rb.dil.push_back(c.resblock_dilation_sizes[j][d]);
-                rb.c1.push_back(conv_from(r + ".convs1." + std::to_string(d), true, tc));
-                rb.c2.push_back(conv_from(r + ".convs2." + std::to_string(d), true, tc));
+                rb.c1.push_back(conv_from(r + ".convs1." + std::to_string(d), true, tc, 0, 16));
+                rb.c2.push_back(conv_from(r + ".convs2." + std::to_string(d), true, tc, 0, 16));
             }
             resblocks.push_back(rb);
         }
@@ -489,7 +494,7 @@ void bv2_engine::run_dds(const DdsW& D, Act x, const int* lens, cudaStream_t s) 
         k_dwconv3_c4<<<grid_tcb(T, C, B), 128, 0, s>>>(x.p, D.sep_w[i], D.sep_b[i], y.p, C, T, dil, lens);
         BV2_CUDA(cudaGetLastError()); launches++;
         layernorm(D.n1[i], y, nullptr, y, s, 1, nullptr, lens, 0);
-        conv(D.c1[i], y, y2, s);
+        conv(D.c1[i], y, y2, s, ConvArgs(), 0, 0, true);
         layernorm(D.n2[i], y2, nullptr, x, s, 1, x.p, lens, i == nl - 1 ? 1 : 0);
         dil *= cfg.sdp_kernel;
     }
@@ -508,14 +513,14 @@ void bv2_engine::run_text_encoder(int B, int T, const int64_t* x, const int64_t*
         BV2_CUDA(cudaGetLastError()); launches++;
     }
     Act proj = ws.act(B, H, T);
-    conv(bert_proj, bc, proj, s);
+    conv(bert_proj, bc, proj, s, ConvArgs(), 0, 0, true);
     k_embed_sum<<<grid_tcb(T, H, B), 128, 0, s>>>(proj.p, reinterpret_cast<const long long*>(x), reinterpret_cast<const long long*>(tone),
                                                   reinterpret_cast<const long long*>(lang), emb, temb, lemb, h.p, H, T, lens,
                                                   std::sqrt((float)H));
     BV2_CUDA(cudaGetLastError()); launches++;
-    run_encoder(enc_p, h, lens, gproj, s, false);
+    run_encoder(enc_p, h, lens, gproj, s, cfg.generator_precision != 0);
     ConvArgs a; a.out_mask = 1; a.lens = lens;
-    conv(enc_proj, h, stats, s, a);
+    conv(enc_proj, h, stats, s, a, 0, 0, true);
 }
 
 // StochasticDurationPredictor(reverse) + DurationPredictor (reference models.py:197-204,245-256, 285-299)
@@ -525,10 +530,10 @@ void bv2_engine::run_durations(Act h, const int* lens, const float* gproj, const
     // ---- SDP conditioning
     Act c = ws.act(B, Cf, T), cond = ws.act(B, Cf, T);
     ConvArgs a0; a0.bias_b = gproj + goff_sdp; a0.bias_b_stride = gproj_n;
-    conv(sdp_pre, h, c, s, a0);
+    conv(sdp_pre, h, c, s, a0, 0, 0, true);
     run_dds(sdp_dds, c, lens, s);
     ConvArgs a1; a1.out_mask = 1; a1.lens = lens;
-    conv(sdp_proj, c, cond, s, a1);
+    conv(sdp_proj, c, cond, s, a1, 0, 0, true);
     debug("sdp_cond", cond);
     {
         size_t n = (size_t)B * 2 * T;
@@ -544,7 +549,7 @@ void bv2_engine::run_durations(Act h, const int* lens, const float* gproj, const
         k_flow_pre<<<grid_tcb(T, Cf, B), 128, 0, s>>>(z, x0ch, cf.pre_w, cf.pre_b, cond.p, hh.p, Cf, T);
         BV2_CUDA(cudaGetLastError()); launches++;
         run_dds(cf.dds, hh, lens, s);
-        conv(cf.proj, hh, pp, s);
+        conv(cf.proj, hh, pp, s, ConvArgs(), 0, 0, true);
         dim3 grid(cdiv(T, 128), B);
         k_spline_inverse<10><<<grid, 128, 0, s>>>(pp.p, 32, z, 1 - x0ch, T, lens, 1.f / std::sqrt((float)Cf), cfg.sdp_tail_bound, dconst);
         BV2_CUDA(cudaGetLastError()); launches++;
@@ -558,10 +563,10 @@ void bv2_engine::run_durations(Act h, const int* lens, const float* gproj, const
     k_add_bvec_mask<<<grid_tcb(T, h.C, B), 128, 0, s>>>(xg.p, gproj + goff_dp, gproj_n, h.C, T, lens);
     BV2_CUDA(cudaGetLastError()); launches++;
     ConvArgs r; r.act = 1;
-    conv(dp_c1, xg, d1, s, r);
+    conv(dp_c1, xg, d1, s, r, 0, 0, true);
     layernorm(dp_n1, d1, nullptr, d1, s, 0, nullptr, lens, 0);
     ConvArgs r2; r2.act = 1; r2.in_mask = 1; r2.lens = lens;
-    conv(dp_c2, d1, d2, s, r2);
+    conv(dp_c2, d1, d2, s, r2, 0, 0, true);
     layernorm(dp_n2, d2, nullptr, d2, s, 0, nullptr, lens, 0);
     ConvArgs r3; r3.in_mask = 1; r3.out_mask = 1; r3.lens = lens;
     conv(dp_proj, d2, dp_out, s, r3);

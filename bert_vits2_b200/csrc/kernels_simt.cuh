@@ -72,9 +72,9 @@ struct ConvArgs {
 // Tile = (16*NI time steps) x (4*CGN output channels), 16*CGN threads, each thread NI x 4 outputs.
 // <8,16>: 128 x 64 tile for long sequences; <1,4>: 16 x 16 tile so that token-rate tensors (T ~ 256) still spread over
 // >= 100 CTAs (the text encoder / duration predictors are latency-bound).
-template <int K, int NI, int CGN>
+template <int K, int NI, int CGN, int CIT>
 __global__ void __launch_bounds__(16 * CGN) k_conv1d_c4(ConvArgs a) {
-    constexpr int TT = 16 * NI, COT = 4 * CGN, CIT = 8, MAXD = 5, NTHR = 16 * CGN;
+    constexpr int TT = 16 * NI, COT = 4 * CGN, MAXD = 5, NTHR = 16 * CGN;
     constexpr int XW = TT + (K - 1) * MAXD;
     __shared__ float sx[CIT][XW];
     __shared__ __align__(16) float sw[CIT][K][COT];
@@ -88,8 +88,8 @@ __global__ void __launch_bounds__(16 * CGN) k_conv1d_c4(ConvArgs a) {
     const float4* x4 = reinterpret_cast<const float4*>(a.x) + ((size_t)b * (a.Cin_total / 4) + a.cin_off / 4) * a.T;
 
     for (int c0 = 0; c0 < a.Cin; c0 += CIT) {
-        for (int i = tid; i < 2 * xw; i += NTHR) {
-            int g = i >= xw ? 1 : 0, p = i - g * xw;
+        for (int i = tid; i < (CIT / 4) * xw; i += NTHR) {
+            int g = i / xw, p = i - g * xw;
             int t = t0 - a.pad + p;
             int cg = c0 / 4 + g;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -166,10 +166,10 @@ inline void launch_conv1d_k(const ConvArgs& a, cudaStream_t st) {
     const long long big_ctas = (long long)cdiv(a.T, 128) * cdiv(a.Cout, 64) * a.B;
     if (big_ctas >= 96) {
         dim3 grid(cdiv(a.T, 128), cdiv(a.Cout, 64), a.B);
-        k_conv1d_c4<K, 8, 16><<<grid, 256, 0, st>>>(a);
+        k_conv1d_c4<K, 8, 16, 8><<<grid, 256, 0, st>>>(a);
     } else {
         dim3 grid(cdiv(a.T, 16), cdiv(a.Cout, 16), a.B);
-        k_conv1d_c4<K, 1, 4><<<grid, 64, 0, st>>>(a);
+        k_conv1d_c4<K, 1, 4, 32><<<grid, 64, 0, st>>>(a);
     }
 }
 

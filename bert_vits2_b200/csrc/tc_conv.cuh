@@ -14,6 +14,7 @@
 // fill of the conv padding rows, fence.proxy.async) and TMEM epilogue (tcgen05.ld -> +bias, +residual, MRF
 // accumulate/scale -> coalesced 16-byte stores).
 #pragma once
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <vector>
@@ -25,6 +26,7 @@ struct TcConvW {
     float* w = nullptr;  // packed [Cout/nt N tiles][nchunks][K][KC/4][nt][4], TF32-rounded (RN): one contiguous smem image per stage
     int Cin = 0, Cout = 0, K = 0, KC = 0, nchunks = 0, nt = 0;
     int ups_u = 0, ups_cout = 0;  // polyphase ConvTranspose1d: Cout = ups_u * ups_cout columns (phase-major)
+    int x3 = 0;  // error-compensated 3xTF32 (hi/lo operand split, fp32-class accuracy) for the stages that feed ceil(durations)
 };
 struct TcEpi {
     float in_slope = 1.f;        // leaky-relu slope applied to the conv INPUT (1 = identity)
@@ -53,16 +55,23 @@ inline float tf32_rn_host(float x) {
 
 // w: [Cout][Cin][K] fp32 (weight-norm already folded)
 // nt = N tile (0: largest divisor of Cout that is a multiple of 16 and <= 256)
-inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>& up, const std::vector<float>& w, int Cout, int Cin, int K, int nt = 0) {
-    TcConvW t; t.Cin = Cin; t.Cout = Cout; t.K = K;
+// kc = K chunk (channels per pipeline stage): 16 for convs launched with thousands of tiles (small stages -> more
+// resident CTAs per SM hide the per-tile latency chain), 32 for few-tile launches (shorter chunk loop per CTA).
+inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>& up, const std::vector<float>& w, int Cout, int Cin, int K, int nt = 0,
+                               int x3 = 0, int kc = 0) {
+    TcConvW t; t.Cin = Cin; t.Cout = Cout; t.K = K; t.x3 = x3;
     if (!nt) { nt = std::min(Cout, 256); while (Cout % nt || nt % 16) nt -= 16; }
-    t.KC = Cin >= 32 ? 32 : Cin;
+    static const int kc_env = getenv("BV2_TC_KC") ? atoi(getenv("BV2_TC_KC")) : 0;  // tuning knob (experiments)
+    if (kc_env) kc = kc_env;
+    if (!kc) kc = 32;
+    t.KC = Cin >= kc ? kc : Cin;
     if (Cin % t.KC != 0 || t.KC % 8 != 0 || Cout % 16 != 0 || Cout < 16)
         throw Error(-2, "tc_conv: unsupported channel counts " + std::to_string(Cin) + "->" + std::to_string(Cout));
     if (nt < 16 || nt > 256 || nt % 16 || Cout % nt) throw Error(-2, "tc_conv: bad N tile");
     t.nt = nt;
     t.nchunks = Cin / t.KC;
-    std::vector<float> p((size_t)Cin * K * Cout);
+    const int parts = x3 ? 2 : 1;  // x3: every stage image is [hi | lo]
+    std::vector<float> p((size_t)Cin * K * Cout * parts);
     const int ncg = t.KC / 4;
     for (int tile = 0; tile < Cout / nt; tile++)
         for (int c = 0; c < t.nchunks; c++)
@@ -71,8 +80,11 @@ inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>&
                     for (int n = 0; n < nt; n++)
                         for (int e = 0; e < 4; e++) {
                             int ci = c * t.KC + g * 4 + e;
-                            p[(((((size_t)tile * t.nchunks + c) * K + j) * ncg + g) * nt + n) * 4 + e] =
-                                tf32_rn_host(w[((size_t)(tile * nt + n) * Cin + ci) * K + j]);
+                            const float v = w[((size_t)(tile * nt + n) * Cin + ci) * K + j];
+                            const float hi = tf32_rn_host(v);
+                            const size_t stage = (((size_t)tile * t.nchunks + c) * K + j) * parts;
+                            p[((stage * ncg + g) * nt + n) * 4 + e] = hi;
+                            if (x3) p[(((stage + 1) * ncg + g) * nt + n) * 4 + e] = tf32_rn_host(v - hi);
                         }
     t.w = up(p);
     return t;
@@ -82,7 +94,8 @@ inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>&
 //   out[t*u + r][co] = sum_m sum_ci x[t + floor((r+p)/u) - m][ci] * w[ci][co][(r+p)%u + m*u]
 // -> an ordinary conv over input-rate time with Kp taps (union of the per-phase offsets), N = u*Cout columns ordered
 // (r, co), structural zeros where a phase does not use a tap.  wT: [Cin][Cout][K] (weight-norm folded).
-inline TcConvW tc_pack_upsample(std::function<float*(const std::vector<float>&)>& up, const std::vector<float>& wT, int Cin, int Cout, int K, int u) {
+inline TcConvW tc_pack_upsample(std::function<float*(const std::vector<float>&)>& up, const std::vector<float>& wT, int Cin, int Cout, int K, int u,
+                                int kc = 0) {
     const int p = (K - u) / 2, taps = K / u;
     int omin = 1 << 30, omax = -(1 << 30);
     for (int r = 0; r < u; r++)
@@ -98,7 +111,7 @@ inline TcConvW tc_pack_upsample(std::function<float*(const std::vector<float>&)>
                     w[(((size_t)(r * Cout + co)) * Cin + ci) * Kp + tap] = wT[((size_t)ci * Cout + co) * K + j];
         }
     int nt = std::min(u * Cout, 256);
-    TcConvW t = tc_pack_weights(up, w, u * Cout, Cin, Kp, nt);
+    TcConvW t = tc_pack_weights(up, w, u * Cout, Cin, Kp, nt, 0, kc);
     t.ups_u = u; t.ups_cout = Cout;
     return t;
 }
@@ -107,7 +120,7 @@ struct TcParams {
     const float* x; float* y; const float* w; const float* bias; const float* res; const float* bias_b; const int* lens;
     int Cin_total, cin_off, Cout_total, cout_off, res_C_total, res_c_off, bias_b_stride;
     int nt;           // columns per N tile
-    int T, B, K, dil, pad, KC, nchunks, R, nws, MT;
+    int T, B, K, dil, pad, KC, nchunks, R, nws, nas, MT, x3;
     uint32_t a_stage_bytes, w_stage_bytes, tmem_cols, idesc;
     float in_slope, out_scale;
     int accumulate, relu, res_mode, in_mask, out_mask, ups_u, ups_cout;
@@ -197,16 +210,18 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
     const int t0 = blockIdx.x * 128 * MT, n0 = blockIdx.y * p.nt, b = blockIdx.z;
     const int nt = p.nt;
     uint8_t* sA = smem;
-    uint8_t* sW = smem + 2 * p.a_stage_bytes;
+    const int NAS = p.nas;
+    uint8_t* sW = smem + (size_t)NAS * p.a_stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)p.nws * p.w_stage_bytes);
-    // barrier map: [0,2) a_full, [2,4) a_ready, [4,6) a_empty, [6,6+nws) w_full, [6+nws,6+2nws) w_empty, acc_full, acc_init
+    // barrier map: a_full[NAS], a_ready[NAS], a_empty[NAS], w_full[nws], w_empty[nws], acc_full, acc_init
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    const int B_AFULL = 0, B_AREADY = 2, B_AEMPTY = 4, B_WFULL = 6, B_WEMPTY = 6 + p.nws, B_ACC = 6 + 2 * p.nws, B_INIT = B_ACC + 1;
+    const int B_AFULL = 0, B_AREADY = NAS, B_AEMPTY = 2 * NAS, B_WFULL = 3 * NAS, B_WEMPTY = 3 * NAS + p.nws, B_ACC = 3 * NAS + 2 * p.nws,
+              B_INIT = B_ACC + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_INIT + 1);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; i++) { mbar_init(BAR(B_AFULL + i), 1); mbar_init(BAR(B_AREADY + i), 128); mbar_init(BAR(B_AEMPTY + i), 1); }
+        for (int i = 0; i < NAS; i++) { mbar_init(BAR(B_AFULL + i), 1); mbar_init(BAR(B_AREADY + i), 128); mbar_init(BAR(B_AEMPTY + i), 1); }
         for (int i = 0; i < p.nws; i++) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
         mbar_init(BAR(B_ACC), 1);
         mbar_init(BAR(B_INIT), 128);
@@ -233,49 +248,61 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
             // ===== TMA producer: activation chunk c+1 is requested before the weight tiles of chunk c
             const uint32_t row_bytes = (uint32_t)(r_hi - r_lo) * 16u;
             auto load_a = [&](int c) {
-                const int sa = c & 1;
-                mbar_wait(BAR(B_AEMPTY + sa), ((c >> 1) & 1) ^ 1);
+                const int sa = c % NAS;
+                mbar_wait(BAR(B_AEMPTY + sa), ((c / NAS) & 1) ^ 1);
                 mbar_expect_tx(BAR(B_AFULL + sa), row_bytes * ncg);
                 const float* src = p.x + (((size_t)b * (p.Cin_total / 4) + p.cin_off / 4 + (size_t)c * ncg) * p.T + (t0 - p.pad + r_lo)) * 4;
                 uint32_t dst = smem_u32(sA + (size_t)sa * p.a_stage_bytes) + (uint32_t)r_lo * 16u;
                 for (int g = 0; g < ncg; g++) bulk_g2s(dst + (uint32_t)g * R * 16u, src + (size_t)g * p.T * 4, row_bytes, BAR(B_AFULL + sa));
             };
-            load_a(0);
+            for (int c = 0; c < NAS - 1 && c < p.nchunks; c++) load_a(c);
             int wi = 0;
-            const float* wtile = p.w + (size_t)blockIdx.y * p.nchunks * p.K * p.KC * nt;
+            const float* wtile = p.w + (size_t)blockIdx.y * p.nchunks * p.K * (p.w_stage_bytes / 4);
             for (int c = 0; c < p.nchunks; c++) {
-                if (c + 1 < p.nchunks) load_a(c + 1);
+                if (c + NAS - 1 < p.nchunks) load_a(c + NAS - 1);
                 for (int j = 0; j < p.K; j++, wi++) {
                     const int sw = wi % p.nws;
                     mbar_wait(BAR(B_WEMPTY + sw), ((wi / p.nws) & 1) ^ 1);
                     mbar_expect_tx(BAR(B_WFULL + sw), p.w_stage_bytes);
-                    bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), wtile + ((size_t)c * p.K + j) * p.KC * nt, p.w_stage_bytes,
+                    bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), wtile + ((size_t)c * p.K + j) * (p.w_stage_bytes / 4), p.w_stage_bytes,
                              BAR(B_WFULL + sw));
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // ===== MMA issuer: per weight tile, MT x KC/8 tcgen05.mma (M=128, N=nt, K=8 tf32), always accumulating
+            // ===== MMA issuer: per weight tile, MT x KC/8 tcgen05.mma (M=128, N=nt, K=8 tf32), always accumulating.
+            // Descriptors are advanced with 64-bit adds on the (addr >> 4) field: this single thread is the issue
+            // bottleneck for narrow N, so the loop body is kept to a handful of integer instructions.
             const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)nt * 16u;
+            const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R), b_kstep = (uint64_t)(2u * (uint32_t)nt);  // two channel groups per MMA
+            const uint64_t a_lo = (uint64_t)((uint32_t)ncg * R), w_lo = (uint64_t)((uint32_t)ncg * nt);     // x3: lo halves
+            const int nk = p.KC / 8;
             int wi = 0;
             mbar_wait(BAR(B_INIT), 0);
             fence_after();
             for (int c = 0; c < p.nchunks; c++) {
-                const int sa = c & 1;
-                mbar_wait(BAR(B_AREADY + sa), (c >> 1) & 1);
+                const int sa = c % NAS;
+                mbar_wait(BAR(B_AREADY + sa), (c / NAS) & 1);
                 fence_after();
-                const uint32_t a_base = smem_u32(sA + (size_t)sa * p.a_stage_bytes);
+                const uint64_t a_desc0 = make_desc(smem_u32(sA + (size_t)sa * p.a_stage_bytes), a_lbo, 128u);
                 for (int j = 0; j < p.K; j++, wi++) {
                     const int sw = wi % p.nws;
                     mbar_wait(BAR(B_WFULL + sw), (wi / p.nws) & 1);
                     fence_after();
-                    const uint32_t w_base = smem_u32(sW + (size_t)sw * p.w_stage_bytes);
+                    const uint64_t b_desc0 = make_desc(smem_u32(sW + (size_t)sw * p.w_stage_bytes), b_lbo, 128u);
                     for (int mt = 0; mt < MT; mt++) {
-                        for (int kk = 0; kk < p.KC / 8; kk++) {
-                            uint64_t ad = make_desc(a_base + ((uint32_t)(2 * kk) * R + (uint32_t)(mt * 128 + j * p.dil)) * 16u, a_lbo, 128u);
-                            uint64_t bd = make_desc(w_base + (uint32_t)(2 * kk) * b_lbo, b_lbo, 128u);
-                            umma_tf32(tmem + (uint32_t)(mt * nt), ad, bd, p.idesc, 1u);
+                        uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(mt * 128 + j * p.dil), bd = b_desc0;
+                        const uint32_t d = tmem + (uint32_t)(mt * nt);
+                        if (!p.x3) {
+                            for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_tf32(d, ad, bd, p.idesc, 1u);
+                        } else {
+                            // a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo   (lo*lo ~ 2^-22 relative, dropped)
+                            for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) {
+                                umma_tf32(d, ad + a_lo, bd, p.idesc, 1u);
+                                umma_tf32(d, ad, bd + w_lo, p.idesc, 1u);
+                                umma_tf32(d, ad, bd, p.idesc, 1u);
+                            }
                         }
                     }
                     umma_commit(BAR(B_WEMPTY + sw));
@@ -328,19 +355,21 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
         // ===== operand prologue on the staged tile (generic proxy), then hand over to the async proxy
         const float slope = p.in_slope;
         for (int c = 0; c < p.nchunks; c++) {
-            const int sa = c & 1;
-            mbar_wait(BAR(B_AFULL + sa), (c >> 1) & 1);
+            const int sa = c % NAS;
+            mbar_wait(BAR(B_AFULL + sa), (c / NAS) & 1);
             float4* A = reinterpret_cast<float4*>(sA + (size_t)sa * p.a_stage_bytes);
             for (int g = 0; g < ncg; g++) {
                 float4* Ag = A + (size_t)g * R;
                 for (int r = tid2; r < R; r += 128) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), lo = v;
                     if (r >= r_lo && r < r_mask_hi) {
-                        v = Ag[r];
-                        v.x = to_tf32(lrelu(v.x, slope)); v.y = to_tf32(lrelu(v.y, slope));
-                        v.z = to_tf32(lrelu(v.z, slope)); v.w = to_tf32(lrelu(v.w, slope));
+                        const float4 a = Ag[r];
+                        const float ax = lrelu(a.x, slope), ay = lrelu(a.y, slope), az = lrelu(a.z, slope), aw = lrelu(a.w, slope);
+                        v.x = to_tf32(ax); v.y = to_tf32(ay); v.z = to_tf32(az); v.w = to_tf32(aw);
+                        lo.x = to_tf32(ax - v.x); lo.y = to_tf32(ay - v.y); lo.z = to_tf32(az - v.z); lo.w = to_tf32(aw - v.w);
                     }
                     Ag[r] = v;
+                    if (p.x3) Ag[(size_t)ncg * R + r] = lo;
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -400,13 +429,20 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     const int halo = (w.K - 1) * e.dil;
     p.MT = MT;
     p.R = MT * 128 + halo;
-    p.a_stage_bytes = (uint32_t)(p.KC * p.R * 4);
-    p.w_stage_bytes = (uint32_t)(p.KC * nt * 4);
+    p.x3 = w.x3;
+    const int parts = w.x3 ? 2 : 1;
+    p.a_stage_bytes = (uint32_t)(p.KC * p.R * 4 * parts);
+    p.w_stage_bytes = (uint32_t)(p.KC * nt * 4 * parts);
     // shared memory per CTA is capped (~100 KB) so that two CTAs co-reside per SM: one CTA's accumulator init / tail
     // overlaps the other's MMA main loop
     const long long nctas = (long long)cdiv(p.T, 128 * MT) * ntiles * p.B;
-    const uint32_t budget = (nctas > num_sms && nt <= 128) ? 100 * 1024 : 200 * 1024;
-    int nws = ((int)budget - 2 * (int)p.a_stage_bytes - 512) / (int)p.w_stage_bytes;
+    static const int smem_kb_env = getenv("BV2_TC_SMEM_KB") ? atoi(getenv("BV2_TC_SMEM_KB")) : 48;  // tuning knob (experiments)
+    const uint32_t budget = (nctas > num_sms && nt <= 128) ? (uint32_t)smem_kb_env * 1024 : 200 * 1024;
+    // activation pipeline depth: up to 4 stages when the K loop is long (hides TMA + prologue latency per chunk)
+    int nas = std::min(3, std::max(2, p.nchunks));
+    while (nas > 2 && (size_t)nas * p.a_stage_bytes + 4 * (size_t)p.w_stage_bytes + 1024 > budget) nas--;
+    p.nas = nas;
+    int nws = ((int)budget - nas * (int)p.a_stage_bytes - 1024) / (int)p.w_stage_bytes;
     p.nws = std::max(2, std::min(nws, 6));
     uint32_t cols = 32; while ((int)cols < MT * nt) cols <<= 1;
     p.tmem_cols = cols;
@@ -415,7 +451,8 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     p.in_mask = e.in_mask; p.out_mask = e.out_mask; p.ups_u = w.ups_u; p.ups_cout = w.ups_cout;
     if (p.in_mask || p.out_mask) BV2_CHECK(e.lens != nullptr, "mask needs lens");
     BV2_CHECK(!(p.relu && (p.res_mode || p.accumulate)), "relu cannot be combined with residual/accumulate (accumulator-init fusion)");
-    const size_t smem = 2 * (size_t)p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + (size_t)(8 + 2 * p.nws) * 8 + 16;
+    const size_t smem = (size_t)p.nas * p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + (size_t)(3 * p.nas + 2 * p.nws + 2) * 8 + 16;
+    BV2_CHECK(smem <= 227 * 1024, "tc_conv1d shared memory");
     static bool attr_set = false;
     if (!attr_set) {
         BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -139,6 +139,48 @@ static int run_ups(int Cin, int Cout, int K, int u, int T, int B, int iters) {
     return ok ? 0 : 1;
 }
 
+// 3xTF32 accuracy: compare against a double-precision conv on the UNROUNDED operands
+static int run_x3(int Cin, int Cout, int K, int T, int nt) {
+    std::mt19937 rng(Cin + Cout * 3 + K);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    const int B = 1;
+    std::vector<float> x((size_t)Cin * T), w((size_t)Cout * Cin * K), bias(Cout);
+    for (auto& v : x) v = nd(rng);
+    for (auto& v : w) v = nd(rng) / std::sqrt((float)(Cin * K));
+    for (auto& v : bias) v = nd(rng);
+    std::vector<float> xc(x.size());
+    for (int c = 0; c < Cin; c++) for (int t = 0; t < T; t++) xc[((size_t)(c / 4) * T + t) * 4 + (c & 3)] = x[(size_t)c * T + t];
+    std::function<float*(const std::vector<float>&)> upf = up;
+    double errs[2];
+    for (int mode = 0; mode < 2; mode++) {
+        TcConvW tw = tc_pack_weights(upf, w, Cout, Cin, K, nt, mode);
+        Act ax; ax.B = B; ax.C = Cin; ax.T = T; ax.p = up(xc);
+        std::vector<float> y0((size_t)Cout * T, 0.f);
+        Act ay; ay.B = B; ay.C = Cout; ay.T = T; ay.p = up(y0);
+        float* dbias = up(bias);
+        TcEpi e;
+        tc_conv1d(tw, dbias, ax, ay, e, 0, 148);
+        cudaError_t er = cudaDeviceSynchronize();
+        if (er != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(er)); return 1; }
+        std::vector<float> got(y0.size());
+        cudaMemcpy(got.data(), ay.p, got.size() * 4, cudaMemcpyDeviceToHost);
+        const int pad = (K - 1) / 2;
+        double maxerr = 0;
+        for (int co = 0; co < Cout; co++)
+            for (int t = 0; t < T; t++) {
+                double s = bias[co];
+                for (int ci = 0; ci < Cin; ci++)
+                    for (int j = 0; j < K; j++) { int tt = t + j - pad; if (tt >= 0 && tt < T) s += (double)x[(size_t)ci * T + tt] * w[((size_t)co * Cin + ci) * K + j]; }
+                maxerr = std::max(maxerr, std::fabs((double)got[((size_t)(co / 4) * T + t) * 4 + (co & 3)] - s));
+            }
+        errs[mode] = maxerr;
+    }
+    bool ok = errs[1] < 2e-5 && errs[1] < errs[0] * 0.05;
+    printf("%s X3 Cin=%4d Cout=%3d K=%d T=%d nt=%d : max err tf32 %.3e, 3xtf32 %.3e\n", ok ? "PASS" : "FAIL", Cin, Cout, K, T, nt, errs[0], errs[1]);
+    fflush(stdout);
+    return ok ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
     int fails = 0;
     bool perf = argc > 1;
@@ -158,6 +200,9 @@ int main(int argc, char** argv) {
         fails += run_case(192, 576, 1, 1, 1573, 2, 1.f, false, false, 1.f, perf ? 10 : 0);   // fused QKV
         fails += run_case(96, 192, 1, 1, 700, 1, 1.f, false, false, 1.f, 0);
         fails += run_case(192, 512, 7, 1, 1573, 1, 1.f, false, false, 1.f, perf ? 10 : 0);   // conv_pre
+        fails += run_x3(32, 32, 1, 100, 32);
+        fails += run_x3(192, 192, 3, 256, 32);
+        fails += run_x3(768, 192, 3, 256, 32);
         fails += run_ups(512, 256, 16, 8, 300, 1, 0);
         fails += run_ups(256, 128, 16, 8, 257, 2, 0);
         fails += run_ups(128, 64, 8, 2, 1000, 1, 0);

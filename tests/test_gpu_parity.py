@@ -40,23 +40,26 @@ def _oracle_stages(meta):
     return cfg, sd, inp, nw, nz, kw, st
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)  # tf32 engine: 3xTF32 error-compensated tensor-core convs here
 @pytest.mark.parametrize("name", ["tflow_b1", "tflow_b3"])
-def test_text_encoder_stage(engines, name):
+def test_text_encoder_stage(engines, name, precision):
     meta, gold = load_golden(name)
     cfg, sd, inp, nw, nz, kw = case_inputs(meta)
-    eng = engines(True, "fp32")
+    eng = engines(True, precision)
     x, m, logs = eng.text_encoder(inp["x"], inp["x_lengths"], inp["sid"], inp["tone"], inp["language"], inp["bert"],
                                   inp["ja_bert"], inp["en_bert"])
     for got, key in ((x, "x"), (m, "m_p_tok"), (logs, "logs_p_tok")):
         err = float((got.cpu() - gold[key]).abs().max())
+        print(f"[{name}/{precision}] {key} max-abs err {err:.2e}")
         assert err < TOL_FP32, (key, err)
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("name", ["tflow_b1", "tflow_b3"])
-def test_duration_stage(engines, name):
+def test_duration_stage(engines, name, precision):
     meta, gold = load_golden(name)
     cfg, sd, inp, nw, nz, kw = case_inputs(meta)
-    eng = engines(True, "fp32")
+    eng = engines(True, precision)
     a, b = eng.duration(gold["x"], inp["x_lengths"], inp["sid"], nw, kw["noise_scale_w"])
     assert float((a.cpu() - gold["logw_sdp"]).abs().max()) < TOL_FP32
     assert float((b.cpu() - gold["logw_dp"]).abs().max()) < TOL_FP32
