@@ -410,6 +410,192 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Persistent variant for narrow layers (Cin <= 32: Generator stages 3/4 = 36 of the 90 MRF convs, the last ups).
+// Those launches have thousands of 128-row tiles with only K * Cin/8 tiny MMAs each, so the one-tile-per-CTA kernel
+// is bound by its per-tile latency chain (launch, TMEM alloc, barrier init, TMA round trip, tail).  Here each CTA
+//   * keeps ALL weight taps resident in shared memory (<= 45 KB, loaded once),
+//   * walks tiles blockIdx.x, +gridDim.x, ... with a 3-deep TMA ring for the activation tiles (producer runs ahead),
+//   * double-buffers the TMEM accumulator: the epilogue warps pre-load tile i+1's accumulator (bias/residual) and
+//     drain tile i-1 while the MMA warp works on tile i.
+// 320 threads: warp 0 producer, warp 1 MMA issuer, warps 2-5 operand prologue, warps 6-9 accumulator init + tail.
+__global__ void __launch_bounds__(320) k_tc_conv1d_persist(TcParams p, int mtiles, int ntiles_total) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = p.nt, NAS = p.nas, R = p.R, ncg = p.KC / 4;
+    uint8_t* sWt = smem;                                   // resident weights: [K][ncg][nt][4]
+    const uint32_t w_bytes = (uint32_t)(p.K * p.KC * nt * 4);
+    uint8_t* sA = smem + ((w_bytes + 127u) & ~127u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)NAS * p.a_stage_bytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    const int B_WFULL = 0, B_AFULL = 1, B_AREADY = 1 + NAS, B_AEMPTY = 1 + 2 * NAS, B_INIT = 1 + 3 * NAS, B_ACC = 3 + 3 * NAS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACC + 2);
+
+    if (threadIdx.x == 0) {
+        mbar_init(BAR(B_WFULL), 1);
+        for (int i = 0; i < NAS; i++) { mbar_init(BAR(B_AFULL + i), 1); mbar_init(BAR(B_AREADY + i), 128); mbar_init(BAR(B_AEMPTY + i), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(BAR(B_INIT + i), 128); mbar_init(BAR(B_ACC + i), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int n_mine = (ntiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(BAR(B_WFULL), w_bytes);
+            bulk_g2s(smem_u32(sWt), p.w, w_bytes, BAR(B_WFULL));
+            for (int i = 0; i < n_mine; i++) {
+                const int tile = blockIdx.x + i * gridDim.x, b = tile / mtiles, t0 = (tile - b * mtiles) * 128;
+                const int r_lo = max(0, p.pad - t0), r_hi = min(R, p.T - (t0 - p.pad));
+                const uint32_t row_bytes = (uint32_t)(r_hi - r_lo) * 16u;
+                const int sa = i % NAS;
+                mbar_wait(BAR(B_AEMPTY + sa), ((i / NAS) & 1) ^ 1);
+                mbar_expect_tx(BAR(B_AFULL + sa), row_bytes * ncg);
+                const float* src = p.x + (((size_t)b * (p.Cin_total / 4) + p.cin_off / 4) * p.T + (t0 - p.pad + r_lo)) * 4;
+                const uint32_t dst = smem_u32(sA + (size_t)sa * p.a_stage_bytes) + (uint32_t)r_lo * 16u;
+                for (int g = 0; g < ncg; g++) bulk_g2s(dst + (uint32_t)g * R * 16u, src + (size_t)g * p.T * 4, row_bytes, BAR(B_AFULL + sa));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)nt * 16u;
+            const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R), b_kstep = (uint64_t)(2u * (uint32_t)nt);
+            const uint64_t b_tap = (uint64_t)((uint32_t)ncg * nt);  // next tap's weight tile, in 16-byte units
+            const int nk = p.KC / 8;
+            const uint64_t b_desc0 = make_desc(smem_u32(sWt), b_lbo, 128u);
+            mbar_wait(BAR(B_WFULL), 0);
+            for (int i = 0; i < n_mine; i++) {
+                const int sa = i % NAS, ab = i & 1;
+                mbar_wait(BAR(B_INIT + ab), (i >> 1) & 1);
+                mbar_wait(BAR(B_AREADY + sa), (i / NAS) & 1);
+                fence_after();
+                const uint64_t a_desc0 = make_desc(smem_u32(sA + (size_t)sa * p.a_stage_bytes), a_lbo, 128u);
+                const uint32_t d = tmem + (uint32_t)(ab * nt);
+                uint64_t bd_tap = b_desc0;
+                for (int j = 0; j < p.K; j++, bd_tap += b_tap) {
+                    uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(j * p.dil), bd = bd_tap;
+                    for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_tf32(d, ad, bd, p.idesc, 1u);
+                }
+                umma_commit(BAR(B_AEMPTY + sa));
+                umma_commit(BAR(B_ACC + ab));
+            }
+        }
+    } else if (warp < 6) {
+        // ===== operand prologue
+        const int tid2 = threadIdx.x - 64;
+        const float slope = p.in_slope;
+        for (int i = 0; i < n_mine; i++) {
+            const int tile = blockIdx.x + i * gridDim.x, b = tile / mtiles, t0 = (tile - b * mtiles) * 128;
+            const int len = p.lens ? p.lens[b] : p.T;
+            const int r_lo = max(0, p.pad - t0), r_hi = min(R, p.T - (t0 - p.pad));
+            const int r_mask_hi = p.in_mask ? min(r_hi, len - (t0 - p.pad)) : r_hi;
+            const int sa = i % NAS;
+            mbar_wait(BAR(B_AFULL + sa), (i / NAS) & 1);
+            float4* A = reinterpret_cast<float4*>(sA + (size_t)sa * p.a_stage_bytes);
+            for (int g = 0; g < ncg; g++) {
+                float4* Ag = A + (size_t)g * R;
+                for (int r = tid2; r < R; r += 128) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r >= r_lo && r < r_mask_hi) {
+                        v = Ag[r];
+                        v.x = to_tf32(lrelu(v.x, slope)); v.y = to_tf32(lrelu(v.y, slope));
+                        v.z = to_tf32(lrelu(v.z, slope)); v.w = to_tf32(lrelu(v.w, slope));
+                    }
+                    Ag[r] = v;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(BAR(B_AREADY + sa));
+        }
+    } else {
+        // ===== accumulator init (tile i+1) and tail (tile i), double-buffered TMEM
+        const int q = warp & 3;
+        const size_t cstride = (size_t)p.T;
+        const float sgn = p.res_mode == 2 ? -1.f : 1.f;
+        auto init_tile = [&](int i) {
+            const int tile = blockIdx.x + i * gridDim.x, b = tile / mtiles, t0 = (tile - b * mtiles) * 128;
+            const int t = t0 + q * 32 + lane;
+            const bool ok = t < p.T;
+            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt);
+            for (int col = 0; col < nt; col += 16) {
+                uint32_t v[16];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const int n = col + 4 * g;
+                    int co = n, tt = t;
+                    size_t tstride = cstride;
+                    if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; tstride = cstride * p.ups_u; }
+                    float4 o = *reinterpret_cast<const float4*>(p.bias + co);
+                    if (p.bias_b) {
+                        const float4 b2 = *reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + co);
+                        o.x += b2.x; o.y += b2.y; o.z += b2.z; o.w += b2.w;
+                    }
+                    if (ok) {
+                        if (p.res_mode) {
+                            const float4 r = reinterpret_cast<const float4*>(p.res)[((size_t)b * (p.res_C_total / 4) + (p.res_c_off + co) / 4) * tstride + tt];
+                            if (p.res_mode == 1) { o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+                            else { o.x -= r.x; o.y -= r.y; o.z -= r.z; o.w -= r.w; }
+                        }
+                        if (p.accumulate) {
+                            const float4 a = reinterpret_cast<const float4*>(p.y)[((size_t)b * (p.Cout_total / 4) + (p.cout_off + co) / 4) * tstride + tt];
+                            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+                        }
+                    }
+                    v[4 * g] = __float_as_uint(o.x); v[4 * g + 1] = __float_as_uint(o.y); v[4 * g + 2] = __float_as_uint(o.z); v[4 * g + 3] = __float_as_uint(o.w);
+                }
+                tmem_st16(trow + (uint32_t)col, v);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            fence_before();
+            mbar_arrive(BAR(B_INIT + (i & 1)));
+        };
+        if (n_mine > 0) init_tile(0);
+        for (int i = 0; i < n_mine; i++) {
+            if (i + 1 < n_mine) init_tile(i + 1);
+            const int tile = blockIdx.x + i * gridDim.x, b = tile / mtiles, t0 = (tile - b * mtiles) * 128;
+            const int len = p.lens ? p.lens[b] : p.T;
+            const int t = t0 + q * 32 + lane;
+            const bool ok = t < p.T;
+            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt);
+            const float s = ((p.out_mask && t >= len) ? 0.f : p.out_scale) * sgn;
+            mbar_wait(BAR(B_ACC + (i & 1)), (i >> 1) & 1);
+            fence_after();
+            for (int col = 0; col < nt; col += 16) {
+                uint32_t v[16];
+                tmem_ld16(trow + (uint32_t)col, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (!ok) continue;
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const int n = col + 4 * g;
+                    int co = n, tt = t;
+                    size_t tstride = cstride;
+                    if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; tstride = cstride * p.ups_u; }
+                    float4 o = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    o.x *= s; o.y *= s; o.z *= s; o.w *= s;
+                    reinterpret_cast<float4*>(p.y)[((size_t)b * (p.Cout_total / 4) + (p.cout_off + co) / 4) * tstride + tt] = o;
+                }
+            }
+            fence_before();  // order this tile's tcgen05.ld before the next init's tcgen05.st on the same columns
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+    }
+}
+
 // x: c4 input [B][x.C/4][T][4]; y: c4 output ([B][y.C/4][T*max(1,ups_u)][4]).  Channel windows via e.cin_off/e.cout_off.
 inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const Act& y, const TcEpi& e, cudaStream_t st, int num_sms) {
     const int u = w.ups_u ? w.ups_u : 1;
@@ -457,6 +643,25 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     if (!attr_set) {
         BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
+    }
+    static const int persist_env = getenv("BV2_TC_PERSIST") ? atoi(getenv("BV2_TC_PERSIST")) : 1;
+    const size_t w_all = (size_t)p.K * p.KC * nt * 4;
+    if (persist_env && p.nchunks == 1 && ntiles == 1 && !w.x3 && w_all <= 64 * 1024 && nctas >= 2 * num_sms) {
+        // narrow layer with many tiles: persistent CTAs, resident weights, double-buffered TMEM
+        p.nas = 3;
+        const size_t wb = (w_all + 127) & ~(size_t)127;
+        const size_t smem_p = wb + (size_t)p.nas * p.a_stage_bytes + (size_t)(3 * p.nas + 5) * 8 + 16;
+        uint32_t pc = 32; while ((int)pc < 2 * nt) pc <<= 1;
+        p.tmem_cols = pc;
+        static bool attr2 = false;
+        if (!attr2) { BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr2 = true; }
+        const int per_sm = smem_p <= 72 * 1024 ? 3 : (smem_p <= 110 * 1024 ? 2 : 1);
+        const int mtiles = cdiv(p.T, 128);
+        const int total = mtiles * p.B;
+        const int grid_p = std::min(total, per_sm * num_sms);
+        k_tc_conv1d_persist<<<grid_p, 320, smem_p, st>>>(p, mtiles, total);
+        BV2_CUDA(cudaGetLastError());
+        return;
     }
     dim3 grid(cdiv(p.T, 128 * MT), ntiles, p.B);
     k_tc_conv1d<<<grid, 192, smem, st>>>(p);
