@@ -429,7 +429,7 @@ void bv2_engine::finalize() {
             for (int co = 0; co < u.Cout; co++)
                 for (int j = 0; j < u.K; j++) p[((size_t)ci * u.K + j) * u.Cout + co] = w[((size_t)ci * u.Cout + co) * u.K + j];
         u.w = upload(p); u.b = upload(W("dec.ups." + std::to_string(i) + ".bias").data);
-        if (tc) u.tc = tc_pack_upsample(*this_uploader(), w, u.Cin, u.Cout, u.K, u.u, (i == 0 || u.Cin <= 32) ? 32 : 16);
+        if (tc) u.tc = tc_pack_upsample(*this_uploader(), w, u.Cin, u.Cout, u.K, u.u, 32);
         ups.push_back(u);
         ch /= 2;
         for (int j = 0; j < c.n_resblock_kernels; j++) {
@@ -437,7 +437,7 @@ void bv2_engine::finalize() {
             std::string r = "dec.resblocks." + std::to_string(i * c.n_resblock_kernels + j);
             for (int d = 0; d < c.n_dilations; d++) {
                 rb.dil.push_back(c.resblock_dilation_sizes[j][d]);
-                const int kc = (ch >= 256 || ch <= 32) ? 32 : 16;  // stage 0: few CTAs -> short chunk loop; ch <= 32: single chunk (persistent kernel)
+                const int kc = 32;  // persistent kernels hide latency with deep rings: fewer, larger chunks
                 rb.c1.push_back(conv_from(r + ".convs1." + std::to_string(d), true, tc, 0, kc));
                 rb.c2.push_back(conv_from(r + ".convs2." + std::to_string(d), true, tc, 0, kc));
             }

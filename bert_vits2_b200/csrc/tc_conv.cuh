@@ -197,12 +197,105 @@ __device__ __forceinline__ float to_tf32(float x) {
 
 }  // namespace tc
 
+namespace tc {
+
+// Pre-load one 128-row x nt accumulator tile: bias (+ per-batch bias) (+/- residual) (+ previous output).
+// All global loads of a 32-column batch are issued before the first tcgen05.st (memory-level parallelism: the
+// epilogue warps are the only threads touching residual/output tensors).
+template <int NG>
+__device__ __forceinline__ void acc_init_tile(const TcParams& p, uint32_t trow, int b, int t, int n0, int nt) {
+    const bool ok = t < p.T;
+    const size_t tstride = (size_t)p.T * (p.ups_u ? p.ups_u : 1);
+    const float4* resb = p.res ? reinterpret_cast<const float4*>(p.res) + (size_t)b * (p.res_C_total / 4) * tstride : nullptr;
+    const float4* yb = reinterpret_cast<const float4*>(p.y) + (size_t)b * (p.Cout_total / 4) * tstride;
+    const float sg = p.res_mode == 1 ? 1.f : -1.f;  // mode 2: tail negates -> res - (conv + bias)
+    for (int col0 = 0; col0 < nt; col0 += 4 * NG) {
+        float4 o[NG];
+        int cos[NG], tts[NG];
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+            const int n = n0 + col0 + 4 * g;
+            int co = n, tt = t;
+            if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; }
+            cos[g] = co; tts[g] = tt;
+            if (col0 + 4 * g < nt) {
+                o[g] = *reinterpret_cast<const float4*>(p.bias + co);
+                if (p.bias_b) {
+                    const float4 b2 = *reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + co);
+                    o[g].x += b2.x; o[g].y += b2.y; o[g].z += b2.z; o[g].w += b2.w;
+                }
+            }
+        }
+        if (ok && p.res_mode) {
+            float4 r[NG];
+#pragma unroll
+            for (int g = 0; g < NG; g++) if (col0 + 4 * g < nt) r[g] = resb[(size_t)((p.res_c_off + cos[g]) / 4) * tstride + tts[g]];
+#pragma unroll
+            for (int g = 0; g < NG; g++) if (col0 + 4 * g < nt) { o[g].x += sg * r[g].x; o[g].y += sg * r[g].y; o[g].z += sg * r[g].z; o[g].w += sg * r[g].w; }
+        }
+        if (ok && p.accumulate) {
+            float4 a[NG];
+#pragma unroll
+            for (int g = 0; g < NG; g++) if (col0 + 4 * g < nt) a[g] = yb[(size_t)((p.cout_off + cos[g]) / 4) * tstride + tts[g]];
+#pragma unroll
+            for (int g = 0; g < NG; g++) if (col0 + 4 * g < nt) { o[g].x += a[g].x; o[g].y += a[g].y; o[g].z += a[g].z; o[g].w += a[g].w; }
+        }
+#pragma unroll
+        for (int h = 0; h < NG / 4; h++) {
+            if (col0 + 16 * h < nt) {
+                uint32_t v[16];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    v[4 * g] = __float_as_uint(o[4 * h + g].x); v[4 * g + 1] = __float_as_uint(o[4 * h + g].y);
+                    v[4 * g + 2] = __float_as_uint(o[4 * h + g].z); v[4 * g + 3] = __float_as_uint(o[4 * h + g].w);
+                }
+                tmem_st16(trow + (uint32_t)(col0 + 16 * h), v);
+            }
+        }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// Drain one accumulator tile: TMEM -> [relu] -> scale/mask -> c4 global (16-byte stores, coalesced across a warp).
+template <int NG>
+__device__ __forceinline__ void acc_tail_tile(const TcParams& p, uint32_t trow, int b, int t, int n0, int nt, int len) {
+    const bool ok = t < p.T;
+    const size_t tstride = (size_t)p.T * (p.ups_u ? p.ups_u : 1);
+    float4* yb = reinterpret_cast<float4*>(p.y) + (size_t)b * (p.Cout_total / 4) * tstride;
+    const float s = ((p.out_mask && t >= len) ? 0.f : p.out_scale) * (p.res_mode == 2 ? -1.f : 1.f);
+    for (int col0 = 0; col0 < nt; col0 += 4 * NG) {
+        uint32_t v[NG / 4][16];
+#pragma unroll
+        for (int h = 0; h < NG / 4; h++) if (col0 + 16 * h < nt) tmem_ld16(trow + (uint32_t)(col0 + 16 * h), v[h]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!ok) continue;
+#pragma unroll
+        for (int h = 0; h < NG / 4; h++) {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                if (col0 + 16 * h + 4 * g < nt) {
+                    const int n = n0 + col0 + 16 * h + 4 * g;
+                    int co = n, tt = t;
+                    if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; }
+                    float4 o = make_float4(__uint_as_float(v[h][4 * g]), __uint_as_float(v[h][4 * g + 1]), __uint_as_float(v[h][4 * g + 2]),
+                                           __uint_as_float(v[h][4 * g + 3]));
+                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    o.x *= s; o.y *= s; o.z *= s; o.w *= s;
+                    yb[(size_t)((p.cout_off + co) / 4) * tstride + tt] = o;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace tc
+
 // grid: (M blocks of MT*128 time steps, N tiles, B)
 //
 // Accumulator-init fusion: before the first MMA the epilogue warps pre-load  bias (+ per-batch bias) (+/- residual)
 // (+ previous output when accumulating)  into the TMEM accumulator with tcgen05.st while the first TMA loads are in
 // flight; every MMA then accumulates, and the tail is only  TMEM -> [relu] -> scale/mask -> store.
-__global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
+__global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -245,21 +338,23 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
 
     if (warp == 0) {
         if (lane == 0) {
-            // ===== TMA producer: activation chunk c+1 is requested before the weight tiles of chunk c
+            // ===== activation producer (TMA bulk copies, one contiguous run per channel group)
             const uint32_t row_bytes = (uint32_t)(r_hi - r_lo) * 16u;
-            auto load_a = [&](int c) {
+            for (int c = 0; c < p.nchunks; c++) {
                 const int sa = c % NAS;
                 mbar_wait(BAR(B_AEMPTY + sa), ((c / NAS) & 1) ^ 1);
                 mbar_expect_tx(BAR(B_AFULL + sa), row_bytes * ncg);
                 const float* src = p.x + (((size_t)b * (p.Cin_total / 4) + p.cin_off / 4 + (size_t)c * ncg) * p.T + (t0 - p.pad + r_lo)) * 4;
                 uint32_t dst = smem_u32(sA + (size_t)sa * p.a_stage_bytes) + (uint32_t)r_lo * 16u;
                 for (int g = 0; g < ncg; g++) bulk_g2s(dst + (uint32_t)g * R * 16u, src + (size_t)g * p.T * 4, row_bytes, BAR(B_AFULL + sa));
-            };
-            for (int c = 0; c < NAS - 1 && c < p.nchunks; c++) load_a(c);
+            }
+        }
+    } else if (warp == 6) {
+        if (lane == 0) {
+            // ===== weight producer: its own thread so the weight ring runs ahead across chunk boundaries
             int wi = 0;
             const float* wtile = p.w + (size_t)blockIdx.y * p.nchunks * p.K * (p.w_stage_bytes / 4);
             for (int c = 0; c < p.nchunks; c++) {
-                if (c + NAS - 1 < p.nchunks) load_a(c + NAS - 1);
                 for (int j = 0; j < p.K; j++, wi++) {
                     const int sw = wi % p.nws;
                     mbar_wait(BAR(B_WEMPTY + sw), ((wi / p.nws) & 1) ^ 1);
@@ -314,42 +409,9 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
     } else {
         const int tid2 = threadIdx.x - 64;
         const int q = warp & 3;
-        const size_t cstride = (size_t)p.T;
         // ===== accumulator init (overlaps the first TMA loads)
-        for (int mt = 0; mt < MT; mt++) {
-            const int t = t0 + mt * 128 + q * 32 + lane;
-            const bool ok = t < p.T;
-            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt);
-            for (int col = 0; col < nt; col += 16) {
-                uint32_t v[16];
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const int n = n0 + col + 4 * g;
-                    int co = n, tt = t;
-                    size_t tstride = cstride;
-                    if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; tstride = cstride * p.ups_u; }
-                    float4 o = *reinterpret_cast<const float4*>(p.bias + co);
-                    if (p.bias_b) {
-                        const float4 b2 = *reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + co);
-                        o.x += b2.x; o.y += b2.y; o.z += b2.z; o.w += b2.w;
-                    }
-                    if (ok) {
-                        if (p.res_mode) {
-                            const float4 r = reinterpret_cast<const float4*>(p.res)[((size_t)b * (p.res_C_total / 4) + (p.res_c_off + co) / 4) * tstride + tt];
-                            if (p.res_mode == 1) { o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
-                            else { o.x -= r.x; o.y -= r.y; o.z -= r.z; o.w -= r.w; }  // epilogue negates: res - (conv + bias)
-                        }
-                        if (p.accumulate) {
-                            const float4 a = reinterpret_cast<const float4*>(p.y)[((size_t)b * (p.Cout_total / 4) + (p.cout_off + co) / 4) * tstride + tt];
-                            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-                        }
-                    }
-                    v[4 * g] = __float_as_uint(o.x); v[4 * g + 1] = __float_as_uint(o.y); v[4 * g + 2] = __float_as_uint(o.z); v[4 * g + 3] = __float_as_uint(o.w);
-                }
-                tmem_st16(trow + (uint32_t)col, v);
-            }
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        for (int mt = 0; mt < MT; mt++)
+            acc_init_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt);
         fence_before();
         mbar_arrive(BAR(B_INIT));
         // ===== operand prologue on the staged tile (generic proxy), then hand over to the async proxy
@@ -375,33 +437,11 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(BAR(B_AREADY + sa));
         }
-        // ===== tail: TMEM -> [relu] -> scale/mask -> c4 global (16-byte stores, coalesced across a warp)
+        // ===== tail
         mbar_wait(BAR(B_ACC), 0);
         fence_after();
-        const float sgn = p.res_mode == 2 ? -1.f : 1.f;
-        for (int mt = 0; mt < MT; mt++) {
-            const int t = t0 + mt * 128 + q * 32 + lane;
-            const bool ok = t < p.T;
-            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt);
-            const float s = ((p.out_mask && t >= len) ? 0.f : p.out_scale) * sgn;
-            for (int col = 0; col < nt; col += 16) {
-                uint32_t v[16];
-                tmem_ld16(trow + (uint32_t)col, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (!ok) continue;
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const int n = n0 + col + 4 * g;
-                    int co = n, tt = t;
-                    size_t tstride = cstride;
-                    if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; tstride = cstride * p.ups_u; }
-                    float4 o = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                    o.x *= s; o.y *= s; o.z *= s; o.w *= s;
-                    reinterpret_cast<float4*>(p.y)[((size_t)b * (p.Cout_total / 4) + (p.cout_off + co) / 4) * tstride + tt] = o;
-                }
-            }
-        }
+        for (int mt = 0; mt < MT; mt++)
+            acc_tail_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, len);
     }
     fence_before();
     __syncthreads();
@@ -419,7 +459,7 @@ __global__ void __launch_bounds__(192) k_tc_conv1d(TcParams p) {
 //   * double-buffers the TMEM accumulator: the epilogue warps pre-load tile i+1's accumulator (bias/residual) and
 //     drain tile i-1 while the MMA warp works on tile i.
 // 320 threads: warp 0 producer, warp 1 MMA issuer, warps 2-5 operand prologue, warps 6-9 accumulator init + tail.
-__global__ void __launch_bounds__(320) k_tc_conv1d_persist(TcParams p, int mtiles, int ntiles_total) {
+__global__ void __launch_bounds__(320, 3) k_tc_conv1d_persist(TcParams p, int mtiles, int ntiles_total) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -519,42 +559,10 @@ __global__ void __launch_bounds__(320) k_tc_conv1d_persist(TcParams p, int mtile
     } else {
         // ===== accumulator init (tile i+1) and tail (tile i), double-buffered TMEM
         const int q = warp & 3;
-        const size_t cstride = (size_t)p.T;
-        const float sgn = p.res_mode == 2 ? -1.f : 1.f;
         auto init_tile = [&](int i) {
             const int tile = blockIdx.x + i * gridDim.x, b = tile / mtiles, t0 = (tile - b * mtiles) * 128;
-            const int t = t0 + q * 32 + lane;
-            const bool ok = t < p.T;
-            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt);
-            for (int col = 0; col < nt; col += 16) {
-                uint32_t v[16];
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const int n = col + 4 * g;
-                    int co = n, tt = t;
-                    size_t tstride = cstride;
-                    if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; tstride = cstride * p.ups_u; }
-                    float4 o = *reinterpret_cast<const float4*>(p.bias + co);
-                    if (p.bias_b) {
-                        const float4 b2 = *reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + co);
-                        o.x += b2.x; o.y += b2.y; o.z += b2.z; o.w += b2.w;
-                    }
-                    if (ok) {
-                        if (p.res_mode) {
-                            const float4 r = reinterpret_cast<const float4*>(p.res)[((size_t)b * (p.res_C_total / 4) + (p.res_c_off + co) / 4) * tstride + tt];
-                            if (p.res_mode == 1) { o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
-                            else { o.x -= r.x; o.y -= r.y; o.z -= r.z; o.w -= r.w; }
-                        }
-                        if (p.accumulate) {
-                            const float4 a = reinterpret_cast<const float4*>(p.y)[((size_t)b * (p.Cout_total / 4) + (p.cout_off + co) / 4) * tstride + tt];
-                            o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
-                        }
-                    }
-                    v[4 * g] = __float_as_uint(o.x); v[4 * g + 1] = __float_as_uint(o.y); v[4 * g + 2] = __float_as_uint(o.z); v[4 * g + 3] = __float_as_uint(o.w);
-                }
-                tmem_st16(trow + (uint32_t)col, v);
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            const int n0 = 0;
+            acc_init_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt), b, t0 + q * 32 + lane, n0, nt);
             fence_before();
             mbar_arrive(BAR(B_INIT + (i & 1)));
         };
@@ -562,30 +570,185 @@ __global__ void __launch_bounds__(320) k_tc_conv1d_persist(TcParams p, int mtile
         for (int i = 0; i < n_mine; i++) {
             if (i + 1 < n_mine) init_tile(i + 1);
             const int tile = blockIdx.x + i * gridDim.x, b = tile / mtiles, t0 = (tile - b * mtiles) * 128;
+            const int n0 = 0;
             const int len = p.lens ? p.lens[b] : p.T;
-            const int t = t0 + q * 32 + lane;
-            const bool ok = t < p.T;
-            const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt);
-            const float s = ((p.out_mask && t >= len) ? 0.f : p.out_scale) * sgn;
             mbar_wait(BAR(B_ACC + (i & 1)), (i >> 1) & 1);
             fence_after();
-            for (int col = 0; col < nt; col += 16) {
-                uint32_t v[16];
-                tmem_ld16(trow + (uint32_t)col, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (!ok) continue;
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const int n = col + 4 * g;
-                    int co = n, tt = t;
-                    size_t tstride = cstride;
-                    if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; tstride = cstride * p.ups_u; }
-                    float4 o = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                    o.x *= s; o.y *= s; o.z *= s; o.w *= s;
-                    reinterpret_cast<float4*>(p.y)[((size_t)b * (p.Cout_total / 4) + (p.cout_off + co) / 4) * tstride + tt] = o;
+            acc_tail_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt), b, t0 + q * 32 + lane, n0, nt, len);
+            fence_before();  // order this tile's tcgen05.ld before the next init's tcgen05.st on the same columns
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Persistent variant with STREAMED weights for wide layers (Cin >= 64): the canonical Blackwell GEMM structure.
+// One CTA per SM walks tiles (n-tile fastest, so CTAs that share an activation tile run together and hit L2); the
+// TMA producer runs continuously over the flat (tile, chunk, tap) sequence, so the activation ring (NAS deep) and
+// the weight ring (nws deep) stay full across tile boundaries; the TMEM accumulator is double-buffered so the
+// epilogue warps pre-load tile i+1's accumulator and drain tile i-1 while the MMA warp is busy with tile i.
+// 352 threads: warp 0 activation producer, warp 1 MMA issuer, warps 2-5 operand prologue, warps 6-9 accumulator init +
+// tail, warp 10 weight producer.
+__global__ void __launch_bounds__(352, 2) k_tc_conv1d_pstream(TcParams p, int mtiles, int ntiles, int tiles_total) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = p.nt, NAS = p.nas, NWS = p.nws, R = p.R, ncg = p.KC / 4, NCH = p.nchunks;
+    uint8_t* sA = smem;
+    uint8_t* sW = smem + (size_t)NAS * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)NWS * p.w_stage_bytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    const int B_AFULL = 0, B_AREADY = NAS, B_AEMPTY = 2 * NAS, B_WFULL = 3 * NAS, B_WEMPTY = 3 * NAS + NWS, B_INIT = 3 * NAS + 2 * NWS,
+              B_ACC = B_INIT + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACC + 2);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NAS; i++) { mbar_init(BAR(B_AFULL + i), 1); mbar_init(BAR(B_AREADY + i), 128); mbar_init(BAR(B_AEMPTY + i), 1); }
+        for (int i = 0; i < NWS; i++) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(BAR(B_INIT + i), 128); mbar_init(BAR(B_ACC + i), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int n_mine = (tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // tile -> (batch, m tile, n tile); n tile fastest
+    auto decode = [&](int i, int& b, int& t0, int& ntile) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        ntile = tile % ntiles;
+        const int mm = tile / ntiles;
+        b = mm / mtiles;
+        t0 = (mm - b * mtiles) * 128;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== activation producer: runs up to NAS (tile, chunk) steps ahead of the MMA warp
+            const int steps = n_mine * NCH;  // flat (tile, chunk) sequence
+            for (int s_ = 0; s_ < steps; s_++) {
+                int b, t0, ntile;
+                decode(s_ / NCH, b, t0, ntile);
+                const int c = s_ % NCH;
+                const int r_lo = max(0, p.pad - t0), r_hi = min(R, p.T - (t0 - p.pad));
+                const uint32_t row_bytes = (uint32_t)(r_hi - r_lo) * 16u;
+                const int sa = s_ % NAS;
+                mbar_wait(BAR(B_AEMPTY + sa), ((s_ / NAS) & 1) ^ 1);
+                mbar_expect_tx(BAR(B_AFULL + sa), row_bytes * ncg);
+                const float* src = p.x + (((size_t)b * (p.Cin_total / 4) + p.cin_off / 4 + (size_t)c * ncg) * p.T + (t0 - p.pad + r_lo)) * 4;
+                const uint32_t dst = smem_u32(sA + (size_t)sa * p.a_stage_bytes) + (uint32_t)r_lo * 16u;
+                for (int g = 0; g < ncg; g++) bulk_g2s(dst + (uint32_t)g * R * 16u, src + (size_t)g * p.T * 4, row_bytes, BAR(B_AFULL + sa));
+            }
+        }
+    } else if (warp == 10) {
+        if (lane == 0) {
+            // ===== weight producer: independent thread, so weight tiles stream up to NWS taps ahead across chunk and tile
+            // boundaries (a single producer would serialise on the activation ring and bubble at every chunk)
+            const int steps = n_mine * NCH;
+            int wi = 0;
+            const size_t wstage_f = p.w_stage_bytes / 4;
+            for (int s_ = 0; s_ < steps; s_++) {
+                int b, t0, ntile;
+                decode(s_ / NCH, b, t0, ntile);
+                const int c = s_ % NCH;
+                const float* wsrc = p.w + ((size_t)ntile * NCH + c) * p.K * wstage_f;
+                for (int j = 0; j < p.K; j++, wi++) {
+                    const int sw = wi % NWS;
+                    mbar_wait(BAR(B_WEMPTY + sw), ((wi / NWS) & 1) ^ 1);
+                    mbar_expect_tx(BAR(B_WFULL + sw), p.w_stage_bytes);
+                    bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), wsrc + (size_t)j * wstage_f, p.w_stage_bytes, BAR(B_WFULL + sw));
                 }
             }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)nt * 16u;
+            const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R), b_kstep = (uint64_t)(2u * (uint32_t)nt);
+            const int nk = p.KC / 8;
+            int wi = 0, s_ = 0;
+            for (int i = 0; i < n_mine; i++) {
+                const int ab = i & 1;
+                mbar_wait(BAR(B_INIT + ab), (i >> 1) & 1);
+                fence_after();
+                const uint32_t d = tmem + (uint32_t)(ab * nt);
+                for (int c = 0; c < NCH; c++, s_++) {
+                    const int sa = s_ % NAS;
+                    mbar_wait(BAR(B_AREADY + sa), (s_ / NAS) & 1);
+                    fence_after();
+                    const uint64_t a_desc0 = make_desc(smem_u32(sA + (size_t)sa * p.a_stage_bytes), a_lbo, 128u);
+                    for (int j = 0; j < p.K; j++, wi++) {
+                        const int sw = wi % NWS;
+                        mbar_wait(BAR(B_WFULL + sw), (wi / NWS) & 1);
+                        fence_after();
+                        uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(j * p.dil);
+                        uint64_t bd = make_desc(smem_u32(sW + (size_t)sw * p.w_stage_bytes), b_lbo, 128u);
+                        for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_tf32(d, ad, bd, p.idesc, 1u);
+                        umma_commit(BAR(B_WEMPTY + sw));
+                    }
+                    umma_commit(BAR(B_AEMPTY + sa));
+                }
+                umma_commit(BAR(B_ACC + ab));
+            }
+        }
+    } else if (warp < 6) {
+        // ===== operand prologue over the flat (tile, chunk) sequence
+        const int tid2 = threadIdx.x - 64;
+        const float slope = p.in_slope;
+        const int steps = n_mine * NCH;
+        for (int s_ = 0; s_ < steps; s_++) {
+            int b, t0, ntile;
+            decode(s_ / NCH, b, t0, ntile);
+            const int len = p.lens ? p.lens[b] : p.T;
+            const int r_lo = max(0, p.pad - t0), r_hi = min(R, p.T - (t0 - p.pad));
+            const int r_mask_hi = p.in_mask ? min(r_hi, len - (t0 - p.pad)) : r_hi;
+            const int sa = s_ % NAS;
+            mbar_wait(BAR(B_AFULL + sa), (s_ / NAS) & 1);
+            float4* A = reinterpret_cast<float4*>(sA + (size_t)sa * p.a_stage_bytes);
+            for (int g = 0; g < ncg; g++) {
+                float4* Ag = A + (size_t)g * R;
+                for (int r = tid2; r < R; r += 128) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r >= r_lo && r < r_mask_hi) {
+                        v = Ag[r];
+                        v.x = to_tf32(lrelu(v.x, slope)); v.y = to_tf32(lrelu(v.y, slope));
+                        v.z = to_tf32(lrelu(v.z, slope)); v.w = to_tf32(lrelu(v.w, slope));
+                    }
+                    Ag[r] = v;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(BAR(B_AREADY + sa));
+        }
+    } else {
+        // ===== accumulator init (tile i+1) and tail (tile i), double-buffered TMEM
+        const int q = warp & 3;
+        auto init_tile = [&](int i) {
+            int b, t0, ntile;
+            decode(i, b, t0, ntile);
+            const int n0 = ntile * nt;
+            acc_init_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt), b, t0 + q * 32 + lane, n0, nt);
+            fence_before();
+            mbar_arrive(BAR(B_INIT + (i & 1)));
+        };
+        if (n_mine > 0) init_tile(0);
+        for (int i = 0; i < n_mine; i++) {
+            if (i + 1 < n_mine) init_tile(i + 1);
+            int b, t0, ntile;
+            decode(i, b, t0, ntile);
+            const int n0 = ntile * nt;
+            const int len = p.lens ? p.lens[b] : p.T;
+            mbar_wait(BAR(B_ACC + (i & 1)), (i >> 1) & 1);
+            fence_after();
+            acc_tail_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt), b, t0 + q * 32 + lane, n0, nt, len);
             fence_before();  // order this tile's tcgen05.ld before the next init's tcgen05.st on the same columns
         }
     }
@@ -663,8 +826,31 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
         BV2_CUDA(cudaGetLastError());
         return;
     }
+    static const int pstream_env = getenv("BV2_TC_PSTREAM") ? atoi(getenv("BV2_TC_PSTREAM")) : 1;
+    if (pstream_env && !w.x3 && nctas >= num_sms && nt >= 128 && 2 * nt <= 512) {  // measured: wins for wide N tiles only
+        // wide layer with at least one tile per SM: persistent CTAs, continuously streamed weights, double-buffered TMEM
+        const bool two_per_sm = 2 * nt <= 256 && (size_t)2 * p.a_stage_bytes + 3 * (size_t)p.w_stage_bytes + 2048 <= 104 * 1024;
+        const uint32_t big = two_per_sm ? 104 * 1024 : 200 * 1024;
+        int nas2 = std::min(4, std::max(2, p.nchunks * 2));
+        while (nas2 > 2 && (size_t)nas2 * p.a_stage_bytes + 3 * (size_t)p.w_stage_bytes + 2048 > big) nas2--;
+        int nws2 = (int)((big - (size_t)nas2 * p.a_stage_bytes - 2048) / p.w_stage_bytes);
+        nws2 = std::max(2, std::min(nws2, 8));
+        p.nas = nas2; p.nws = nws2;
+        uint32_t pc = 32; while ((int)pc < 2 * nt) pc <<= 1;
+        p.tmem_cols = pc;
+        const size_t smem_s = (size_t)nas2 * p.a_stage_bytes + (size_t)nws2 * p.w_stage_bytes + (size_t)(3 * nas2 + 2 * nws2 + 4) * 8 + 16;
+        BV2_CHECK(smem_s <= 227 * 1024, "tc_conv1d pstream shared memory");
+        static bool attr3 = false;
+        if (!attr3) { BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d_pstream, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr3 = true; }
+        const int mtiles = cdiv(p.T, 128);
+        const int total = mtiles * p.B * ntiles;
+        const int grid_s = std::min(total, (two_per_sm ? 2 : 1) * num_sms);
+        k_tc_conv1d_pstream<<<grid_s, 352, smem_s, st>>>(p, mtiles, ntiles, total);
+        BV2_CUDA(cudaGetLastError());
+        return;
+    }
     dim3 grid(cdiv(p.T, 128 * MT), ntiles, p.B);
-    k_tc_conv1d<<<grid, 192, smem, st>>>(p);
+    k_tc_conv1d<<<grid, 224, smem, st>>>(p);
     BV2_CUDA(cudaGetLastError());
 }
 
