@@ -206,13 +206,13 @@ struct bv2_engine {
                 for (int i2 = 0; i2 < H * H; i2++) w[(size_t)p * H * H + i2] = wt.data[i2] * s;
                 for (int i2 = 0; i2 < H; i2++) b[p * H + i2] = bt.data[i2] * s;
             }
-            L.qkv = make_conv(w, 3 * H, H, 1, &b, tc_mode, tc_mode == 2 ? 32 : 96);
-            L.o = conv_from(a + ".conv_o", false, tc_mode, tc_mode == 2 ? 32 : 48);
+            L.qkv = make_conv(w, 3 * H, H, 1, &b, tc_mode, tc_mode == 2 ? 32 : 96, 64);
+            L.o = conv_from(a + ".conv_o", false, tc_mode, tc_mode == 2 ? 32 : 48, 64);
             L.relk = upload(W(a + ".emb_rel_k").data);
             L.relv = upload(W(a + ".emb_rel_v").data);
             L.n1 = ln_from(name + ".norm_layers_1." + std::to_string(i));
-            L.f1 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_1", false, tc_mode, tc_mode == 2 ? 32 : 128);
-            L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2", false, tc_mode, 32);
+            L.f1 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_1", false, tc_mode, tc_mode == 2 ? 32 : 128, 64);
+            L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2", false, tc_mode, 32, 64);
             L.n2 = ln_from(name + ".norm_layers_2." + std::to_string(i));
             e.layers.push_back(L);
         }
@@ -468,7 +468,22 @@ void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const fl
             BV2_CUDA(cudaGetLastError()); launches++;
         }
         conv(L.qkv, x, qkv, s, ConvArgs(), 0, 0, tc);
-        {
+        if (tc) {
+            // tensor-core attention: S = Q.K^T (tcgen05) -> softmax + relative terms (SIMT) -> att += P.V (tcgen05)
+            const size_t mk = ws.used();
+            const int Fp = (T + 127) / 128 * 128;
+            Act S = ws.act(B * nh, Fp, T);
+            float* vt = ws.alloc((size_t)B * nh * Fp * 96);
+            dim3 gv(cdiv(Fp, 128), 24, B * nh);
+            k_pack_vt<96><<<gv, 128, 0, s>>>(qkv.p, vt, H, nh, T, Fp, lens);
+            BV2_CUDA(cudaGetLastError()); launches++;
+            tc_attn_qk(qkv, H, nh, S, s); launches++;
+            dim3 gs(cdiv(T, 32), B * nh);
+            k_attn_softmax<96, 16><<<gs, 512, 0, s>>>(qkv.p, S.p, L.relk, L.relv, att.p, H, nh, T, Fp, lens, cfg.window_size);
+            BV2_CUDA(cudaGetLastError()); launches++;
+            tc_attn_pv(S, vt, H, nh, att, s); launches++;
+            ws.release(mk);
+        } else {
             dim3 grid(cdiv(T, 16), nh, B);
             k_attention_rel<96><<<grid, 128, 0, s>>>(qkv.p, L.relk, L.relv, att.p, H, T, lens, cfg.window_size);
             BV2_CUDA(cudaGetLastError()); launches++;
@@ -519,7 +534,7 @@ void bv2_engine::run_text_encoder(int B, int T, const int64_t* x, const int64_t*
                                                   reinterpret_cast<const long long*>(lang), emb, temb, lemb, h.p, H, T, lens,
                                                   std::sqrt((float)H));
     BV2_CUDA(cudaGetLastError()); launches++;
-    run_encoder(enc_p, h, lens, gproj, s, cfg.generator_precision != 0);
+    run_encoder(enc_p, h, lens, gproj, s, false);  // feeds ceil(durations): FP32 FMA only
     ConvArgs a; a.out_mask = 1; a.lens = lens;
     conv(enc_proj, h, stats, s, a, 0, 0, true);
 }
@@ -689,7 +704,8 @@ static size_t ws_bytes_for(const bv2_config& c, int B, int T, int F) {
     // generous upper bounds; every buffer is bump-allocated per call
     size_t tok = (size_t)B * T, frm = (size_t)B * std::max(F, 1);
     size_t enc = tok * (3 * c.bert_dim + 16 * c.hidden_channels + c.filter_channels + 2 * c.dp_filter + 64) * 4;
-    size_t flow = frm * (12 * c.hidden_channels + c.filter_channels + 4 * c.inter_channels) * 4;
+    size_t flow = frm * (12 * c.hidden_channels + c.filter_channels + 4 * c.inter_channels) * 4 +
+                  (size_t)B * c.n_heads * ((size_t)F + 128) * ((size_t)F + 96) * 4 + (1u << 20);  // attention S/P + V^T
     size_t gen = frm * ((size_t)c.upsample_initial_channel + 5ull * 8192 * 5) * 4;  // 5 buffers of C*L per stage
     return enc + flow + gen + (64u << 20);
 }

@@ -895,4 +895,155 @@ __global__ void __launch_bounds__(256) k_conv_post_tanh(const float* __restrict_
     y[(size_t)b * T + t] = tanhf(acc);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core attention, middle stage (the Q.K^T and P.V contractions run on tcgen05: tc_attn_qk / tc_attn_pv).
+// S: c4 over keys [Z = B*heads][Fp/4][T queries][4] holding q_i.k_j; rewritten in place with the softmax
+// probabilities of reference attentions.py:280-308 (banded relative-key logits added here, keys >= len excluded,
+// rows of invalid queries and columns >= len zeroed so the P.V GEMM can run over the padded key range).
+// Also initialises att[b][h*DK+d][i] = sum_r p[i,i+r-w] * Ev[r][d] (relative-value term, :311-318); the P.V GEMM
+// then accumulates onto it.  Block = 32 queries x 4 key partitions; loads are coalesced across queries.
+// ------------------------------------------------------------------------------------------------
+template <int DK, int NP>
+__global__ void __launch_bounds__(32 * NP) k_attn_softmax(const float* __restrict__ qkv, float* __restrict__ S, const float* __restrict__ rel_k,
+                                                     const float* __restrict__ rel_v, float* __restrict__ att, int H, int heads, int T, int Fp,
+                                                     const int* __restrict__ lens, int window) {
+    constexpr int NCG = DK / 4;
+    __shared__ float sEk[9 * DK], sEv[9 * DK];
+    __shared__ float sqrel[NP][32][9];
+    __shared__ float sm[NP][32], sl[NP][32];
+    __shared__ float sprel[32][9];
+    const int tid = threadIdx.x, qi = tid & 31, part = tid >> 5;
+    const int z = blockIdx.y, b = z / heads, h = z - b * heads;
+    const int i = blockIdx.x * 32 + qi;
+    const int len = lens ? lens[b] : T;
+    const int nrel = 2 * window + 1;
+    for (int k = tid; k < nrel * DK; k += 32 * NP) { sEk[k] = rel_k[k]; sEv[k] = rel_v[k]; }
+    for (int k = tid; k < 32 * 9; k += 32 * NP) sprel[k / 9][k % 9] = 0.f;
+    __syncthreads();
+    const bool inb = i < T, valid = i < len;
+    // ---- relative-key logits q_i . Ek[r] (each partition sums NCG/4 channel groups)
+    {
+        float acc[9];
+#pragma unroll
+        for (int r = 0; r < 9; r++) acc[r] = 0.f;
+        if (inb) {
+            const float4* q4 = reinterpret_cast<const float4*>(qkv) + ((size_t)b * (3 * H / 4) + h * NCG) * T + i;
+            for (int cg = part; cg < NCG; cg += NP) {
+                const float4 qv = q4[(size_t)cg * T];
+#pragma unroll
+                for (int r = 0; r < 9; r++) {
+                    if (r < nrel) {
+                        const float* e = &sEk[r * DK + cg * 4];
+                        acc[r] = fmaf(qv.x, e[0], fmaf(qv.y, e[1], fmaf(qv.z, e[2], fmaf(qv.w, e[3], acc[r]))));
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 9; r++) sqrel[part][qi][r] = acc[r];
+    }
+    __syncthreads();
+    float qrel[9];
+#pragma unroll
+    for (int r = 0; r < 9; r++) { float a = 0.f;
+#pragma unroll
+        for (int pp = 0; pp < NP; pp++) a += sqrel[pp][qi][r];
+        qrel[r] = a; }
+    float4* Srow = reinterpret_cast<float4*>(S) + (size_t)z * (Fp / 4) * T + i;
+    auto rel_of = [&](int d) { float v = 0.f;
+#pragma unroll
+        for (int r = 0; r < 9; r++) v = (r == d) ? qrel[r] : v;
+        return v; };
+    // ---- pass 1: online (max, sum) over this partition's key groups
+    float m = -INFINITY, l = 0.f;
+    const int ngv = (len + 3) / 4;
+    if (valid) {
+        // 4 key groups per iteration: the loads are issued together (the online max/sum chain is serial, the loads are not)
+        for (int jg0 = part; jg0 < ngv; jg0 += 4 * NP) {
+            float4 sv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (jg0 + NP * u < ngv) sv[u] = Srow[(size_t)(jg0 + NP * u) * T];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int jg = jg0 + NP * u;
+                if (jg >= ngv) break;
+                float v[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
+                float mx = -INFINITY;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int j = jg * 4 + e, d = j - i + window;
+                    if ((unsigned)d < (unsigned)nrel) v[e] += rel_of(d);
+                    if (j >= len) v[e] = -INFINITY;
+                    mx = fmaxf(mx, v[e]);
+                }
+                if (mx > m) { l *= expf(m - mx); m = mx; }
+#pragma unroll
+                for (int e = 0; e < 4; e++) l += expf(v[e] - m);
+            }
+        }
+    }
+    sm[part][qi] = m; sl[part][qi] = l;
+    __syncthreads();
+    float M = -INFINITY;
+#pragma unroll
+    for (int pp = 0; pp < NP; pp++) M = fmaxf(M, sm[pp][qi]);
+    float L = 0.f;
+#pragma unroll
+    for (int pp = 0; pp < NP; pp++) if (sm[pp][qi] > -INFINITY) L += sl[pp][qi] * expf(sm[pp][qi] - M);
+    const float inv = (valid && L > 0.f) ? 1.f / L : 0.f;
+    // ---- pass 2: probabilities (zeros for excluded keys / invalid queries) over the PADDED key range
+    if (inb) {
+        for (int jg0 = part; jg0 < Fp / 4; jg0 += 4 * NP) {
+            float4 sv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (valid && jg0 + NP * u < ngv) sv[u] = Srow[(size_t)(jg0 + NP * u) * T];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int jg = jg0 + NP * u;
+                if (jg >= Fp / 4) break;
+                float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid && jg < ngv) {
+                    float v[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w}, pr[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const int j = jg * 4 + e, d = j - i + window;
+                        if ((unsigned)d < (unsigned)nrel) v[e] += rel_of(d);
+                        pr[e] = (j < len) ? expf(v[e] - M) * inv : 0.f;
+                        if ((unsigned)d < (unsigned)nrel && j < len) sprel[qi][d] = pr[e];
+                    }
+                    out = make_float4(pr[0], pr[1], pr[2], pr[3]);
+                }
+                Srow[(size_t)jg * T] = out;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- relative-value term -> initial value of the attention output
+    if (inb) {
+        float4* o4 = reinterpret_cast<float4*>(att) + ((size_t)b * (H / 4) + h * NCG) * T + i;
+        for (int cg = part; cg < NCG; cg += NP) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < nrel; r++) {
+                const float pw = sprel[qi][r];
+                const float* e = &sEv[r * DK + cg * 4];
+                o.x = fmaf(pw, e[0], o.x); o.y = fmaf(pw, e[1], o.y); o.z = fmaf(pw, e[2], o.z); o.w = fmaf(pw, e[3], o.w);
+            }
+            o4[(size_t)cg * T] = o;
+        }
+    }
+}
+
+// V^T pack for the P.V GEMM: vt[z][Fp/32][8][DK][4] (the UMMA K-major B-operand image, K = keys), zeros for keys >= len.
+template <int DK>
+__global__ void k_pack_vt(const float* __restrict__ qkv, float* __restrict__ vt, int H, int heads, int T, int Fp, const int* __restrict__ lens) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cg = blockIdx.y, z = blockIdx.z, b = z / heads, h = z - b * heads;
+    if (t >= Fp) return;
+    const int len = lens ? lens[b] : T;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < len && t < T) v = reinterpret_cast<const float4*>(qkv)[((size_t)b * (3 * H / 4) + 2 * H / 4 + h * (DK / 4) + cg) * T + t];
+    float* dst = vt + ((((size_t)z * (Fp / 32) + t / 32) * 8 + (t % 32) / 4) * DK + cg * 4) * 4 + (t & 3);
+    dst[0] = v.x; dst[4] = v.y; dst[8] = v.z; dst[12] = v.w;
+}
+
 }  // namespace bv2

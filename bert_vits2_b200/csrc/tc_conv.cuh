@@ -124,6 +124,13 @@ struct TcParams {
     uint32_t a_stage_bytes, w_stage_bytes, tmem_cols, idesc;
     float in_slope, out_scale;
     int accumulate, relu, res_mode, in_mask, out_mask, ups_u, ups_cout;
+    // batched-GEMM extensions (attention): grid z = b * zsplit + h
+    int zsplit;                 // 0/1: z == batch
+    int x_batch_z, y_batch_z;   // 1: tensor's batch index is z (else b)
+    int x_c_zstride, y_c_zstride;  // channel offset added per h
+    long long w_zstride;        // packed-weight offset per z (floats)
+    int w_mode;                 // 1: B operand rows come from a c4 activation tensor (K == 1): w = tensor base
+    int w_ld, w_rows, w_c_total, w_c_off, w_c_zstride;
 };
 
 namespace tc {
@@ -203,11 +210,13 @@ namespace tc {
 // All global loads of a 32-column batch are issued before the first tcgen05.st (memory-level parallelism: the
 // epilogue warps are the only threads touching residual/output tensors).
 template <int NG>
-__device__ __forceinline__ void acc_init_tile(const TcParams& p, uint32_t trow, int b, int t, int n0, int nt) {
+__device__ __forceinline__ void acc_init_tile(const TcParams& p, uint32_t trow, int b, int t, int n0, int nt, int yb = -1, int coff = -1) {
     const bool ok = t < p.T;
     const size_t tstride = (size_t)p.T * (p.ups_u ? p.ups_u : 1);
-    const float4* resb = p.res ? reinterpret_cast<const float4*>(p.res) + (size_t)b * (p.res_C_total / 4) * tstride : nullptr;
-    const float4* yb = reinterpret_cast<const float4*>(p.y) + (size_t)b * (p.Cout_total / 4) * tstride;
+    if (yb < 0) yb = b;
+    if (coff < 0) coff = p.cout_off;
+    const float4* resb = p.res ? reinterpret_cast<const float4*>(p.res) + (size_t)yb * (p.res_C_total / 4) * tstride : nullptr;
+    const float4* ybp = reinterpret_cast<const float4*>(p.y) + (size_t)yb * (p.Cout_total / 4) * tstride;
     const float sg = p.res_mode == 1 ? 1.f : -1.f;  // mode 2: tail negates -> res - (conv + bias)
     for (int col0 = 0; col0 < nt; col0 += 4 * NG) {
         float4 o[NG];
@@ -219,7 +228,7 @@ __device__ __forceinline__ void acc_init_tile(const TcParams& p, uint32_t trow, 
             if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; }
             cos[g] = co; tts[g] = tt;
             if (col0 + 4 * g < nt) {
-                o[g] = *reinterpret_cast<const float4*>(p.bias + co);
+                o[g] = p.bias ? *reinterpret_cast<const float4*>(p.bias + co) : make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.bias_b) {
                     const float4 b2 = *reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + co);
                     o[g].x += b2.x; o[g].y += b2.y; o[g].z += b2.z; o[g].w += b2.w;
@@ -236,7 +245,7 @@ __device__ __forceinline__ void acc_init_tile(const TcParams& p, uint32_t trow, 
         if (ok && p.accumulate) {
             float4 a[NG];
 #pragma unroll
-            for (int g = 0; g < NG; g++) if (col0 + 4 * g < nt) a[g] = yb[(size_t)((p.cout_off + cos[g]) / 4) * tstride + tts[g]];
+            for (int g = 0; g < NG; g++) if (col0 + 4 * g < nt) a[g] = ybp[(size_t)((coff + cos[g]) / 4) * tstride + tts[g]];
 #pragma unroll
             for (int g = 0; g < NG; g++) if (col0 + 4 * g < nt) { o[g].x += a[g].x; o[g].y += a[g].y; o[g].z += a[g].z; o[g].w += a[g].w; }
         }
@@ -258,10 +267,12 @@ __device__ __forceinline__ void acc_init_tile(const TcParams& p, uint32_t trow, 
 
 // Drain one accumulator tile: TMEM -> [relu] -> scale/mask -> c4 global (16-byte stores, coalesced across a warp).
 template <int NG>
-__device__ __forceinline__ void acc_tail_tile(const TcParams& p, uint32_t trow, int b, int t, int n0, int nt, int len) {
+__device__ __forceinline__ void acc_tail_tile(const TcParams& p, uint32_t trow, int b, int t, int n0, int nt, int len, int yb = -1, int coff = -1) {
     const bool ok = t < p.T;
     const size_t tstride = (size_t)p.T * (p.ups_u ? p.ups_u : 1);
-    float4* yb = reinterpret_cast<float4*>(p.y) + (size_t)b * (p.Cout_total / 4) * tstride;
+    if (yb < 0) yb = b;
+    if (coff < 0) coff = p.cout_off;
+    float4* ybp = reinterpret_cast<float4*>(p.y) + (size_t)yb * (p.Cout_total / 4) * tstride;
     const float s = ((p.out_mask && t >= len) ? 0.f : p.out_scale) * (p.res_mode == 2 ? -1.f : 1.f);
     for (int col0 = 0; col0 < nt; col0 += 4 * NG) {
         uint32_t v[NG / 4][16];
@@ -281,7 +292,7 @@ __device__ __forceinline__ void acc_tail_tile(const TcParams& p, uint32_t trow, 
                                            __uint_as_float(v[h][4 * g + 3]));
                     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     o.x *= s; o.y *= s; o.z *= s; o.w *= s;
-                    yb[(size_t)((p.cout_off + co) / 4) * tstride + tt] = o;
+                    ybp[(size_t)((coff + co) / 4) * tstride + tt] = o;
                 }
             }
         }
@@ -300,7 +311,11 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int MT = p.MT;
-    const int t0 = blockIdx.x * 128 * MT, n0 = blockIdx.y * p.nt, b = blockIdx.z;
+    const int t0 = blockIdx.x * 128 * MT, n0 = blockIdx.y * p.nt, z = blockIdx.z;
+    const int zs = p.zsplit > 1 ? p.zsplit : 1;
+    const int b = z / zs, hz = z - b * zs;
+    const int xb = p.x_batch_z ? z : b, yb = p.y_batch_z ? z : b;
+    const int cin_off = p.cin_off + hz * p.x_c_zstride, cout_off = p.cout_off + hz * p.y_c_zstride;
     const int nt = p.nt;
     uint8_t* sA = smem;
     const int NAS = p.nas;
@@ -344,7 +359,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
                 const int sa = c % NAS;
                 mbar_wait(BAR(B_AEMPTY + sa), ((c / NAS) & 1) ^ 1);
                 mbar_expect_tx(BAR(B_AFULL + sa), row_bytes * ncg);
-                const float* src = p.x + (((size_t)b * (p.Cin_total / 4) + p.cin_off / 4 + (size_t)c * ncg) * p.T + (t0 - p.pad + r_lo)) * 4;
+                const float* src = p.x + (((size_t)xb * (p.Cin_total / 4) + cin_off / 4 + (size_t)c * ncg) * p.T + (t0 - p.pad + r_lo)) * 4;
                 uint32_t dst = smem_u32(sA + (size_t)sa * p.a_stage_bytes) + (uint32_t)r_lo * 16u;
                 for (int g = 0; g < ncg; g++) bulk_g2s(dst + (uint32_t)g * R * 16u, src + (size_t)g * p.T * 4, row_bytes, BAR(B_AFULL + sa));
             }
@@ -353,14 +368,30 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
         if (lane == 0) {
             // ===== weight producer: its own thread so the weight ring runs ahead across chunk boundaries
             int wi = 0;
-            const float* wtile = p.w + (size_t)blockIdx.y * p.nchunks * p.K * (p.w_stage_bytes / 4);
-            for (int c = 0; c < p.nchunks; c++) {
-                for (int j = 0; j < p.K; j++, wi++) {
+            if (!p.w_mode) {
+                const float* wtile = p.w + (size_t)z * p.w_zstride + (size_t)blockIdx.y * p.nchunks * p.K * (p.w_stage_bytes / 4);
+                for (int c = 0; c < p.nchunks; c++) {
+                    for (int j = 0; j < p.K; j++, wi++) {
+                        const int sw = wi % p.nws;
+                        mbar_wait(BAR(B_WEMPTY + sw), ((wi / p.nws) & 1) ^ 1);
+                        mbar_expect_tx(BAR(B_WFULL + sw), p.w_stage_bytes);
+                        bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), wtile + ((size_t)c * p.K + j) * (p.w_stage_bytes / 4), p.w_stage_bytes,
+                                 BAR(B_WFULL + sw));
+                    }
+                }
+            } else {
+                // B operand = rows n0.. of a c4 activation tensor (attention keys): one bulk copy per channel group
+                const int nvalid = max(0, min(nt, p.w_rows - n0));
+                const uint32_t rb = (uint32_t)nvalid * 16u;
+                const float* wb = p.w + (((size_t)b * (p.w_c_total / 4) + (p.w_c_off + hz * p.w_c_zstride) / 4) * p.w_ld + n0) * 4;
+                for (int c = 0; c < p.nchunks; c++, wi++) {
                     const int sw = wi % p.nws;
                     mbar_wait(BAR(B_WEMPTY + sw), ((wi / p.nws) & 1) ^ 1);
-                    mbar_expect_tx(BAR(B_WFULL + sw), p.w_stage_bytes);
-                    bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), wtile + ((size_t)c * p.K + j) * (p.w_stage_bytes / 4), p.w_stage_bytes,
-                             BAR(B_WFULL + sw));
+                    mbar_expect_tx(BAR(B_WFULL + sw), rb * ncg);
+                    const uint32_t dst = smem_u32(sW + (size_t)sw * p.w_stage_bytes);
+                    if (nvalid)
+                        for (int g = 0; g < ncg; g++)
+                            bulk_g2s(dst + (uint32_t)g * nt * 16u, wb + (size_t)(c * ncg + g) * p.w_ld * 4, rb, BAR(B_WFULL + sw));
                 }
             }
         }
@@ -411,7 +442,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
         const int q = warp & 3;
         // ===== accumulator init (overlaps the first TMA loads)
         for (int mt = 0; mt < MT; mt++)
-            acc_init_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt);
+            acc_init_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, yb, cout_off);
         fence_before();
         mbar_arrive(BAR(B_INIT));
         // ===== operand prologue on the staged tile (generic proxy), then hand over to the async proxy
@@ -441,7 +472,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
         mbar_wait(BAR(B_ACC), 0);
         fence_after();
         for (int mt = 0; mt < MT; mt++)
-            acc_tail_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, len);
+            acc_tail_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, len, yb, cout_off);
     }
     fence_before();
     __syncthreads();
@@ -792,7 +823,7 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     while (nas > 2 && (size_t)nas * p.a_stage_bytes + 4 * (size_t)p.w_stage_bytes + 1024 > budget) nas--;
     p.nas = nas;
     int nws = ((int)budget - nas * (int)p.a_stage_bytes - 1024) / (int)p.w_stage_bytes;
-    p.nws = std::max(2, std::min(nws, 6));
+    p.nws = std::max(2, std::min(nws, 8));
     uint32_t cols = 32; while ((int)cols < MT * nt) cols <<= 1;
     p.tmem_cols = cols;
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((128u >> 4) << 24);
@@ -852,6 +883,60 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     dim3 grid(cdiv(p.T, 128 * MT), ntiles, p.B);
     k_tc_conv1d<<<grid, 224, smem, st>>>(p);
     BV2_CUDA(cudaGetLastError());
+}
+
+
+inline void tc_launch_simple(TcParams& p, int ntiles, int zdim, cudaStream_t st) {
+    const int halo = (p.K - 1) * p.dil;
+    p.MT = 1; p.R = 128 + halo; p.pad = (p.K - 1) / 2 * p.dil;
+    p.a_stage_bytes = (uint32_t)(p.KC * p.R * 4);
+    p.w_stage_bytes = (uint32_t)(p.KC * p.nt * 4);
+    const long long nctas = (long long)cdiv(p.T, 128) * ntiles * zdim;
+    const uint32_t budget = nctas > 148 ? 100 * 1024 : 200 * 1024;
+    int nas = std::min(3, std::max(2, p.nchunks));
+    while (nas > 2 && (size_t)nas * p.a_stage_bytes + 3 * (size_t)p.w_stage_bytes + 1024 > budget) nas--;
+    p.nas = nas;
+    int nws = ((int)budget - nas * (int)p.a_stage_bytes - 1024) / (int)p.w_stage_bytes;
+    p.nws = std::max(2, std::min(nws, 8));
+    uint32_t cols = 32; while ((int)cols < p.nt) cols <<= 1;
+    p.tmem_cols = cols;
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt >> 3) << 17) | ((128u >> 4) << 24);
+    const size_t smem = (size_t)p.nas * p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + (size_t)(3 * p.nas + 2 * p.nws + 2) * 8 + 16;
+    BV2_CHECK(smem <= 227 * 1024, "tc gemm shared memory");
+    static bool attr_set = false;
+    if (!attr_set) { BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+    dim3 grid(cdiv(p.T, 128), ntiles, zdim);
+    k_tc_conv1d<<<grid, 224, smem, st>>>(p);
+    BV2_CUDA(cudaGetLastError());
+}
+
+// S[z][keys][queries] (c4 over keys) = Q . K^T for every (batch, head): qkv c4 [B][3H/4][T][4], q pre-scaled.
+// Keys are padded to Fp (multiple of 128); columns >= T hold garbage and are never read by the softmax.
+inline void tc_attn_qk(const Act& qkv, int H, int heads, const Act& S, cudaStream_t st) {
+    const int dk = H / heads;
+    TcParams p{};
+    p.x = qkv.p; p.y = S.p; p.w = qkv.p; p.bias = nullptr;
+    p.Cin_total = qkv.C; p.cin_off = 0; p.x_c_zstride = dk; p.Cout_total = S.C; p.cout_off = 0; p.res_C_total = S.C;
+    p.T = qkv.T; p.B = qkv.B; p.K = 1; p.dil = 1; p.KC = 32; p.nchunks = dk / 32; p.nt = 128;
+    p.in_slope = 1.f; p.out_scale = 1.f;
+    p.zsplit = heads; p.x_batch_z = 0; p.y_batch_z = 1;
+    p.w_mode = 1; p.w_ld = qkv.T; p.w_rows = qkv.T; p.w_c_total = qkv.C; p.w_c_off = H; p.w_c_zstride = dk;
+    BV2_CHECK(dk % 32 == 0 && S.C % 128 == 0 && S.T == qkv.T && S.B == qkv.B * heads, "tc_attn_qk shapes");
+    tc_launch_simple(p, S.C / 128, qkv.B * heads, st);
+}
+
+// att[b][h*dk + d][i] += sum_j P[z][j][i] * V[j][d]  (P = c4 over keys, vt = packed V^T [z][Fp/32][8][dk][4])
+inline void tc_attn_pv(const Act& P, const float* vt, int H, int heads, const Act& att, cudaStream_t st) {
+    const int dk = H / heads;
+    TcParams p{};
+    p.x = P.p; p.y = att.p; p.w = vt; p.bias = nullptr;
+    p.Cin_total = P.C; p.cin_off = 0; p.Cout_total = att.C; p.cout_off = 0; p.y_c_zstride = dk; p.res_C_total = att.C;
+    p.T = P.T; p.B = att.B; p.K = 1; p.dil = 1; p.KC = 64; p.nchunks = P.C / 64; p.nt = dk;  // long reduction (keys): big chunks
+    p.in_slope = 1.f; p.out_scale = 1.f; p.accumulate = 1;
+    p.zsplit = heads; p.x_batch_z = 1; p.y_batch_z = 0;
+    p.w_mode = 0; p.w_zstride = (long long)P.C * dk;
+    BV2_CHECK(dk % 16 == 0 && dk <= 256 && P.C % 64 == 0 && P.B == att.B * heads && att.T == P.T, "tc_attn_pv shapes");
+    tc_launch_simple(p, 1, P.B, st);
 }
 
 }  // namespace bv2
