@@ -102,6 +102,14 @@ struct bv2_engine {
         float* gproj = nullptr; float* w_ceil = nullptr;
     } st;
     long long* h_ylen = nullptr;  // pinned
+    // side streams: the MRF's resblocks (k = 3, 7, 11) of one Generator stage are independent chains of 6 convs
+    cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_rb[4] = {nullptr, nullptr, nullptr, nullptr};
+    void ensure_side_streams() {
+        if (ev_fork) return;
+        for (int i = 0; i < 4; i++) { BV2_CUDA(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking)); BV2_CUDA(cudaEventCreateWithFlags(&ev_rb[i], cudaEventDisableTiming)); }
+        BV2_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    }
     bool profiling = false;
     struct StageEv { cudaEvent_t a = nullptr, b = nullptr; bool rec = false; };
     std::map<std::string, StageEv> stage_ev;
@@ -120,6 +128,8 @@ struct bv2_engine {
     ~bv2_engine() {
         for (void* p : dev_allocs) cudaFree(p);
         if (h_ylen) cudaFreeHost(h_ylen);
+        for (int i = 0; i < 4; i++) { if (side[i]) cudaStreamDestroy(side[i]); if (ev_rb[i]) cudaEventDestroy(ev_rb[i]); }
+        if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto& kv : stage_ev) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
     }
 
@@ -641,11 +651,12 @@ void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_
     const bool tc = cfg.generator_precision != 0;
     conv(conv_pre, z, x, s, a, 0, 0, tc);
     const int nk = cfg.n_resblock_kernels, nd = cfg.n_dilations;
+    BV2_CHECK(nk <= 4, "at most 4 resblock kernels");
+    ensure_side_streams();
     for (int i = 0; i < cfg.n_ups; i++) {
         const UpW& u = ups[i];
         const int Lo = L * u.u;
-        Act xu = ws.act(B, u.Cout, Lo), xt = ws.act(B, u.Cout, Lo), ra = ws.act(B, u.Cout, Lo), rb = ws.act(B, u.Cout, Lo),
-            S = ws.act(B, u.Cout, Lo);
+        Act S = ws.act(B, u.Cout, Lo), xu = ws.act(B, u.Cout, Lo);
         ConvTArgs t; t.x = x.p; t.Cin = u.Cin; t.Tin = L; t.w = u.w; t.bias = u.b; t.y = xu.p; t.Cout = u.Cout; t.Tout = Lo;
         t.K = u.K; t.u = u.u; t.p = (u.K - u.u) / 2; t.B = B; t.in_slope = 0.1f;
         if (tc) {
@@ -656,7 +667,12 @@ void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_
             k_convT_c4<<<grid, 256, 0, s>>>(t);
             BV2_CUDA(cudaGetLastError()); launches++;
         }
+        // fork: resblock j runs on its own stream; only the last conv of each chain (the MRF running sum) is ordered
+        BV2_CUDA(cudaEventRecord(ev_fork, s));
         for (int j = 0; j < nk; j++) {
+            cudaStream_t sj = j == 0 ? s : side[j];
+            if (j) BV2_CUDA(cudaStreamWaitEvent(sj, ev_fork, 0));
+            Act xt = ws.act(B, u.Cout, Lo), ra = ws.act(B, u.Cout, Lo), rb = ws.act(B, u.Cout, Lo);
             const ResBlockW& R = resblocks[i * nk + j];
             Act cur = xu;
             for (int d = 0; d < nd; d++) {
@@ -664,20 +680,25 @@ void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_
                 Act nxt = last ? S : (cur.p == ra.p ? rb : ra);
                 if (tc) {
                     TcEpi e1; e1.in_slope = 0.1f; e1.dil = R.dil[d];
-                    tc_conv1d(R.c1[d].tc, R.c1[d].b, cur, xt, e1, s, num_sms); launches++;
+                    tc_conv1d(R.c1[d].tc, R.c1[d].b, cur, xt, e1, sj, num_sms); launches++;
+                    if (last && j > 0) BV2_CUDA(cudaStreamWaitEvent(sj, ev_rb[j - 1], 0));  // S += ... after resblock j-1 wrote S
                     TcEpi e2; e2.in_slope = 0.1f; e2.res = cur.p; e2.res_mode = 1;
                     if (last) { e2.accumulate = j > 0; e2.out_scale = (j == nk - 1) ? 1.f / nk : 1.f; }
-                    tc_conv1d(R.c2[d].tc, R.c2[d].b, xt, nxt, e2, s, num_sms); launches++;
+                    tc_conv1d(R.c2[d].tc, R.c2[d].b, xt, nxt, e2, sj, num_sms); launches++;
                 } else {
                     ConvArgs c1; c1.in_slope = 0.1f; c1.dil = R.dil[d];
-                    conv(R.c1[d], cur, xt, s, c1);
+                    conv(R.c1[d], cur, xt, sj, c1);
+                    if (last && j > 0) BV2_CUDA(cudaStreamWaitEvent(sj, ev_rb[j - 1], 0));
                     ConvArgs c2; c2.in_slope = 0.1f; c2.res_mode = 1; c2.res = cur.p; c2.res_C_total = u.Cout;
                     if (last) { c2.accumulate = j > 0; c2.out_scale = (j == nk - 1) ? 1.f / nk : 1.f; }
-                    conv(R.c2[d], xt, nxt, s, c2);
+                    conv(R.c2[d], xt, nxt, sj, c2);
                 }
                 cur = nxt;
             }
+            BV2_CUDA(cudaEventRecord(ev_rb[j], sj));
         }
+        // join: the caller's stream continues after the last resblock (which itself waited for all earlier ones)
+        if (nk > 1) BV2_CUDA(cudaStreamWaitEvent(s, ev_rb[nk - 1], 0));
         if (i == 0) debug("gen_stage0", S);
         x = S; L = Lo; ch = u.Cout;
     }
@@ -706,7 +727,7 @@ static size_t ws_bytes_for(const bv2_config& c, int B, int T, int F) {
     size_t enc = tok * (3 * c.bert_dim + 16 * c.hidden_channels + c.filter_channels + 2 * c.dp_filter + 64) * 4;
     size_t flow = frm * (12 * c.hidden_channels + c.filter_channels + 4 * c.inter_channels) * 4 +
                   (size_t)B * c.n_heads * ((size_t)F + 128) * ((size_t)F + 96) * 4 + (1u << 20);  // attention S/P + V^T
-    size_t gen = frm * ((size_t)c.upsample_initial_channel + 5ull * 8192 * 5) * 4;  // 5 buffers of C*L per stage
+    size_t gen = frm * ((size_t)c.upsample_initial_channel + 11ull * 8192 * 5) * 4;  // 11 buffers of C*L per stage (3 resblock chains)
     return enc + flow + gen + (64u << 20);
 }
 

@@ -72,13 +72,18 @@ struct ConvArgs {
 // Tile = (16*NI time steps) x (4*CGN output channels), 16*CGN threads, each thread NI x 4 outputs.
 // <8,16>: 128 x 64 tile for long sequences; <1,4>: 16 x 16 tile so that token-rate tensors (T ~ 256) still spread over
 // >= 100 CTAs (the text encoder / duration predictors are latency-bound).
-template <int K, int NI, int CGN, int CIT>
-__global__ void __launch_bounds__(16 * CGN) k_conv1d_c4(ConvArgs a) {
-    constexpr int TT = 16 * NI, COT = 4 * CGN, MAXD = 5, NTHR = 16 * CGN;
+// KS > 1: intra-CTA split of the input-channel reduction (KS thread groups each take CIT/KS channels of every chunk and
+// the partial sums are combined through shared memory): the token-rate convs run at ~1 CTA per SM, so instruction
+// latency, not throughput, bounds them.
+template <int K, int NI, int CGN, int CIT, int KS = 1>
+__global__ void __launch_bounds__(16 * CGN * KS) k_conv1d_c4(ConvArgs a) {
+    constexpr int TT = 16 * NI, COT = 4 * CGN, MAXD = 5, NTHR = 16 * CGN * KS, NT1 = 16 * CGN;
     constexpr int XW = TT + (K - 1) * MAXD;
+    static_assert(KS == 1 || NI == 1, "split reduction only for the small tile");
     __shared__ float sx[CIT][XW];
     __shared__ __align__(16) float sw[CIT][K][COT];
-    const int tid = threadIdx.x, tl = tid & 15, cgo = tid >> 4;
+    __shared__ __align__(16) float sred[KS > 1 ? KS : 1][KS > 1 ? NT1 : 1][4];
+    const int tid = threadIdx.x % NT1, ks = threadIdx.x / NT1, tl = tid & 15, cgo = tid >> 4;
     const int b = blockIdx.z, t0 = blockIdx.x * TT, co0 = blockIdx.y * COT;
     const int len = a.lens ? a.lens[b] : a.T;
     const int xw = TT + (K - 1) * a.dil;
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(16 * CGN) k_conv1d_c4(ConvArgs a) {
     const float4* x4 = reinterpret_cast<const float4*>(a.x) + ((size_t)b * (a.Cin_total / 4) + a.cin_off / 4) * a.T;
 
     for (int c0 = 0; c0 < a.Cin; c0 += CIT) {
-        for (int i = tid; i < (CIT / 4) * xw; i += NTHR) {
+        for (int i = threadIdx.x; i < (CIT / 4) * xw; i += NTHR) {
             int g = i / xw, p = i - g * xw;
             int t = t0 - a.pad + p;
             int cg = c0 / 4 + g;
@@ -102,7 +107,7 @@ __global__ void __launch_bounds__(16 * CGN) k_conv1d_c4(ConvArgs a) {
             }
             sx[g * 4 + 0][p] = v.x; sx[g * 4 + 1][p] = v.y; sx[g * 4 + 2][p] = v.z; sx[g * 4 + 3][p] = v.w;
         }
-        for (int i = tid; i < CIT * K * (COT / 4); i += NTHR) {
+        for (int i = threadIdx.x; i < CIT * K * (COT / 4); i += NTHR) {
             int c4i = i % (COT / 4), r = i / (COT / 4);
             int j = r % K, ci = r / K;
             int co = co0 + c4i * 4;
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(16 * CGN) k_conv1d_c4(ConvArgs a) {
         }
         __syncthreads();
 #pragma unroll 2
-        for (int ci = 0; ci < CIT; ci++) {
+        for (int ci = ks * (CIT / KS); ci < (ks + 1) * (CIT / KS); ci++) {
 #pragma unroll
             for (int j = 0; j < K; j++) {
                 const float4 w4 = *reinterpret_cast<const float4*>(&sw[ci][j][cgo * 4]);
@@ -129,6 +134,16 @@ __global__ void __launch_bounds__(16 * CGN) k_conv1d_c4(ConvArgs a) {
             }
         }
         __syncthreads();
+    }
+    if (KS > 1) {
+        *reinterpret_cast<float4*>(sred[ks][tid]) = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+        __syncthreads();
+        if (ks != 0) return;
+#pragma unroll
+        for (int q = 1; q < KS; q++) {
+            const float4 v = *reinterpret_cast<const float4*>(sred[q][tid]);
+            acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
+        }
     }
     const int co = co0 + cgo * 4;
     if (co >= a.Cout) return;
@@ -169,7 +184,7 @@ inline void launch_conv1d_k(const ConvArgs& a, cudaStream_t st) {
         k_conv1d_c4<K, 8, 16, 8><<<grid, 256, 0, st>>>(a);
     } else {
         dim3 grid(cdiv(a.T, 16), cdiv(a.Cout, 16), a.B);
-        k_conv1d_c4<K, 1, 4, 32><<<grid, 64, 0, st>>>(a);
+        k_conv1d_c4<K, 1, 4, 32, 4><<<grid, 256, 0, st>>>(a);
     }
 }
 
