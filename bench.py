@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("BV2_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
+    ap.add_argument("--batched-steps", type=int, default=5, help="extra config-3 (B=32) measurement; 0 disables")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -320,6 +321,35 @@ def main():
                          "tensor_tflops": GEN_FLOP_PER_FRAME * fpu / (g_ms * 1e-3) / 1e12},
             "stage_ms": {"encoder_duration": enc_ms, "flow": flow_ms, "generator": g_ms},
         }
+        # extra (not the headline): BASELINE.json config 3 -- B=32 mixed ZH/JP/EN 128-phoneme utterances on the same engine
+        if world == 1 and args.batched_steps > 0:
+            try:
+                inp3 = synth.synthetic_inputs(cfg, [128] * 32, [i % 3 for i in range(32)], seed=3)
+                nw3, nz3 = synth.synthetic_noise(cfg, 32, 128, 2048, seed=3)
+                d3 = {k: v.to(dev) for k, v in inp3.items()}
+                nw3, nz3 = nw3.to(dev), nz3.to(dev)
+
+                def step3():
+                    yl, F3 = eng.infer_begin(d3["x"], d3["x_lengths"], d3["sid"], d3["tone"], d3["language"], d3["bert"], d3["ja_bert"],
+                                             d3["en_bert"], nw3, INFER_KW["noise_scale_w"], INFER_KW["length_scale"], INFER_KW["sdp_ratio"])
+                    eng.infer_finish(32, 128, F3, nz3, INFER_KW["noise_scale"])
+                    return int(yl.sum()), F3
+                for _ in range(2):
+                    step3()
+                torch.cuda.synchronize(dev)
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record()
+                fr3 = 0
+                for _ in range(args.batched_steps):
+                    f3, F3 = step3()
+                    fr3 += f3
+                b1.record(); torch.cuda.synchronize(dev)
+                ms3 = b0.elapsed_time(b1)
+                line["config3_batched"] = {"workload": "B=32, T=128 mixed ZH/JP/EN, full path", "value": fr3 * HOP / SR / (ms3 * 1e-3),
+                                           "unit": "audio-s/s", "ms_per_step": ms3 / args.batched_steps, "valid_frames_per_step": fr3 / args.batched_steps,
+                                           "padded_frames": int(F3)}
+            except Exception as ex:  # never let the extra measurement break the contract line
+                line["config3_batched"] = {"error": str(ex)[:200]}
         # CPU baseline on rank 0 at N=1 only: bounded sample of the same workload
         if world == 1 and args.cpu_baseline_steps > 0:
             line["cpu_baseline"], _ = cpu_oracle_rate(cfg, sd, budget_s=20.0, max_iters=args.cpu_baseline_steps)

@@ -656,7 +656,9 @@ void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_
     for (int i = 0; i < cfg.n_ups; i++) {
         const UpW& u = ups[i];
         const int Lo = L * u.u;
-        Act S = ws.act(B, u.Cout, Lo), xu = ws.act(B, u.Cout, Lo);
+        Act S = ws.act(B, u.Cout, Lo);
+        const size_t mark_after_S = ws.used();  // stage temporaries are released after the join; S (next stage's input) stays
+        Act xu = ws.act(B, u.Cout, Lo);
         ConvTArgs t; t.x = x.p; t.Cin = u.Cin; t.Tin = L; t.w = u.w; t.bias = u.b; t.y = xu.p; t.Cout = u.Cout; t.Tout = Lo;
         t.K = u.K; t.u = u.u; t.p = (u.K - u.u) / 2; t.B = B; t.in_slope = 0.1f;
         if (tc) {
@@ -701,6 +703,7 @@ void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_
         if (nk > 1) BV2_CUDA(cudaStreamWaitEvent(s, ev_rb[nk - 1], 0));
         if (i == 0) debug("gen_stage0", S);
         x = S; L = Lo; ch = u.Cout;
+        ws.release(mark_after_S);
     }
     dim3 grid(cdiv(L, 256), B);
     k_conv_post_tanh<16, 7><<<grid, 256, 0, s>>>(x.p, conv_post_w, o, L, 0.01f);
@@ -727,7 +730,7 @@ static size_t ws_bytes_for(const bv2_config& c, int B, int T, int F) {
     size_t enc = tok * (3 * c.bert_dim + 16 * c.hidden_channels + c.filter_channels + 2 * c.dp_filter + 64) * 4;
     size_t flow = frm * (12 * c.hidden_channels + c.filter_channels + 4 * c.inter_channels) * 4 +
                   (size_t)B * c.n_heads * ((size_t)F + 128) * ((size_t)F + 96) * 4 + (1u << 20);  // attention S/P + V^T
-    size_t gen = frm * ((size_t)c.upsample_initial_channel + 11ull * 8192 * 5) * 4;  // 11 buffers of C*L per stage (3 resblock chains)
+    size_t gen = frm * ((size_t)c.upsample_initial_channel + 8192ull * (5 + 10) + 4096) * 4;  // 5 stage outputs + 10 temporaries (3 resblock chains)
     return enc + flow + gen + (64u << 20);
 }
 
