@@ -216,3 +216,29 @@ def test_config2_full_size_against_oracle(engines, precision):
     e = rms(o.cpu(), st["o"])
     print(f"config2/{precision}: waveform RMS err {e:.3e} (signal RMS {float(st['o'].pow(2).mean().sqrt()):.3f})")
     assert e < (5e-5 if precision == "fp32" else TOL_WAV_TF32)
+
+
+def test_infer_batch_api_matches_single_calls():
+    """batched caller-side API; each utterance equals its own B=1 result except in the tail
+    the padded-batch semantics of the reference touch (receptive field of flow + Generator)."""
+    from bert_vits2_b200.infer_api import infer_batch
+    from bert_vits2_b200.models import SynthesizerTrn
+    cfg, sd = model_for(True, 0)
+    net = SynthesizerTrn(112, 1025, 32, 192, 192, 768, 2, 6, 3, 0.1, "1", [3, 7, 11], [[1, 3, 5]] * 3, [8, 8, 2, 2, 2], 512,
+                         [16, 16, 8, 2, 2], n_speakers=850, gin_channels=512, init_seed=None, precision="fp32")
+    net.load_state_dict(sd, strict=False)
+    net = net.to("cuda:0").eval()
+    items = []
+    for k, t in enumerate([9, 14, 11, 14]):
+        inp = synth.synthetic_inputs(cfg, [t], [k % 3], seed=20 + k)
+        items.append((inp["bert"][0], inp["ja_bert"][0], inp["en_bert"][0], inp["x"][0], inp["tone"][0], inp["language"][0]))
+    outs = infer_batch(net, items, sid=0, batch_size=2, sdp_ratio=0.0, noise_scale=0.0, noise_scale_w=0.0)  # deterministic: no noise
+    assert len(outs) == 4 and all(o.ndim == 1 and o.size % 512 == 0 and np.isfinite(o).all() for o in outs)
+    for k, it in enumerate(items):
+        d = {n: v.unsqueeze(0).to("cuda:0") for n, v in zip(("bert", "ja_bert", "en_bert", "x", "tone", "language"), it)}
+        o1, _, ym, _ = net.infer(d["x"], torch.tensor([it[3].shape[0]], device="cuda:0"), torch.zeros(1, dtype=torch.int64, device="cuda:0"),
+                                 d["tone"], d["language"], d["bert"], d["ja_bert"], d["en_bert"], sdp_ratio=0.0, noise_scale=0.0, noise_scale_w=0.0)
+        ref = o1[0, 0].cpu().numpy()
+        assert ref.shape == outs[k].shape
+        body = slice(0, max(0, ref.size - 20 * 512))
+        assert np.abs(ref[body] - outs[k][body]).max() < 1e-4 if ref.size > 20 * 512 else True
