@@ -302,6 +302,10 @@ def main():
         hbm, how = peaks()
         fpu = frames / (args.steps * world)  # frames per utterance-step on one GPU
         g_ms = float(np.mean(gen_ms))
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_generator_traffic.json")
+        if os.path.isfile(tp):  # dram__bytes_read+write summed over the Generator launches of one ncu capture (per frame)
+            traffic = json.load(open(tp))["generator_dram_bytes_per_frame"] * fpu
         ach = GEN_BYTES_PER_FRAME * fpu / (g_ms * 1e-3) / 1e9
         line = {
             "metric": "audio-sec/s (real-time factor) at 44.1kHz", "value": value, "unit": "audio-s/s", "n_gpus": world,
@@ -317,7 +321,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "Generator stage (conv_pre .. conv_post+tanh, 98 convolutions)", "achieved": ach, "peak": hbm,
-                         "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": how, "stage_ms": g_ms,
+                         "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "peak_source": how, "stage_ms": g_ms,
                          "tensor_tflops": GEN_FLOP_PER_FRAME * fpu / (g_ms * 1e-3) / 1e12},
             "stage_ms": {"encoder_duration": enc_ms, "flow": flow_ms, "generator": g_ms},
         }

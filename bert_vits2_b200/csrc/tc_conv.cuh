@@ -343,6 +343,10 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
     __syncthreads();
     fence_after();
     const uint32_t tmem = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the
+    // previous kernel in the stream; from here on this grid reads activations that kernel produced.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int R = p.R, ncg = p.KC / 4;
     const int len = p.lens ? p.lens[b] : p.T;
@@ -518,6 +522,10 @@ __global__ void __launch_bounds__(320, 3) k_tc_conv1d_persist(TcParams p, int mt
     __syncthreads();
     fence_after();
     const uint32_t tmem = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the
+    // previous kernel in the stream; from here on this grid reads activations that kernel produced.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int n_mine = (ntiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
 
     if (warp == 0) {
@@ -652,6 +660,10 @@ __global__ void __launch_bounds__(352, 2) k_tc_conv1d_pstream(TcParams p, int mt
     __syncthreads();
     fence_after();
     const uint32_t tmem = *tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the
+    // previous kernel in the stream; from here on this grid reads activations that kernel produced.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int n_mine = (tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     // tile -> (batch, m tile, n tile); n tile fastest
     auto decode = [&](int i, int& b, int& t0, int& ntile) {
@@ -790,6 +802,18 @@ __global__ void __launch_bounds__(352, 2) k_tc_conv1d_pstream(TcParams p, int mt
     }
 }
 
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static const int pdl_env = getenv("BV2_PDL") ? atoi(getenv("BV2_PDL")) : 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_env ? 1 : 0;
+    BV2_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
 // x: c4 input [B][x.C/4][T][4]; y: c4 output ([B][y.C/4][T*max(1,ups_u)][4]).  Channel windows via e.cin_off/e.cout_off.
 inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const Act& y, const TcEpi& e, cudaStream_t st, int num_sms) {
     const int u = w.ups_u ? w.ups_u : 1;
@@ -853,8 +877,7 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
         const int mtiles = cdiv(p.T, 128);
         const int total = mtiles * p.B;
         const int grid_p = std::min(total, per_sm * num_sms);
-        k_tc_conv1d_persist<<<grid_p, 320, smem_p, st>>>(p, mtiles, total);
-        BV2_CUDA(cudaGetLastError());
+        launch_pdl(k_tc_conv1d_persist, dim3(grid_p), dim3(320), smem_p, st, p, mtiles, total);
         return;
     }
     static const int pstream_env = getenv("BV2_TC_PSTREAM") ? atoi(getenv("BV2_TC_PSTREAM")) : 1;
@@ -876,13 +899,11 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
         const int mtiles = cdiv(p.T, 128);
         const int total = mtiles * p.B * ntiles;
         const int grid_s = std::min(total, (two_per_sm ? 2 : 1) * num_sms);
-        k_tc_conv1d_pstream<<<grid_s, 352, smem_s, st>>>(p, mtiles, ntiles, total);
-        BV2_CUDA(cudaGetLastError());
+        launch_pdl(k_tc_conv1d_pstream, dim3(grid_s), dim3(352), smem_s, st, p, mtiles, ntiles, total);
         return;
     }
     dim3 grid(cdiv(p.T, 128 * MT), ntiles, p.B);
-    k_tc_conv1d<<<grid, 224, smem, st>>>(p);
-    BV2_CUDA(cudaGetLastError());
+    launch_pdl(k_tc_conv1d, grid, dim3(224), smem, st, p);
 }
 
 
@@ -906,8 +927,7 @@ inline void tc_launch_simple(TcParams& p, int ntiles, int zdim, cudaStream_t st)
     static bool attr_set = false;
     if (!attr_set) { BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
     dim3 grid(cdiv(p.T, 128), ntiles, zdim);
-    k_tc_conv1d<<<grid, 224, smem, st>>>(p);
-    BV2_CUDA(cudaGetLastError());
+    launch_pdl(k_tc_conv1d, grid, dim3(224), smem, st, p);
 }
 
 // S[z][keys][queries] (c4 over keys) = Q . K^T for every (batch, head): qkv c4 [B][3H/4][T][4], q pre-scaled.
