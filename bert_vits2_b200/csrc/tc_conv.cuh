@@ -356,20 +356,40 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
     const int r_mask_hi = p.in_mask ? min(r_hi, len - (t0 - p.pad)) : r_hi;  // rows >= this read as zero (x * x_mask)
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== activation producer (TMA bulk copies, one contiguous run per channel group)
-            const uint32_t row_bytes = (uint32_t)(r_hi - r_lo) * 16u;
-            for (int c = 0; c < p.nchunks; c++) {
-                const int sa = c % NAS;
+        // ===== activation producer: lane 0 owns the mbarrier protocol, lanes 0..ncg-1 each issue one TMA bulk copy (one
+        // contiguous run per channel group) so a chunk's copies are issued in parallel instead of serially by one thread
+        const uint32_t row_bytes = (uint32_t)(r_hi - r_lo) * 16u;
+        for (int c = 0; c < p.nchunks; c++) {
+            const int sa = c % NAS;
+            if (lane == 0) {
                 mbar_wait(BAR(B_AEMPTY + sa), ((c / NAS) & 1) ^ 1);
                 mbar_expect_tx(BAR(B_AFULL + sa), row_bytes * ncg);
-                const float* src = p.x + (((size_t)xb * (p.Cin_total / 4) + cin_off / 4 + (size_t)c * ncg) * p.T + (t0 - p.pad + r_lo)) * 4;
-                uint32_t dst = smem_u32(sA + (size_t)sa * p.a_stage_bytes) + (uint32_t)r_lo * 16u;
-                for (int g = 0; g < ncg; g++) bulk_g2s(dst + (uint32_t)g * R * 16u, src + (size_t)g * p.T * 4, row_bytes, BAR(B_AFULL + sa));
+            }
+            __syncwarp();
+            if (lane < ncg) {
+                const float* src = p.x + (((size_t)xb * (p.Cin_total / 4) + cin_off / 4 + (size_t)c * ncg + lane) * p.T + (t0 - p.pad + r_lo)) * 4;
+                const uint32_t dst = smem_u32(sA + (size_t)sa * p.a_stage_bytes) + ((uint32_t)lane * R + (uint32_t)r_lo) * 16u;
+                bulk_g2s(dst, src, row_bytes, BAR(B_AFULL + sa));
             }
         }
     } else if (warp == 6) {
-        if (lane == 0) {
+        if (p.w_mode) {
+            // B operand = rows n0.. of a c4 activation tensor (attention keys): lanes issue one bulk copy per channel group
+            const int nvalid = max(0, min(nt, p.w_rows - n0));
+            const uint32_t rb = (uint32_t)nvalid * 16u;
+            const float* wb = p.w + (((size_t)b * (p.w_c_total / 4) + (p.w_c_off + hz * p.w_c_zstride) / 4) * p.w_ld + n0) * 4;
+            for (int c = 0; c < p.nchunks; c++) {
+                const int sw = c % p.nws;
+                if (lane == 0) {
+                    mbar_wait(BAR(B_WEMPTY + sw), ((c / p.nws) & 1) ^ 1);
+                    mbar_expect_tx(BAR(B_WFULL + sw), rb * ncg);
+                }
+                __syncwarp();
+                if (nvalid && lane < ncg)
+                    bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes) + (uint32_t)lane * nt * 16u, wb + (size_t)(c * ncg + lane) * p.w_ld * 4, rb,
+                             BAR(B_WFULL + sw));
+            }
+        } else if (lane == 0) {
             // ===== weight producer: its own thread so the weight ring runs ahead across chunk boundaries
             int wi = 0;
             if (!p.w_mode) {
@@ -532,16 +552,20 @@ __global__ void __launch_bounds__(320, 3) k_tc_conv1d_persist(TcParams p, int mt
         if (lane == 0) {
             mbar_expect_tx(BAR(B_WFULL), w_bytes);
             bulk_g2s(smem_u32(sWt), p.w, w_bytes, BAR(B_WFULL));
-            for (int i = 0; i < n_mine; i++) {
-                const int tile = blockIdx.x + i * gridDim.x, b = tile / mtiles, t0 = (tile - b * mtiles) * 128;
-                const int r_lo = max(0, p.pad - t0), r_hi = min(R, p.T - (t0 - p.pad));
-                const uint32_t row_bytes = (uint32_t)(r_hi - r_lo) * 16u;
-                const int sa = i % NAS;
+        }
+        for (int i = 0; i < n_mine; i++) {
+            const int tile = blockIdx.x + i * gridDim.x, b = tile / mtiles, t0 = (tile - b * mtiles) * 128;
+            const int r_lo = max(0, p.pad - t0), r_hi = min(R, p.T - (t0 - p.pad));
+            const uint32_t row_bytes = (uint32_t)(r_hi - r_lo) * 16u;
+            const int sa = i % NAS;
+            if (lane == 0) {
                 mbar_wait(BAR(B_AEMPTY + sa), ((i / NAS) & 1) ^ 1);
                 mbar_expect_tx(BAR(B_AFULL + sa), row_bytes * ncg);
-                const float* src = p.x + (((size_t)b * (p.Cin_total / 4) + p.cin_off / 4) * p.T + (t0 - p.pad + r_lo)) * 4;
-                const uint32_t dst = smem_u32(sA + (size_t)sa * p.a_stage_bytes) + (uint32_t)r_lo * 16u;
-                for (int g = 0; g < ncg; g++) bulk_g2s(dst + (uint32_t)g * R * 16u, src + (size_t)g * p.T * 4, row_bytes, BAR(B_AFULL + sa));
+            }
+            __syncwarp();
+            if (lane < ncg) {
+                const float* src = p.x + (((size_t)b * (p.Cin_total / 4) + p.cin_off / 4 + lane) * p.T + (t0 - p.pad + r_lo)) * 4;
+                bulk_g2s(smem_u32(sA + (size_t)sa * p.a_stage_bytes) + ((uint32_t)lane * R + (uint32_t)r_lo) * 16u, src, row_bytes, BAR(B_AFULL + sa));
             }
         }
     } else if (warp == 1) {
@@ -675,21 +699,23 @@ __global__ void __launch_bounds__(352, 2) k_tc_conv1d_pstream(TcParams p, int mt
     };
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== activation producer: runs up to NAS (tile, chunk) steps ahead of the MMA warp
-            const int steps = n_mine * NCH;  // flat (tile, chunk) sequence
-            for (int s_ = 0; s_ < steps; s_++) {
-                int b, t0, ntile;
-                decode(s_ / NCH, b, t0, ntile);
-                const int c = s_ % NCH;
-                const int r_lo = max(0, p.pad - t0), r_hi = min(R, p.T - (t0 - p.pad));
-                const uint32_t row_bytes = (uint32_t)(r_hi - r_lo) * 16u;
-                const int sa = s_ % NAS;
+        // ===== activation producer: runs up to NAS (tile, chunk) steps ahead of the MMA warp; copies issued by ncg lanes
+        const int steps = n_mine * NCH;  // flat (tile, chunk) sequence
+        for (int s_ = 0; s_ < steps; s_++) {
+            int b, t0, ntile;
+            decode(s_ / NCH, b, t0, ntile);
+            const int c = s_ % NCH;
+            const int r_lo = max(0, p.pad - t0), r_hi = min(R, p.T - (t0 - p.pad));
+            const uint32_t row_bytes = (uint32_t)(r_hi - r_lo) * 16u;
+            const int sa = s_ % NAS;
+            if (lane == 0) {
                 mbar_wait(BAR(B_AEMPTY + sa), ((s_ / NAS) & 1) ^ 1);
                 mbar_expect_tx(BAR(B_AFULL + sa), row_bytes * ncg);
-                const float* src = p.x + (((size_t)b * (p.Cin_total / 4) + p.cin_off / 4 + (size_t)c * ncg) * p.T + (t0 - p.pad + r_lo)) * 4;
-                const uint32_t dst = smem_u32(sA + (size_t)sa * p.a_stage_bytes) + (uint32_t)r_lo * 16u;
-                for (int g = 0; g < ncg; g++) bulk_g2s(dst + (uint32_t)g * R * 16u, src + (size_t)g * p.T * 4, row_bytes, BAR(B_AFULL + sa));
+            }
+            __syncwarp();
+            if (lane < ncg) {
+                const float* src = p.x + (((size_t)b * (p.Cin_total / 4) + p.cin_off / 4 + (size_t)c * ncg + lane) * p.T + (t0 - p.pad + r_lo)) * 4;
+                bulk_g2s(smem_u32(sA + (size_t)sa * p.a_stage_bytes) + ((uint32_t)lane * R + (uint32_t)r_lo) * 16u, src, row_bytes, BAR(B_AFULL + sa));
             }
         }
     } else if (warp == 10) {
