@@ -226,30 +226,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    gather_buf = None
+    from bert_vits2_b200.sharding import gather_waveforms
 
-    def gather_wave(o):
-        # the ONLY exchange step of the path: final waveform batch to rank 0 over NVLink (NCCL)
-        nonlocal gather_buf
+    def gather_wave(o, ylen):
+        # the ONLY exchange step of the path: final waveform batch to rank 0 over NVLink (NCCL); shapes may differ per rank
         if world == 1:
             return
-        if rank == 0 and (gather_buf is None or gather_buf[0].shape != o.shape):
-            gather_buf = [torch.empty_like(o) for _ in range(world)]
-        dist.gather(o, gather_buf if rank == 0 else None, dst=0)
+        gather_waveforms(o, torch.as_tensor(ylen, device=o.device) * HOP, dst=0)
 
     def step_resident():
         ylen, F = eng.infer_begin(d_inp["x"], d_inp["x_lengths"], d_inp["sid"], d_inp["tone"], d_inp["language"], d_inp["bert"],
                                   d_inp["ja_bert"], d_inp["en_bert"], d_nw, INFER_KW["noise_scale_w"], INFER_KW["length_scale"],
                                   INFER_KW["sdp_ratio"])
         o, attn, y_mask, aux = eng.infer_finish(B, T, F, d_nz, INFER_KW["noise_scale"])
-        gather_wave(o)
+        gather_wave(o, ylen)
         return int(ylen.sum()), o
 
     def step_e2e():
         dd = {k: v.to(dev, non_blocking=True) for k, v in h_inp.items()}
         o, attn, y_mask, aux = net.infer(dd["x"], dd["x_lengths"], dd["sid"], dd["tone"], dd["language"], dd["bert"], dd["ja_bert"],
                                          dd["en_bert"], **INFER_KW)
-        gather_wave(o)
+        gather_wave(o, net.last_y_lengths)
         wav = o[:, 0].cpu()  # D2H of the step's result, as infer.py:315-318 does
         return int(net.last_y_lengths.sum()), wav
 
