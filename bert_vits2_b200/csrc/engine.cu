@@ -254,6 +254,7 @@ struct bv2_engine {
     void finalize();
 
     // ---------------------------------------------------------------- launch helpers
+    int tc_out_tf32 = 0, tc_skip_xform = 0;  // one-shot modifiers for the next tensor-core conv() call
     void conv(const ConvW& cw, const Act& x, const Act& y, cudaStream_t s, ConvArgs extra = ConvArgs(), int cin_off = 0,
               int cout_off = 0, bool allow_tc = false) {
         if (allow_tc && cw.tc.w) {
@@ -262,7 +263,9 @@ struct bv2_engine {
             e.res_C_total = extra.res_C_total; e.res_c_off = extra.res_c_off; e.accumulate = extra.accumulate; e.out_scale = extra.out_scale;
             e.out_mask = extra.out_mask; e.lens = extra.lens; e.bias_b = extra.bias_b; e.bias_b_stride = extra.bias_b_stride;
             e.cin_off = cin_off; e.cout_off = cout_off; e.dil = extra.dil ? extra.dil : 1;
+            e.out_tf32 = tc_out_tf32; e.skip_xform = tc_skip_xform;
             BV2_CHECK(x.T == y.T && x.B == y.B, "conv T/B mismatch");
+            tc_out_tf32 = 0; tc_skip_xform = 0;
             tc_conv1d(cw.tc, cw.b, x, y, e, s, num_sms);
             launches++;
             return;
@@ -477,7 +480,9 @@ void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const fl
             k_add_bvec_mask<<<grid_tcb(T, H, B), 128, 0, s>>>(x.p, gproj + E.g_off, gproj_n, H, T, lens);
             BV2_CUDA(cudaGetLastError()); launches++;
         }
+        tc_out_tf32 = tc ? 1 : 0;  // q, k, v feed tensor-core GEMMs directly
         conv(L.qkv, x, qkv, s, ConvArgs(), 0, 0, tc);
+        tc_out_tf32 = 0;
         if (tc) {
             // tensor-core attention: S = Q.K^T (tcgen05) -> softmax + relative terms (SIMT) -> att += P.V (tcgen05)
             const size_t mk = ws.used();
@@ -498,7 +503,9 @@ void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const fl
             k_attention_rel<96><<<grid, 128, 0, s>>>(qkv.p, L.relk, L.relv, att.p, H, T, lens, cfg.window_size);
             BV2_CUDA(cudaGetLastError()); launches++;
         }
+        tc_skip_xform = tc ? 1 : 0;  // att was rounded by the P.V tail
         conv(L.o, att, y, s, ConvArgs(), 0, 0, tc);
+        tc_skip_xform = 0;
         layernorm(L.n1, x, y.p, x, s, 0, nullptr, lens, 0);
         ConvArgs a1; a1.in_mask = 1; a1.act = 1; a1.lens = lens;
         conv(L.f1, x, f, s, a1, 0, 0, tc);

@@ -1023,7 +1023,7 @@ __global__ void __launch_bounds__(32 * NP) k_attn_softmax(const float* __restric
                     for (int e = 0; e < 4; e++) {
                         const int j = jg * 4 + e, d = j - i + window;
                         if ((unsigned)d < (unsigned)nrel) v[e] += rel_of(d);
-                        pr[e] = (j < len) ? expf(v[e] - M) * inv : 0.f;
+                        pr[e] = (j < len) ? tf32_rna(expf(v[e] - M) * inv) : 0.f;  // TF32-exact: the P.V GEMM skips its prologue
                         if ((unsigned)d < (unsigned)nrel && j < len) sprel[qi][d] = pr[e];
                     }
                     out = make_float4(pr[0], pr[1], pr[2], pr[3]);

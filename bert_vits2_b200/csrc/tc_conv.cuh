@@ -43,6 +43,8 @@ struct TcEpi {
     int bias_b_stride = 0;
     int cin_off = 0, cout_off = 0;  // channel windows inside x / y (multiples of 4)
     int dil = 1;
+    int out_tf32 = 0;    // round the stored output to TF32 (RN): the consumer may then skip its operand prologue
+    int skip_xform = 0;  // input already TF32-exact, no activation / mask / padding needed (K == 1): prologue warps only forward the barrier
 };
 
 inline float tf32_rn_host(float x) {
@@ -124,6 +126,7 @@ struct TcParams {
     uint32_t a_stage_bytes, w_stage_bytes, tmem_cols, idesc;
     float in_slope, out_scale;
     int accumulate, relu, res_mode, in_mask, out_mask, ups_u, ups_cout;
+    int out_tf32, skip_xform;
     // batched-GEMM extensions (attention): grid z = b * zsplit + h
     int zsplit;                 // 0/1: z == batch
     int x_batch_z, y_batch_z;   // 1: tensor's batch index is z (else b)
@@ -295,6 +298,7 @@ __device__ __forceinline__ void acc_tail_tile(const TcParams& p, uint32_t trow, 
                                            __uint_as_float(v[h][4 * g + 3]));
                     if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     o.x *= s; o.y *= s; o.z *= s; o.w *= s;
+                    if (p.out_tf32) { o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w); }
                     ybp[(size_t)((coff + co) / 4) * tstride + tt] = o;
                 }
             }
@@ -478,7 +482,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
             const int sa = c % NAS;
             mbar_wait(BAR(B_AFULL + sa), (c / NAS) & 1);
             float4* A = reinterpret_cast<float4*>(sA + (size_t)sa * p.a_stage_bytes);
-            for (int g = 0; g < ncg; g++) {
+            for (int g = 0; g < (p.skip_xform ? 0 : ncg); g++) {
                 float4* Ag = A + (size_t)g * R;
                 for (int r = tid2; r < R; r += 128) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f), lo = v;
@@ -870,7 +874,9 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     // overlaps the other's MMA main loop
     const long long nctas = (long long)cdiv(p.T, 128 * MT) * ntiles * p.B;
     static const int smem_kb_env = getenv("BV2_TC_SMEM_KB") ? atoi(getenv("BV2_TC_SMEM_KB")) : 48;  // tuning knob (experiments)
-    const uint32_t budget = (nctas > num_sms && nt <= 128) ? (uint32_t)smem_kb_env * 1024 : 200 * 1024;
+    uint32_t budget = (nctas > num_sms && nt <= 128) ? (uint32_t)smem_kb_env * 1024 : 200 * 1024;
+    if (nt > 128 && 2 * nctas > num_sms && 2ull * p.a_stage_bytes + 2ull * p.w_stage_bytes + 2048 <= 112 * 1024)
+        budget = 112 * 1024;  // wide layer launched on three streams at once (MRF resblock chains): let two CTAs share an SM
     // activation pipeline depth: up to 4 stages when the K loop is long (hides TMA + prologue latency per chunk)
     int nas = std::min(3, std::max(2, p.nchunks));
     while (nas > 2 && (size_t)nas * p.a_stage_bytes + 4 * (size_t)p.w_stage_bytes + 1024 > budget) nas--;
@@ -882,6 +888,8 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((128u >> 4) << 24);
     p.in_slope = e.in_slope; p.out_scale = e.out_scale; p.accumulate = e.accumulate; p.relu = e.relu; p.res_mode = e.res ? (e.res_mode ? e.res_mode : 1) : 0;
     p.in_mask = e.in_mask; p.out_mask = e.out_mask; p.ups_u = w.ups_u; p.ups_cout = w.ups_cout;
+    p.out_tf32 = e.out_tf32; p.skip_xform = e.skip_xform;
+    if (e.skip_xform) BV2_CHECK(w.K == 1 && e.in_slope == 1.f && !e.in_mask, "skip_xform needs a plain 1x1 conv input");
     if (p.in_mask || p.out_mask) BV2_CHECK(e.lens != nullptr, "mask needs lens");
     BV2_CHECK(!(p.relu && (p.res_mode || p.accumulate)), "relu cannot be combined with residual/accumulate (accumulator-init fusion)");
     const size_t smem = (size_t)p.nas * p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + (size_t)(3 * p.nas + 2 * p.nws + 2) * 8 + 16;
@@ -893,7 +901,7 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     }
     static const int persist_env = getenv("BV2_TC_PERSIST") ? atoi(getenv("BV2_TC_PERSIST")) : 1;
     const size_t w_all = (size_t)p.K * p.KC * nt * 4;
-    if (persist_env && p.nchunks == 1 && ntiles == 1 && !w.x3 && w_all <= 64 * 1024 && nctas >= 2 * num_sms) {
+    if (persist_env && !e.skip_xform && p.nchunks == 1 && ntiles == 1 && !w.x3 && w_all <= 64 * 1024 && nctas >= 2 * num_sms) {
         // narrow layer with many tiles: persistent CTAs, resident weights, double-buffered TMEM
         p.nas = 3;
         const size_t wb = (w_all + 127) & ~(size_t)127;
@@ -910,7 +918,7 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
         return;
     }
     static const int pstream_env = getenv("BV2_TC_PSTREAM") ? atoi(getenv("BV2_TC_PSTREAM")) : 1;
-    if (pstream_env && !w.x3 && nctas >= num_sms && nt >= 128 && 2 * nt <= 512) {  // measured: wins for wide N tiles only
+    if (pstream_env && !e.skip_xform && !w.x3 && nctas >= num_sms && nt >= 128 && 2 * nt <= 512) {  // measured: wins for wide N tiles only
         // wide layer with at least one tile per SM: persistent CTAs, continuously streamed weights, double-buffered TMEM
         const bool two_per_sm = 2 * nt <= 256 && (size_t)2 * p.a_stage_bytes + 3 * (size_t)p.w_stage_bytes + 2048 <= 104 * 1024;
         const uint32_t big = two_per_sm ? 104 * 1024 : 200 * 1024;
@@ -970,6 +978,7 @@ inline void tc_attn_qk(const Act& qkv, int H, int heads, const Act& S, cudaStrea
     p.in_slope = 1.f; p.out_scale = 1.f;
     p.zsplit = heads; p.x_batch_z = 0; p.y_batch_z = 1;
     p.w_mode = 1; p.w_ld = qkv.T; p.w_rows = qkv.T; p.w_c_total = qkv.C; p.w_c_off = H; p.w_c_zstride = dk;
+    p.skip_xform = 1;  // q/k/v were rounded to TF32 by the QKV projection's tail
     BV2_CHECK(dk % 32 == 0 && S.C % 128 == 0 && S.T == qkv.T && S.B == qkv.B * heads, "tc_attn_qk shapes");
     tc_launch_simple(p, S.C / 128, qkv.B * heads, st);
 }
@@ -984,6 +993,8 @@ inline void tc_attn_pv(const Act& P, const float* vt, int H, int heads, const Ac
     p.in_slope = 1.f; p.out_scale = 1.f; p.accumulate = 1;
     p.zsplit = heads; p.x_batch_z = 1; p.y_batch_z = 0;
     p.w_mode = 0; p.w_zstride = (long long)P.C * dk;
+    p.skip_xform = 1;  // P rounded by k_attn_softmax, V^T is a copy of the rounded v
+    p.out_tf32 = 1;    // conv_o consumes it without a prologue
     BV2_CHECK(dk % 16 == 0 && dk <= 256 && P.C % 64 == 0 && P.B == att.B * heads && att.T == P.T, "tc_attn_pv shapes");
     tc_launch_simple(p, 1, P.B, st);
 }
