@@ -215,10 +215,12 @@ namespace tc {
 // Pre-load one 128-row x nt accumulator tile: bias (+ per-batch bias) (+/- residual) (+ previous output).
 // All global loads of a 32-column batch are issued before the first tcgen05.st (memory-level parallelism: the
 // epilogue warps are the only threads touching residual/output tensors).
-template <int NG>
+// GEN = 1: generic epilogue (polyphase ConvTranspose scatter, per-batch bias, relu); GEN = 0: plain conv epilogue.  The plain
+// instantiation is 10-20 % faster on the MRF convs (measured): these kernels run at their register caps.
+template <int NG, int GEN>
 __device__ __forceinline__ void acc_init_tile(const TcParams& p, uint32_t trow, int b, int t, int n0, int nt, int yb = -1, int coff = -1) {
     const bool ok = t < p.T;
-    const size_t tstride = (size_t)p.T * (p.ups_u ? p.ups_u : 1);
+    const size_t tstride = (size_t)p.T * ((GEN && p.ups_u) ? p.ups_u : 1);
     if (yb < 0) yb = b;
     if (coff < 0) coff = p.cout_off;
     const float4* resb = p.res ? reinterpret_cast<const float4*>(p.res) + (size_t)yb * (p.res_C_total / 4) * tstride : nullptr;
@@ -231,11 +233,11 @@ __device__ __forceinline__ void acc_init_tile(const TcParams& p, uint32_t trow, 
         for (int g = 0; g < NG; g++) {
             const int n = n0 + col0 + 4 * g;
             int co = n, tt = t;
-            if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; }
+            if (GEN && p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; }
             cos[g] = co; tts[g] = tt;
             if (col0 + 4 * g < nt) {
                 o[g] = p.bias ? *reinterpret_cast<const float4*>(p.bias + co) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias_b) {
+                if (GEN && p.bias_b) {
                     const float4 b2 = *reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + co);
                     o[g].x += b2.x; o[g].y += b2.y; o[g].z += b2.z; o[g].w += b2.w;
                 }
@@ -272,10 +274,10 @@ __device__ __forceinline__ void acc_init_tile(const TcParams& p, uint32_t trow, 
 }
 
 // Drain one accumulator tile: TMEM -> [relu] -> scale/mask -> c4 global (16-byte stores, coalesced across a warp).
-template <int NG>
+template <int NG, int GEN>
 __device__ __forceinline__ void acc_tail_tile(const TcParams& p, uint32_t trow, int b, int t, int n0, int nt, int len, int yb = -1, int coff = -1) {
     const bool ok = t < p.T;
-    const size_t tstride = (size_t)p.T * (p.ups_u ? p.ups_u : 1);
+    const size_t tstride = (size_t)p.T * ((GEN && p.ups_u) ? p.ups_u : 1);
     if (yb < 0) yb = b;
     if (coff < 0) coff = p.cout_off;
     float4* ybp = reinterpret_cast<float4*>(p.y) + (size_t)yb * (p.Cout_total / 4) * tstride;
@@ -293,10 +295,10 @@ __device__ __forceinline__ void acc_tail_tile(const TcParams& p, uint32_t trow, 
                 if (col0 + 16 * h + 4 * g < nt) {
                     const int n = n0 + col0 + 16 * h + 4 * g;
                     int co = n, tt = t;
-                    if (p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; }
+                    if (GEN && p.ups_u) { const int r = n / p.ups_cout; co = n - r * p.ups_cout; tt = t * p.ups_u + r; }
                     float4 o = make_float4(__uint_as_float(v[h][4 * g]), __uint_as_float(v[h][4 * g + 1]), __uint_as_float(v[h][4 * g + 2]),
                                            __uint_as_float(v[h][4 * g + 3]));
-                    if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (GEN && p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     o.x *= s; o.y *= s; o.z *= s; o.w *= s;
                     if (p.out_tf32) { o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w); }
                     ybp[(size_t)((coff + co) / 4) * tstride + tt] = o;
@@ -313,6 +315,7 @@ __device__ __forceinline__ void acc_tail_tile(const TcParams& p, uint32_t trow, 
 // Accumulator-init fusion: before the first MMA the epilogue warps pre-load  bias (+ per-batch bias) (+/- residual)
 // (+ previous output when accumulating)  into the TMEM accumulator with tcgen05.st while the first TMA loads are in
 // flight; every MMA then accumulates, and the tail is only  TMEM -> [relu] -> scale/mask -> store.
+template <int GEN>
 __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -473,7 +476,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
         const int q = warp & 3;
         // ===== accumulator init (overlaps the first TMA loads)
         for (int mt = 0; mt < MT; mt++)
-            acc_init_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, yb, cout_off);
+            acc_init_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, yb, cout_off);
         fence_before();
         mbar_arrive(BAR(B_INIT));
         // ===== operand prologue on the staged tile (generic proxy), then hand over to the async proxy
@@ -503,7 +506,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
         mbar_wait(BAR(B_ACC), 0);
         fence_after();
         for (int mt = 0; mt < MT; mt++)
-            acc_tail_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, len, yb, cout_off);
+            acc_tail_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, len, yb, cout_off);
     }
     fence_before();
     __syncthreads();
@@ -521,6 +524,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
 //   * double-buffers the TMEM accumulator: the epilogue warps pre-load tile i+1's accumulator (bias/residual) and
 //     drain tile i-1 while the MMA warp works on tile i.
 // 320 threads: warp 0 producer, warp 1 MMA issuer, warps 2-5 operand prologue, warps 6-9 accumulator init + tail.
+template <int GEN>
 __global__ void __launch_bounds__(320, 3) k_tc_conv1d_persist(TcParams p, int mtiles, int ntiles_total) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -632,7 +636,7 @@ __global__ void __launch_bounds__(320, 3) k_tc_conv1d_persist(TcParams p, int mt
         auto init_tile = [&](int i) {
             const int tile = blockIdx.x + i * gridDim.x, b = tile / mtiles, t0 = (tile - b * mtiles) * 128;
             const int n0 = 0;
-            acc_init_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt), b, t0 + q * 32 + lane, n0, nt);
+            acc_init_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt), b, t0 + q * 32 + lane, n0, nt);
             fence_before();
             mbar_arrive(BAR(B_INIT + (i & 1)));
         };
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(320, 3) k_tc_conv1d_persist(TcParams p, int mt
             const int len = p.lens ? p.lens[b] : p.T;
             mbar_wait(BAR(B_ACC + (i & 1)), (i >> 1) & 1);
             fence_after();
-            acc_tail_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt), b, t0 + q * 32 + lane, n0, nt, len);
+            acc_tail_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt), b, t0 + q * 32 + lane, n0, nt, len);
             fence_before();  // order this tile's tcgen05.ld before the next init's tcgen05.st on the same columns
         }
     }
@@ -663,6 +667,7 @@ __global__ void __launch_bounds__(320, 3) k_tc_conv1d_persist(TcParams p, int mt
 // epilogue warps pre-load tile i+1's accumulator and drain tile i-1 while the MMA warp is busy with tile i.
 // 352 threads: warp 0 activation producer, warp 1 MMA issuer, warps 2-5 operand prologue, warps 6-9 accumulator init +
 // tail, warp 10 weight producer.
+template <int GEN>
 __global__ void __launch_bounds__(352, 2) k_tc_conv1d_pstream(TcParams p, int mtiles, int ntiles, int tiles_total) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -811,7 +816,7 @@ __global__ void __launch_bounds__(352, 2) k_tc_conv1d_pstream(TcParams p, int mt
             int b, t0, ntile;
             decode(i, b, t0, ntile);
             const int n0 = ntile * nt;
-            acc_init_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt), b, t0 + q * 32 + lane, n0, nt);
+            acc_init_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt), b, t0 + q * 32 + lane, n0, nt);
             fence_before();
             mbar_arrive(BAR(B_INIT + (i & 1)));
         };
@@ -824,7 +829,7 @@ __global__ void __launch_bounds__(352, 2) k_tc_conv1d_pstream(TcParams p, int mt
             const int len = p.lens ? p.lens[b] : p.T;
             mbar_wait(BAR(B_ACC + (i & 1)), (i >> 1) & 1);
             fence_after();
-            acc_tail_tile<4>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt), b, t0 + q * 32 + lane, n0, nt, len);
+            acc_tail_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((i & 1) * nt), b, t0 + q * 32 + lane, n0, nt, len);
             fence_before();  // order this tile's tcgen05.ld before the next init's tcgen05.st on the same columns
         }
     }
@@ -896,9 +901,11 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     BV2_CHECK(smem <= 227 * 1024, "tc_conv1d shared memory");
     static bool attr_set = false;
     if (!attr_set) {
-        BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
+    const bool generic = w.ups_u || e.bias_b || e.relu;
     static const int persist_env = getenv("BV2_TC_PERSIST") ? atoi(getenv("BV2_TC_PERSIST")) : 1;
     const size_t w_all = (size_t)p.K * p.KC * nt * 4;
     if (persist_env && !e.skip_xform && p.nchunks == 1 && ntiles == 1 && !w.x3 && w_all <= 64 * 1024 && nctas >= 2 * num_sms) {
@@ -909,12 +916,16 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
         uint32_t pc = 32; while ((int)pc < 2 * nt) pc <<= 1;
         p.tmem_cols = pc;
         static bool attr2 = false;
-        if (!attr2) { BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr2 = true; }
+        if (!attr2) {
+            BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d_persist<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr2 = true;
+        }
         const int per_sm = smem_p <= 72 * 1024 ? 3 : (smem_p <= 110 * 1024 ? 2 : 1);
         const int mtiles = cdiv(p.T, 128);
         const int total = mtiles * p.B;
         const int grid_p = std::min(total, per_sm * num_sms);
-        launch_pdl(k_tc_conv1d_persist, dim3(grid_p), dim3(320), smem_p, st, p, mtiles, total);
+        launch_pdl(generic ? k_tc_conv1d_persist<1> : k_tc_conv1d_persist<0>, dim3(grid_p), dim3(320), smem_p, st, p, mtiles, total);
         return;
     }
     static const int pstream_env = getenv("BV2_TC_PSTREAM") ? atoi(getenv("BV2_TC_PSTREAM")) : 1;
@@ -932,15 +943,19 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
         const size_t smem_s = (size_t)nas2 * p.a_stage_bytes + (size_t)nws2 * p.w_stage_bytes + (size_t)(3 * nas2 + 2 * nws2 + 4) * 8 + 16;
         BV2_CHECK(smem_s <= 227 * 1024, "tc_conv1d pstream shared memory");
         static bool attr3 = false;
-        if (!attr3) { BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d_pstream, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr3 = true; }
+        if (!attr3) {
+            BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d_pstream<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d_pstream<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr3 = true;
+        }
         const int mtiles = cdiv(p.T, 128);
         const int total = mtiles * p.B * ntiles;
         const int grid_s = std::min(total, (two_per_sm ? 2 : 1) * num_sms);
-        launch_pdl(k_tc_conv1d_pstream, dim3(grid_s), dim3(352), smem_s, st, p, mtiles, ntiles, total);
+        launch_pdl(generic ? k_tc_conv1d_pstream<1> : k_tc_conv1d_pstream<0>, dim3(grid_s), dim3(352), smem_s, st, p, mtiles, ntiles, total);
         return;
     }
     dim3 grid(cdiv(p.T, 128 * MT), ntiles, p.B);
-    launch_pdl(k_tc_conv1d, grid, dim3(224), smem, st, p);
+    launch_pdl(generic ? k_tc_conv1d<1> : k_tc_conv1d<0>, grid, dim3(224), smem, st, p);
 }
 
 
@@ -962,9 +977,9 @@ inline void tc_launch_simple(TcParams& p, int ntiles, int zdim, cudaStream_t st)
     const size_t smem = (size_t)p.nas * p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + (size_t)(3 * p.nas + 2 * p.nws + 2) * 8 + 16;
     BV2_CHECK(smem <= 227 * 1024, "tc gemm shared memory");
     static bool attr_set = false;
-    if (!attr_set) { BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+    if (!attr_set) { BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
     dim3 grid(cdiv(p.T, 128), ntiles, zdim);
-    launch_pdl(k_tc_conv1d, grid, dim3(224), smem, st, p);
+    launch_pdl(k_tc_conv1d<0>, grid, dim3(224), smem, st, p);
 }
 
 // S[z][keys][queries] (c4 over keys) = Q . K^T for every (batch, head): qkv c4 [B][3H/4][T][4], q pre-scaled.
