@@ -260,17 +260,18 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    frames, gen_ms = 0, []
+    frames, gen_ms, flow_l, enc_l = 0, [], [], []
     for _ in range(args.steps):
         f, o = step_resident()
         frames += f
         gen_ms.append(eng.stage_ms("generator"))  # blocks on this step's generator end event only
+        flow_l.append(eng.stage_ms("flow")); enc_l.append(eng.stage_ms("encoder_duration"))
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.launch_count - l0
-    flow_ms, enc_ms = eng.stage_ms("flow"), eng.stage_ms("encoder_duration")
+    flow_ms, enc_ms = float(np.mean(flow_l)), float(np.mean(enc_l))
     # ---------------- end to end through the public API with host buffers
     for _ in range(args.warmup):
         step_e2e()
