@@ -315,7 +315,7 @@ __device__ __forceinline__ void acc_tail_tile(const TcParams& p, uint32_t trow, 
 // Accumulator-init fusion: before the first MMA the epilogue warps pre-load  bias (+ per-batch bias) (+/- residual)
 // (+ previous output when accumulating)  into the TMEM accumulator with tcgen05.st while the first TMA loads are in
 // flight; every MMA then accumulates, and the tail is only  TMEM -> [relu] -> scale/mask -> store.
-template <int GEN>
+template <int GEN, int X3 = 0>
 __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
                     for (int mt = 0; mt < MT; mt++) {
                         uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(mt * 128 + j * p.dil), bd = b_desc0;
                         const uint32_t d = tmem + (uint32_t)(mt * nt);
-                        if (!p.x3) {
+                        if (!X3) {
                             for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_tf32(d, ad, bd, p.idesc, 1u);
                         } else {
                             // a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo   (lo*lo ~ 2^-22 relative, dropped)
@@ -493,10 +493,10 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
                         const float4 a = Ag[r];
                         const float ax = lrelu(a.x, slope), ay = lrelu(a.y, slope), az = lrelu(a.z, slope), aw = lrelu(a.w, slope);
                         v.x = to_tf32(ax); v.y = to_tf32(ay); v.z = to_tf32(az); v.w = to_tf32(aw);
-                        lo.x = to_tf32(ax - v.x); lo.y = to_tf32(ay - v.y); lo.z = to_tf32(az - v.z); lo.w = to_tf32(aw - v.w);
+                        if (X3) { lo.x = to_tf32(ax - v.x); lo.y = to_tf32(ay - v.y); lo.z = to_tf32(az - v.z); lo.w = to_tf32(aw - v.w); }
                     }
                     Ag[r] = v;
-                    if (p.x3) Ag[(size_t)ncg * R + r] = lo;
+                    if (X3) Ag[(size_t)ncg * R + r] = lo;
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -955,6 +955,12 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
         return;
     }
     dim3 grid(cdiv(p.T, 128 * MT), ntiles, p.B);
+    if (w.x3) {  // accuracy-study instantiation (tests/cuda/tc_probe.cu); not used by the engine
+        static bool a3 = false;
+        if (!a3) { BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); a3 = true; }
+        launch_pdl(k_tc_conv1d<1, 1>, grid, dim3(224), smem, st, p);
+        return;
+    }
     launch_pdl(generic ? k_tc_conv1d<1> : k_tc_conv1d<0>, grid, dim3(224), smem, st, p);
 }
 
