@@ -309,6 +309,7 @@ struct bv2_engine {
                           const float* ja, const float* en, const int* lens, const float* gproj, Act& h, Act& stats, cudaStream_t s);
     void run_durations(Act h, const int* lens, const float* gproj, const float* noise_w, float nsw, float* z, Act& dp_out, int* zch,
                        cudaStream_t s);
+    void run_dp(Act h, const int* lens, const float* gproj, Act& dp_out, Act xg, Act d1, Act d2, cudaStream_t s);
     void run_flow(Act z, const int* lens, const float* gproj, cudaStream_t s);
     void run_generator(Act z, const int* lens_or_null, const float* gdec, int g_stride, float* o, cudaStream_t s);
     int* lens_to_device(const int64_t* x_lengths_dev, int B, Arena& ar, cudaStream_t s);
@@ -527,9 +528,12 @@ void bv2_engine::run_dds(const DdsW& D, Act x, const int* lens, cudaStream_t s) 
     const int nl = (int)D.c1.size();
     int dil = 1;
     for (int i = 0; i < nl; i++) {
-        k_dwconv3_c4<<<grid_tcb(T, C, B), 128, 0, s>>>(x.p, D.sep_w[i], D.sep_b[i], y.p, C, T, dil, lens);
-        BV2_CUDA(cudaGetLastError()); launches++;
-        layernorm(D.n1[i], y, nullptr, y, s, 1, nullptr, lens, 0);
+        {   // depthwise dilated conv + LayerNorm + GELU in one launch (the output row of the conv is the LN row)
+            LnArgs a; a.x = x.p; a.add = nullptr; a.gamma = D.n1[i].g; a.beta = D.n1[i].b; a.y = y.p; a.post_res = nullptr; a.C = C; a.T = T;
+            a.B = B; a.gelu = 1; a.relu_in = 0; a.out_mask = 0; a.lens = lens; a.eps = 1e-5f;
+            a.dw_w = D.sep_w[i]; a.dw_b = D.sep_b[i]; a.dw_dil = dil;
+            launch_layernorm(a, s); launches++;
+        }
         conv(D.c1[i], y, y2, s, ConvArgs(), 0, 0, true);
         layernorm(D.n2[i], y2, nullptr, x, s, 1, x.p, lens, i == nl - 1 ? 1 : 0);
         dil *= cfg.sdp_kernel;
@@ -563,6 +567,16 @@ void bv2_engine::run_text_encoder(int B, int T, const int64_t* x, const int64_t*
 void bv2_engine::run_durations(Act h, const int* lens, const float* gproj, const float* noise_w, float nsw, float* z, Act& dp_out,
                                int* zch_out, cudaStream_t s) {
     const int B = h.B, T = h.T, Cf = cfg.sdp_filter;
+    // ---- DP on a side stream (buffers allocated before the SDP's stack-disciplined temporaries)
+    ensure_side_streams();
+    {
+        const int Cd = cfg.dp_filter;
+        Act xg = ws.act(B, h.C, T), d1 = ws.act(B, Cd, T), d2 = ws.act(B, Cd, T);
+        BV2_CUDA(cudaEventRecord(ev_fork, s));
+        BV2_CUDA(cudaStreamWaitEvent(side[3], ev_fork, 0));
+        run_dp(h, lens, gproj, dp_out, xg, d1, d2, side[3]);
+        BV2_CUDA(cudaEventRecord(ev_rb[3], side[3]));
+    }
     // ---- SDP conditioning
     Act c = ws.act(B, Cf, T), cond = ws.act(B, Cf, T);
     ConvArgs a0; a0.bias_b = gproj + goff_sdp; a0.bias_b_stride = gproj_n;
@@ -592,9 +606,12 @@ void bv2_engine::run_durations(Act h, const int* lens, const float* gproj, const
     }
     sflip ^= 1;  // final Flip before ElementwiseAffine
     *zch_out = sflip ? 1 : 0;  // physical channel holding logical channel 0
-    // ---- DP
-    const int Cd = cfg.dp_filter;
-    Act xg = ws.act(B, h.C, T), d1 = ws.act(B, Cd, T), d2 = ws.act(B, Cd, T);
+    BV2_CUDA(cudaStreamWaitEvent(s, ev_rb[3], 0));  // join the DP chain
+}
+
+// DurationPredictor (reference models.py:285-299); independent of the SDP chain -> runs on a side stream
+void bv2_engine::run_dp(Act h, const int* lens, const float* gproj, Act& dp_out, Act xg, Act d1, Act d2, cudaStream_t s) {
+    const int B = h.B, T = h.T;
     BV2_CUDA(cudaMemcpyAsync(xg.p, h.p, h.elems() * sizeof(float), cudaMemcpyDeviceToDevice, s));
     k_add_bvec_mask<<<grid_tcb(T, h.C, B), 128, 0, s>>>(xg.p, gproj + goff_dp, gproj_n, h.C, T, lens);
     BV2_CUDA(cudaGetLastError()); launches++;

@@ -297,6 +297,8 @@ struct LnArgs {
     int relu_in;    // apply relu to input before LN (DurationPredictor: relu then norm, models.py:291-292)
     int out_mask; const int* lens;
     float eps;
+    // optional fused depthwise k=3 dilated conv in front of the norm (DDSConv: norms_1(convs_sep(x * x_mask)), modules.py:122-123)
+    const float* dw_w = nullptr; const float* dw_b = nullptr; int dw_dil = 1;
 };
 
 __global__ void __launch_bounds__(256) k_layernorm_c4(LnArgs a) {
@@ -314,7 +316,22 @@ __global__ void __launch_bounds__(256) k_layernorm_c4(LnArgs a) {
     for (int i = 0; i < 8; i++) {
         int cg = part + 8 * i;
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && cg < ncg) {
+        if (valid && cg < ncg && a.dw_w) {
+            const int len = a.lens[b];
+            float4 acc = *reinterpret_cast<const float4*>(a.dw_b + cg * 4);
+            const float* wc = a.dw_w + cg * 4 * 3;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int tt = t + (j - 1) * a.dw_dil;
+                if (tt >= 0 && tt < a.T && tt < len) {
+                    const float4 xv = x4[(size_t)cg * a.T + tt];
+                    acc.x = fmaf(xv.x, wc[0 * 3 + j], acc.x); acc.y = fmaf(xv.y, wc[1 * 3 + j], acc.y);
+                    acc.z = fmaf(xv.z, wc[2 * 3 + j], acc.z); acc.w = fmaf(xv.w, wc[3 * 3 + j], acc.w);
+                }
+            }
+            v[i] = acc;
+            s += (acc.x + acc.y) + (acc.z + acc.w);
+        } else if (valid && cg < ncg) {
             v[i] = x4[(size_t)cg * a.T + t];
             if (a4) { float4 r = a4[(size_t)cg * a.T + t]; v[i].x += r.x; v[i].y += r.y; v[i].z += r.z; v[i].w += r.w; }
             if (a.relu_in) { v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f); }

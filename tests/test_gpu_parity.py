@@ -242,3 +242,28 @@ def test_infer_batch_api_matches_single_calls():
         assert ref.shape == outs[k].shape
         body = slice(0, max(0, ref.size - 20 * 512))
         assert np.abs(ref[body] - outs[k][body]).max() < 1e-4 if ref.size > 20 * 512 else True
+
+
+def test_long_utterance_T512_and_batch8(engines):
+    """BASELINE.json config 4 upper bound (512 phonemes, ~3k frames) and a B=8 ragged batch: full path vs the CPU oracle."""
+    from oracle import vits2_oracle as O
+    cfg, sd = model_for(True, 0)
+    eng = engines(True, "tf32")
+    for lengths, langs, seed in (([512], [0], 31), ([64, 57, 33, 64, 12, 40, 64, 25], [0, 1, 2, 0, 1, 2, 0, 1], 32)):
+        B, T = len(lengths), max(lengths)
+        inp = synth.synthetic_inputs(cfg, lengths, langs, seed=seed)
+        nw, nz = synth.synthetic_noise(cfg, B, T, 8192, seed=seed)
+        st = O.infer(sd, cfg, **inp, noise_w=nw, noise_z=nz, sdp_ratio=0.5, noise_scale=0.6, noise_scale_w=0.9, length_scale=1.0,
+                     return_stages=True)
+        ylen, F = eng.infer_begin(inp["x"], inp["x_lengths"], inp["sid"], inp["tone"], inp["language"], inp["bert"], inp["ja_bert"],
+                                  inp["en_bert"], nw, 0.9, 1.0, 0.5)
+        w_ceil = eng.debug_read("w_ceil", (B, 1, T))
+        flips = int((w_ceil != st["w_ceil"]).sum())
+        if flips:
+            ylen, F = eng.infer_begin(inp["x"], inp["x_lengths"], inp["sid"], inp["tone"], inp["language"], inp["bert"], inp["ja_bert"],
+                                      inp["en_bert"], nw, 0.9, 1.0, 0.5, w_ceil_override=st["w_ceil"][:, 0])
+        assert flips <= 2 and ylen.tolist() == st["y_lengths"].tolist()
+        o, attn, y_mask, (z, z_p, m_p, logs_p) = eng.infer_finish(B, T, F, nz, 0.6)
+        e = rms(o.cpu(), st["o"])
+        print(f"B={B} T={T} F={F}: duration flips {flips}, waveform RMS err {e:.3e}, z max err {float((z.cpu() - st['z']).abs().max()):.2e}")
+        assert torch.isfinite(o).all() and e < TOL_WAV_TF32
