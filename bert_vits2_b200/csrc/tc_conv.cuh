@@ -310,6 +310,41 @@ __device__ __forceinline__ void acc_tail_tile(const TcParams& p, uint32_t trow, 
 
 }  // namespace tc
 
+namespace tc {
+// Operand prologue of one staged activation chunk [ncg][R][4] (generic proxy): leaky-relu + RN-TF32, zero rows outside
+// [r_lo, r_hi).  The stage is contiguous, so the loop runs over flat 16-byte elements with 4 independent load->store
+// chains per thread (the un-unrolled per-row loop exposed the full LDS latency on every element).
+__device__ __forceinline__ void xform_stage(float4* A, int ncg, int R, int r_lo, int r_hi, float slope, int tid2) {
+    const int total = ncg * R;
+    int r[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) r[u] = (tid2 + 128 * u) % R;
+    const int step = 512 % R;  // row advance per iteration (512 elements), R >= 128
+    const int wraps = 512 / R;
+    (void)wraps;
+    for (int i0 = tid2; i0 < total; i0 += 512) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + 128 * u;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < total && r[u] >= r_lo && r[u] < r_hi) v[u] = A[i];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + 128 * u;
+            if (i < total) {
+                float4 o;
+                o.x = to_tf32(lrelu(v[u].x, slope)); o.y = to_tf32(lrelu(v[u].y, slope));
+                o.z = to_tf32(lrelu(v[u].z, slope)); o.w = to_tf32(lrelu(v[u].w, slope));
+                A[i] = o;
+            }
+            r[u] += step; if (r[u] >= R) r[u] -= R;
+        }
+    }
+}
+}  // namespace tc
+
 // grid: (M blocks of MT*128 time steps, N tiles, B)
 //
 // Accumulator-init fusion: before the first MMA the epilogue warps pre-load  bias (+ per-batch bias) (+/- residual)
@@ -485,7 +520,8 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
             const int sa = c % NAS;
             mbar_wait(BAR(B_AFULL + sa), (c / NAS) & 1);
             float4* A = reinterpret_cast<float4*>(sA + (size_t)sa * p.a_stage_bytes);
-            for (int g = 0; g < (p.skip_xform ? 0 : ncg); g++) {
+            if (!X3 && !p.skip_xform) xform_stage(A, ncg, R, r_lo, r_mask_hi, slope, tid2);
+            for (int g = 0; g < ((p.skip_xform || !X3) ? 0 : ncg); g++) {
                 float4* Ag = A + (size_t)g * R;
                 for (int r = tid2; r < R; r += 128) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f), lo = v;
@@ -615,18 +651,7 @@ __global__ void __launch_bounds__(320, 3) k_tc_conv1d_persist(TcParams p, int mt
             const int sa = i % NAS;
             mbar_wait(BAR(B_AFULL + sa), (i / NAS) & 1);
             float4* A = reinterpret_cast<float4*>(sA + (size_t)sa * p.a_stage_bytes);
-            for (int g = 0; g < ncg; g++) {
-                float4* Ag = A + (size_t)g * R;
-                for (int r = tid2; r < R; r += 128) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r >= r_lo && r < r_mask_hi) {
-                        v = Ag[r];
-                        v.x = to_tf32(lrelu(v.x, slope)); v.y = to_tf32(lrelu(v.y, slope));
-                        v.z = to_tf32(lrelu(v.z, slope)); v.w = to_tf32(lrelu(v.w, slope));
-                    }
-                    Ag[r] = v;
-                }
-            }
+            xform_stage(A, ncg, R, r_lo, r_mask_hi, slope, tid2);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(BAR(B_AREADY + sa));
         }
@@ -794,18 +819,7 @@ __global__ void __launch_bounds__(352, 2) k_tc_conv1d_pstream(TcParams p, int mt
             const int sa = s_ % NAS;
             mbar_wait(BAR(B_AFULL + sa), (s_ / NAS) & 1);
             float4* A = reinterpret_cast<float4*>(sA + (size_t)sa * p.a_stage_bytes);
-            for (int g = 0; g < ncg; g++) {
-                float4* Ag = A + (size_t)g * R;
-                for (int r = tid2; r < R; r += 128) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r >= r_lo && r < r_mask_hi) {
-                        v = Ag[r];
-                        v.x = to_tf32(lrelu(v.x, slope)); v.y = to_tf32(lrelu(v.y, slope));
-                        v.z = to_tf32(lrelu(v.z, slope)); v.w = to_tf32(lrelu(v.w, slope));
-                    }
-                    Ag[r] = v;
-                }
-            }
+            xform_stage(A, ncg, R, r_lo, r_mask_hi, slope, tid2);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(BAR(B_AREADY + sa));
         }
