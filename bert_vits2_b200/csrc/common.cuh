@@ -6,6 +6,7 @@
 #include <cmath>
 #include <string>
 #include <stdexcept>
+#include <cstdlib>
 
 namespace bv2 {
 
@@ -60,5 +61,21 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Launch with programmatic stream serialization: the kernel may start while its predecessor in the stream drains; every
+// kernel launched this way executes `griddepcontrol.wait` (pdl_wait()) before touching data produced upstream.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static const int pdl_env = getenv("BV2_PDL") ? atoi(getenv("BV2_PDL")) : 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_env ? 1 : 0;
+    BV2_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 }  // namespace bv2

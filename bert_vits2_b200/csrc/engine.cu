@@ -494,12 +494,12 @@ void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const fl
             Act S = ws.act(B * nh, Fp, T);
             float* vt = ws.alloc((size_t)B * nh * Fp * 96);
             dim3 gv(cdiv(Fp, 128), 24, B * nh);
-            k_pack_vt<96><<<gv, 128, 0, s>>>(qkv.p, vt, H, nh, T, Fp, lens);
-            BV2_CUDA(cudaGetLastError()); launches++;
+            launch_pdl(k_pack_vt<96>, gv, dim3(128), 0, s, (const float*)qkv.p, vt, H, nh, T, Fp, lens); launches++;
             tc_attn_qk(qkv, H, nh, S, s); launches++;
             dim3 gs(cdiv(T, 32), B * nh);
-            k_attn_softmax<96, 16><<<gs, 512, 0, s>>>(qkv.p, S.p, L.relk, L.relv, att.p, H, nh, T, Fp, lens, cfg.window_size);
-            BV2_CUDA(cudaGetLastError()); launches++;
+            launch_pdl(k_attn_softmax<96, 16>, gs, dim3(512), 0, s, (const float*)qkv.p, S.p, (const float*)L.relk, (const float*)L.relv, att.p, H, nh, T, Fp,
+                       lens, (int)cfg.window_size);
+            launches++;
             tc_attn_pv(S, vt, H, nh, att, s); launches++;
             ws.release(mk);
         } else {

@@ -77,6 +77,7 @@ struct ConvArgs {
 // latency, not throughput, bounds them.
 template <int K, int NI, int CGN, int CIT, int KS = 1>
 __global__ void __launch_bounds__(16 * CGN * KS) k_conv1d_c4(ConvArgs a) {
+    pdl_wait();
     constexpr int TT = 16 * NI, COT = 4 * CGN, MAXD = 5, NTHR = 16 * CGN * KS, NT1 = 16 * CGN;
     constexpr int XW = TT + (K - 1) * MAXD;
     static_assert(KS == 1 || NI == 1, "split reduction only for the small tile");
@@ -181,10 +182,10 @@ inline void launch_conv1d_k(const ConvArgs& a, cudaStream_t st) {
     const long long big_ctas = (long long)cdiv(a.T, 128) * cdiv(a.Cout, 64) * a.B;
     if (big_ctas >= 96) {
         dim3 grid(cdiv(a.T, 128), cdiv(a.Cout, 64), a.B);
-        k_conv1d_c4<K, 8, 16, 8><<<grid, 256, 0, st>>>(a);
+        launch_pdl(k_conv1d_c4<K, 8, 16, 8>, grid, dim3(256), 0, st, a);
     } else {
         dim3 grid(cdiv(a.T, 16), cdiv(a.Cout, 16), a.B);
-        k_conv1d_c4<K, 1, 4, 32, 4><<<grid, 256, 0, st>>>(a);
+        launch_pdl(k_conv1d_c4<K, 1, 4, 32, 4>, grid, dim3(256), 0, st, a);
     }
 }
 
@@ -302,6 +303,7 @@ struct LnArgs {
 };
 
 __global__ void __launch_bounds__(256) k_layernorm_c4(LnArgs a) {
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int part = lane & 7, tsub = lane >> 3;
     const int t = (blockIdx.x * 8 + warp) * 4 + tsub;
@@ -381,8 +383,7 @@ __global__ void __launch_bounds__(256) k_layernorm_c4(LnArgs a) {
 inline void launch_layernorm(const LnArgs& a, cudaStream_t st) {
     BV2_CHECK(a.C % 4 == 0 && a.C <= 256, "layernorm C");
     dim3 grid(cdiv(a.T, 32), a.B);
-    k_layernorm_c4<<<grid, 256, 0, st>>>(a);
-    BV2_CUDA(cudaGetLastError());
+    launch_pdl(k_layernorm_c4, grid, dim3(256), 0, st, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -939,6 +940,7 @@ template <int DK, int NP>
 __global__ void __launch_bounds__(32 * NP) k_attn_softmax(const float* __restrict__ qkv, float* __restrict__ S, const float* __restrict__ rel_k,
                                                      const float* __restrict__ rel_v, float* __restrict__ att, int H, int heads, int T, int Fp,
                                                      const int* __restrict__ lens, int window) {
+    pdl_wait();
     constexpr int NCG = DK / 4;
     __shared__ float sEk[9 * DK], sEv[9 * DK];
     __shared__ float sqrel[NP][32][9];
@@ -1068,6 +1070,7 @@ __global__ void __launch_bounds__(32 * NP) k_attn_softmax(const float* __restric
 // V^T pack for the P.V GEMM: vt[z][Fp/32][8][DK][4] (the UMMA K-major B-operand image, K = keys), zeros for keys >= len.
 template <int DK>
 __global__ void k_pack_vt(const float* __restrict__ qkv, float* __restrict__ vt, int H, int heads, int T, int Fp, const int* __restrict__ lens) {
+    pdl_wait();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int cg = blockIdx.y, z = blockIdx.z, b = z / heads, h = z - b * heads;
     if (t >= Fp) return;

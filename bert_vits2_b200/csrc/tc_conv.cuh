@@ -854,18 +854,6 @@ __global__ void __launch_bounds__(352, 2) k_tc_conv1d_pstream(TcParams p, int mt
     }
 }
 
-template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    static const int pdl_env = getenv("BV2_PDL") ? atoi(getenv("BV2_PDL")) : 1;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl_env ? 1 : 0;
-    BV2_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
-}
-
 // x: c4 input [B][x.C/4][T][4]; y: c4 output ([B][y.C/4][T*max(1,ups_u)][4]).  Channel windows via e.cin_off/e.cout_off.
 inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const Act& y, const TcEpi& e, cudaStream_t st, int num_sms) {
     const int u = w.ups_u ? w.ups_u : 1;
