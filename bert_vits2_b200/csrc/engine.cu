@@ -225,7 +225,7 @@ struct bv2_engine {
             L.relv = upload(W(a + ".emb_rel_v").data);
             L.n1 = ln_from(name + ".norm_layers_1." + std::to_string(i));
             L.f1 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_1", false, tc_mode, tc_mode == 2 ? 32 : 128, 64);
-            L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2", false, tc_mode, 32, 64);
+            L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2", false, tc_mode, tc_mode == 2 ? 32 : (getenv("BV2_F2_NT") ? atoi(getenv("BV2_F2_NT")) : 32), 64);
             L.n2 = ln_from(name + ".norm_layers_2." + std::to_string(i));
             e.layers.push_back(L);
         }
@@ -455,8 +455,9 @@ void bv2_engine::finalize() {
             for (int d = 0; d < c.n_dilations; d++) {
                 rb.dil.push_back(c.resblock_dilation_sizes[j][d]);
                 const int kc = 32;  // persistent kernels hide latency with deep rings: fewer, larger chunks
-                rb.c1.push_back(conv_from(r + ".convs1." + std::to_string(d), true, tc, 0, kc));
-                rb.c2.push_back(conv_from(r + ".convs2." + std::to_string(d), true, tc, 0, kc));
+                const int nt0 = (ch >= 256 && getenv("BV2_S0_NT")) ? atoi(getenv("BV2_S0_NT")) : 0;  // tuning knob (stage 0 N tile)
+                rb.c1.push_back(conv_from(r + ".convs1." + std::to_string(d), true, tc, nt0, kc));
+                rb.c2.push_back(conv_from(r + ".convs2." + std::to_string(d), true, tc, nt0, kc));
             }
             resblocks.push_back(rb);
         }

@@ -560,8 +560,8 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
 //   * double-buffers the TMEM accumulator: the epilogue warps pre-load tile i+1's accumulator (bias/residual) and
 //     drain tile i-1 while the MMA warp works on tile i.
 // 320 threads: warp 0 producer, warp 1 MMA issuer, warps 2-5 operand prologue, warps 6-9 accumulator init + tail.
-template <int GEN>
-__global__ void __launch_bounds__(320, 3) k_tc_conv1d_persist(TcParams p, int mtiles, int ntiles_total) {
+template <int GEN, int OCC = 3>
+__global__ void __launch_bounds__(320, OCC) k_tc_conv1d_persist(TcParams p, int mtiles, int ntiles_total) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -921,13 +921,17 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
         if (!attr2) {
             BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d_persist<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d_persist<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            BV2_CUDA(cudaFuncSetAttribute(k_tc_conv1d_persist<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr2 = true;
         }
-        const int per_sm = smem_p <= 72 * 1024 ? 3 : (smem_p <= 110 * 1024 ? 2 : 1);
+        static const int occ_env = getenv("BV2_PERSIST_OCC") ? atoi(getenv("BV2_PERSIST_OCC")) : 2;  // measured: 2 CTAs/SM with 102 registers (no spills) beats 3 with 68
+        int per_sm = smem_p <= 72 * 1024 ? 3 : (smem_p <= 110 * 1024 ? 2 : 1);
+        if (occ_env == 2 && !generic) per_sm = std::min(per_sm, 2);
         const int mtiles = cdiv(p.T, 128);
         const int total = mtiles * p.B;
         const int grid_p = std::min(total, per_sm * num_sms);
-        launch_pdl(generic ? k_tc_conv1d_persist<1> : k_tc_conv1d_persist<0>, dim3(grid_p), dim3(320), smem_p, st, p, mtiles, total);
+        if (occ_env == 2 && !generic) launch_pdl(k_tc_conv1d_persist<0, 2>, dim3(grid_p), dim3(320), smem_p, st, p, mtiles, total);
+        else launch_pdl(generic ? k_tc_conv1d_persist<1> : k_tc_conv1d_persist<0>, dim3(grid_p), dim3(320), smem_p, st, p, mtiles, total);
         return;
     }
     static const int pstream_env = getenv("BV2_TC_PSTREAM") ? atoi(getenv("BV2_TC_PSTREAM")) : 1;
