@@ -192,6 +192,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("BV2_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--batched-steps", type=int, default=5, help="extra config-3 (B=32) measurement; 0 disables")
+    ap.add_argument("--gather-waveforms", action="store_true",
+                    help="N>1: also collect every rank's waveforms on rank 0 inside the timed region (optional exchange step)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -229,8 +231,10 @@ def main():
     from bert_vits2_b200.sharding import gather_waveforms
 
     def gather_wave(o, ylen):
-        # the ONLY exchange step of the path: final waveform batch to rank 0 over NVLink (NCCL); shapes may differ per rank
-        if world == 1:
+        # The path shards by utterance with NO data-path collective: every rank returns its own waveforms to its own caller
+        # (one server replica per GPU).  --gather-waveforms adds the optional collection of all waveforms on rank 0 over
+        # NVLink (NCCL; shapes may differ per rank) for jobs that write one output set from a single process.
+        if world == 1 or not args.gather_waveforms:
             return
         gather_waveforms(o, torch.as_tensor(ylen, device=o.device) * HOP, dst=0)
 
@@ -311,7 +315,8 @@ def main():
             "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": "config2: B=1, T=256 ZH phonemes per GPU, full SynthesizerTrn.infer path (transformer flow)",
                        "global_batch": world * B, "frames_per_utterance": fpu, "audio_seconds_per_step": audio / args.steps,
-                       "parallelism": f"dp{world} (utterance sharding, NCCL gather of waveforms)" if world > 1 else "single GPU",
+                       "parallelism": (f"dp{world} (utterance sharding, " + ("NCCL gather of waveforms to rank 0)" if args.gather_waveforms
+                                                                                 else "no data-path collective)")) if world > 1 else "single GPU",
                        "precision": args.precision,
                        "l2": "no explicit flush: each step streams ~0.7 GB of fp32 activations (> 126 MB L2)"},
             "e2e": {"value": e2e_v, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

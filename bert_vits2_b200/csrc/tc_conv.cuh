@@ -1026,4 +1026,250 @@ inline void tc_attn_pv(const Act& P, const float* vt, int H, int heads, const Ac
     tc_launch_simple(p, 1, P.B, st);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Fused ResBlock pair (reference modules.py:296-309):  y = conv2(lrelu(conv1(lrelu(x)))) + x  [(+ y_old) * scale]
+// conv1: K taps, dilation d;  conv2: K taps, dilation 1;  C channels in and out.  One CTA produces TO = 128-(K-1) output
+// rows: phase 1 accumulates conv1 for 128 rows in TMEM (D1), the epilogue warps turn D1 into the TF32 A-operand image
+// XT[C/4][128+K-1][4] in SHARED memory (zero outside the sequence = conv2's padding), phase 2 runs conv2 straight from
+// XT into a second accumulator (D2) that was pre-loaded with bias2 + residual.  The intermediate never touches HBM:
+// 5 activation round trips per pair become ~2.5 and two launches become one.
+struct TcPairParams {
+    const float* x; float* y; const float* w1; const float* w2; const float* b1; const float* b2;
+    int C, T, B, K, dil, KC, nchunks, R1, RT, TO, nws, nas;
+    uint32_t a_stage_bytes, w_stage_bytes, xt_bytes, tmem_cols, idesc;
+    float out_scale; int accumulate;
+};
+
+__global__ void __launch_bounds__(256, 2) k_tc_pair(TcPairParams p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int C = p.C, NAS = p.nas, NWS = p.nws, R = p.R1, RT = p.RT, ncg = p.KC / 4, NCH = p.nchunks;
+    const int t0 = blockIdx.x * p.TO, b = blockIdx.y;
+    const int p2 = (p.K - 1) / 2, p1 = p2 * p.dil;
+    uint8_t* sA = smem;
+    uint8_t* sW = sA + (size_t)NAS * p.a_stage_bytes;
+    float4* XT = reinterpret_cast<float4*>(sW + (size_t)NWS * p.w_stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(XT) + p.xt_bytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    const int B_AFULL = 0, B_AREADY = NAS, B_AEMPTY = 2 * NAS, B_WFULL = 3 * NAS, B_WEMPTY = 3 * NAS + NWS, B_INIT = 3 * NAS + 2 * NWS,
+              B_ACC1 = B_INIT + 1, B_XT = B_INIT + 2, B_ACC2 = B_INIT + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACC2 + 1);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NAS; i++) { mbar_init(BAR(B_AFULL + i), 1); mbar_init(BAR(B_AREADY + i), 128); mbar_init(BAR(B_AEMPTY + i), 1); }
+        for (int i = 0; i < NWS; i++) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
+        mbar_init(BAR(B_INIT), 128); mbar_init(BAR(B_ACC1), 1); mbar_init(BAR(B_XT), 128); mbar_init(BAR(B_ACC2), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // staged x rows r <-> t = t0 - p2 - p1 + r
+    const int tx0 = t0 - p2 - p1;
+    const int r_lo = max(0, -tx0), r_hi = min(R, p.T - tx0);
+
+    if (warp == 0) {
+        const uint32_t row_bytes = (uint32_t)(r_hi - r_lo) * 16u;
+        for (int c = 0; c < NCH; c++) {
+            const int sa = c % NAS;
+            if (lane == 0) {
+                mbar_wait(BAR(B_AEMPTY + sa), ((c / NAS) & 1) ^ 1);
+                mbar_expect_tx(BAR(B_AFULL + sa), row_bytes * ncg);
+            }
+            __syncwarp();
+            if (lane < ncg) {
+                const float* src = p.x + (((size_t)b * (C / 4) + (size_t)c * ncg + lane) * p.T + (tx0 + r_lo)) * 4;
+                bulk_g2s(smem_u32(sA + (size_t)sa * p.a_stage_bytes) + ((uint32_t)lane * R + (uint32_t)r_lo) * 16u, src, row_bytes, BAR(B_AFULL + sa));
+            }
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {
+            const size_t wst = p.w_stage_bytes / 4;
+            int wi = 0;
+            for (int ph = 0; ph < 2; ph++) {
+                const float* wsrc = ph ? p.w2 : p.w1;
+                for (int c = 0; c < NCH; c++)
+                    for (int j = 0; j < p.K; j++, wi++) {
+                        const int sw = wi % NWS;
+                        mbar_wait(BAR(B_WEMPTY + sw), ((wi / NWS) & 1) ^ 1);
+                        mbar_expect_tx(BAR(B_WFULL + sw), p.w_stage_bytes);
+                        bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), wsrc + ((size_t)c * p.K + j) * wst, p.w_stage_bytes, BAR(B_WFULL + sw));
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t b_lbo = (uint32_t)C * 16u;
+            const uint64_t b_kstep = (uint64_t)(2u * (uint32_t)C);
+            const int nk = p.KC / 8;
+            int wi = 0;
+            mbar_wait(BAR(B_INIT), 0);
+            fence_after();
+            // ---- phase 1: D1 = conv1 over the staged, activated x chunks
+            {
+                const uint32_t a_lbo = (uint32_t)R * 16u;
+                const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R);
+                for (int c = 0; c < NCH; c++) {
+                    const int sa = c % NAS;
+                    mbar_wait(BAR(B_AREADY + sa), (c / NAS) & 1);
+                    fence_after();
+                    const uint64_t a_desc0 = make_desc(smem_u32(sA + (size_t)sa * p.a_stage_bytes), a_lbo, 128u);
+                    for (int j = 0; j < p.K; j++, wi++) {
+                        const int sw = wi % NWS;
+                        mbar_wait(BAR(B_WFULL + sw), (wi / NWS) & 1);
+                        fence_after();
+                        uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(j * p.dil);
+                        uint64_t bd = make_desc(smem_u32(sW + (size_t)sw * p.w_stage_bytes), b_lbo, 128u);
+                        for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_tf32(tmem, ad, bd, p.idesc, 1u);
+                        umma_commit(BAR(B_WEMPTY + sw));
+                    }
+                    umma_commit(BAR(B_AEMPTY + sa));
+                }
+                umma_commit(BAR(B_ACC1));
+            }
+            // ---- phase 2: D2 += conv2 over XT (resident in smem)
+            mbar_wait(BAR(B_XT), 0);
+            fence_after();
+            {
+                const uint32_t a_lbo = (uint32_t)RT * 16u;
+                const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)RT);
+                const uint64_t xt_desc0 = make_desc(smem_u32(XT), a_lbo, 128u);
+                for (int c = 0; c < NCH; c++) {
+                    const uint64_t a_desc0 = xt_desc0 + (uint64_t)((uint32_t)(c * ncg) * (uint32_t)RT);
+                    for (int j = 0; j < p.K; j++, wi++) {
+                        const int sw = wi % NWS;
+                        mbar_wait(BAR(B_WFULL + sw), (wi / NWS) & 1);
+                        fence_after();
+                        uint64_t ad = a_desc0 + (uint64_t)(uint32_t)j;
+                        uint64_t bd = make_desc(smem_u32(sW + (size_t)sw * p.w_stage_bytes), b_lbo, 128u);
+                        for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_tf32(tmem + (uint32_t)C, ad, bd, p.idesc, 1u);
+                        umma_commit(BAR(B_WEMPTY + sw));
+                    }
+                }
+                umma_commit(BAR(B_ACC2));
+            }
+        }
+    } else if (warp >= 4) {
+        const int tid2 = threadIdx.x - 128;
+        const int q = warp & 3, m = q * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        const int t_out = t0 + m;
+        const bool ok_out = m < p.TO && t_out < p.T;
+        const float4* xb = reinterpret_cast<const float4*>(p.x) + (size_t)b * (C / 4) * p.T;
+        float4* yb = reinterpret_cast<float4*>(p.y) + (size_t)b * (C / 4) * p.T;
+        // ---- accumulator init: D1 = bias1 ; D2 = bias2 + x (+ y_old)
+        for (int col = 0; col < C; col += 16) {
+            uint32_t v1[16], v2[16];
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const int cg = (col >> 2) + g;
+                const float4 bb1 = *reinterpret_cast<const float4*>(p.b1 + cg * 4);
+                float4 o = *reinterpret_cast<const float4*>(p.b2 + cg * 4);
+                if (ok_out) {
+                    const float4 r = xb[(size_t)cg * p.T + t_out];
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                    if (p.accumulate) { const float4 a = yb[(size_t)cg * p.T + t_out]; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+                }
+                v1[4 * g] = __float_as_uint(bb1.x); v1[4 * g + 1] = __float_as_uint(bb1.y); v1[4 * g + 2] = __float_as_uint(bb1.z); v1[4 * g + 3] = __float_as_uint(bb1.w);
+                v2[4 * g] = __float_as_uint(o.x); v2[4 * g + 1] = __float_as_uint(o.y); v2[4 * g + 2] = __float_as_uint(o.z); v2[4 * g + 3] = __float_as_uint(o.w);
+            }
+            tmem_st16(trow + (uint32_t)col, v1);
+            tmem_st16(trow + (uint32_t)(C + col), v2);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        fence_before();
+        mbar_arrive(BAR(B_INIT));
+        // ---- operand prologue of the x chunks (phase 1)
+        for (int c = 0; c < NCH; c++) {
+            const int sa = c % NAS;
+            mbar_wait(BAR(B_AFULL + sa), (c / NAS) & 1);
+            xform_stage(reinterpret_cast<float4*>(sA + (size_t)sa * p.a_stage_bytes), ncg, R, r_lo, r_hi, 0.1f, tid2);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(BAR(B_AREADY + sa));
+        }
+        // ---- epilogue 1: D1 -> lrelu -> TF32 -> XT (A-operand image of conv2); rows outside the sequence are conv2's zero padding
+        mbar_wait(BAR(B_ACC1), 0);
+        fence_after();
+        const int t_xt = t0 - p2 + m;
+        const bool xt_in = t_xt >= 0 && t_xt < p.T;
+        for (int col = 0; col < C; col += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + (uint32_t)col, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (xt_in) {
+                    o.x = to_tf32(lrelu(__uint_as_float(v[4 * g]), 0.1f)); o.y = to_tf32(lrelu(__uint_as_float(v[4 * g + 1]), 0.1f));
+                    o.z = to_tf32(lrelu(__uint_as_float(v[4 * g + 2]), 0.1f)); o.w = to_tf32(lrelu(__uint_as_float(v[4 * g + 3]), 0.1f));
+                }
+                XT[(size_t)((col >> 2) + g) * RT + m] = o;
+            }
+        }
+        if (m < p.K - 1)  // rows 128..RT-1 are only read by the discarded output rows; keep them finite
+            for (int cg = 0; cg < C / 4; cg++) XT[(size_t)cg * RT + 128 + m] = make_float4(0.f, 0.f, 0.f, 0.f);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fence_before();
+        mbar_arrive(BAR(B_XT));
+        // ---- tail: D2 -> scale -> store the TO valid rows
+        mbar_wait(BAR(B_ACC2), 0);
+        fence_after();
+        for (int col = 0; col < C; col += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + (uint32_t)(C + col), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (!ok_out) continue;
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+                yb[(size_t)((col >> 2) + g) * p.T + t_out] = make_float4(__uint_as_float(v[4 * g]) * p.out_scale, __uint_as_float(v[4 * g + 1]) * p.out_scale,
+                                                                         __uint_as_float(v[4 * g + 2]) * p.out_scale, __uint_as_float(v[4 * g + 3]) * p.out_scale);
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// returns false when the shapes do not fit (caller falls back to two launches)
+inline bool tc_pair(const TcConvW& w1, const TcConvW& w2, const float* b1, const float* b2, const Act& x, const Act& y, int dil, float out_scale,
+                    int accumulate, cudaStream_t st) {
+    const int C = w1.Cin;
+    if (!(w1.Cout == C && w2.Cin == C && w2.Cout == C && w1.K == w2.K && w1.KC == w2.KC && w1.nt == C && w2.nt == C && !w1.x3 && !w1.ups_u && C <= 128 && (w1.K & 1)))
+        return false;
+    TcPairParams p{};
+    p.x = x.p; p.y = y.p; p.w1 = w1.w; p.w2 = w2.w; p.b1 = b1; p.b2 = b2;
+    p.C = C; p.T = x.T; p.B = x.B; p.K = w1.K; p.dil = dil; p.KC = w1.KC; p.nchunks = w1.nchunks;
+    p.R1 = 128 + (p.K - 1) * dil; p.RT = 128 + p.K - 1; p.TO = 128 - (p.K - 1);
+    p.a_stage_bytes = (uint32_t)(p.KC * p.R1 * 4); p.w_stage_bytes = (uint32_t)(p.KC * C * 4); p.xt_bytes = (uint32_t)(C * p.RT * 4);
+    p.nas = std::min(2, std::max(2, p.nchunks));
+    const long long fixed = (long long)p.nas * p.a_stage_bytes + p.xt_bytes + 1024;
+    // shared-memory budgets for 3 / 2 / 1 resident CTAs per SM; take the first that leaves a >=3-deep weight ring
+    int nws = 0;
+    for (long long budget : {74LL * 1024, 112LL * 1024, 224LL * 1024}) {
+        nws = (int)((budget - fixed) / (long long)p.w_stage_bytes);
+        if (nws >= 3) break;
+    }
+    if (nws < 2) return false;
+    p.nws = std::min(nws, 6);
+    uint32_t cols = 32; while ((int)cols < 2 * C) cols <<= 1;
+    p.tmem_cols = cols;
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
+    p.out_scale = out_scale; p.accumulate = accumulate;
+    const size_t smem = (size_t)p.nas * p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + p.xt_bytes + (size_t)(3 * p.nas + 2 * p.nws + 5) * 8 + 16;
+    static bool attr = false;
+    if (!attr) { BV2_CUDA(cudaFuncSetAttribute(k_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    launch_pdl(k_tc_pair, dim3(cdiv(p.T, p.TO), p.B), dim3(256), smem, st, p);
+    return true;
+}
+
 }  // namespace bv2

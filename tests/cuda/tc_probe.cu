@@ -183,6 +183,94 @@ static int run_x3(int Cin, int Cout, int K, int T, int nt) {
     return ok ? 0 : 1;
 }
 
+// Fused ResBlock pair: y = (conv2(lrelu(conv1(lrelu(x)))) + x [+ y0]) * scale, checked at sampled time steps.
+static int run_pair(int C, int K, int dil, int T, int B, bool acc, float scale, int iters, int kc = 0) {
+    std::mt19937 rng(C * 31 + K * 7 + dil + T);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    std::vector<float> x((size_t)B * C * T), w1((size_t)C * C * K), w2((size_t)C * C * K), b1(C), b2(C), y0((size_t)B * C * T);
+    for (auto& v : x) v = nd(rng);
+    for (auto& v : w1) v = nd(rng) / std::sqrt((float)(C * K));
+    for (auto& v : w2) v = nd(rng) / std::sqrt((float)(C * K));
+    for (auto& v : b1) v = nd(rng);
+    for (auto& v : b2) v = nd(rng);
+    for (auto& v : y0) v = nd(rng);
+    auto to_c4 = [&](const std::vector<float>& s) {
+        std::vector<float> d(s.size());
+        for (int b = 0; b < B; b++) for (int c = 0; c < C; c++) for (int t = 0; t < T; t++)
+            d[(((size_t)b * (C / 4) + c / 4) * T + t) * 4 + (c & 3)] = s[((size_t)b * C + c) * T + t];
+        return d;
+    };
+    std::function<float*(const std::vector<float>&)> upf = up;
+    TcConvW tw1 = tc_pack_weights(upf, w1, C, C, K, C, 0, kc), tw2 = tc_pack_weights(upf, w2, C, C, K, C, 0, kc);
+    Act ax; ax.B = B; ax.C = C; ax.T = T; ax.p = up(to_c4(x));
+    Act ay; ay.B = B; ay.C = C; ay.T = T; ay.p = up(to_c4(y0));
+    float* db1 = up(b1); float* db2 = up(b2);
+    if (!tc_pair(tw1, tw2, db1, db2, ax, ay, dil, scale, acc ? 1 : 0, 0)) { printf("SKIP pair C=%d K=%d (does not fit)\n", C, K); return 0; }
+    cudaError_t er = cudaDeviceSynchronize();
+    if (er != cudaSuccess) { printf("CUDA error (pair C=%d K=%d d=%d): %s\n", C, K, dil, cudaGetErrorString(er)); return 1; }
+    std::vector<float> got((size_t)B * C * T);
+    cudaMemcpy(got.data(), ay.p, got.size() * 4, cudaMemcpyDeviceToHost);
+    const int p2 = (K - 1) / 2, p1 = p2 * dil;
+    std::vector<float> xa(x.size()), w1r(w1.size()), w2r(w2.size());
+    for (size_t i = 0; i < x.size(); i++) { float v = x[i]; v = v > 0 ? v : v * 0.1f; xa[i] = tf32_rn_host(v); }
+    for (size_t i = 0; i < w1.size(); i++) { w1r[i] = tf32_rn_host(w1[i]); w2r[i] = tf32_rn_host(w2[i]); }
+    double maxerr = 0, maxref = 0;
+    std::vector<float> xt((size_t)C * K);
+    std::vector<int> ts;
+    for (int t = 0; t < T; t += std::max(1, T / 150 - 1)) ts.push_back(t);
+    for (int t : {1, 2, T - 2, T - 1, 117, 118, 119, 127, 128, 129}) if (t >= 0 && t < T) ts.push_back(t);
+    for (int b = 0; b < B; b++)
+        for (int t : ts) {
+            for (int c = 0; c < C; c++)
+                for (int j2 = 0; j2 < K; j2++) {
+                    const int tt = t + j2 - p2;
+                    float o = 0.f;
+                    if (tt >= 0 && tt < T) {
+                        double s = b1[c];
+                        for (int ci = 0; ci < C; ci++)
+                            for (int j = 0; j < K; j++) {
+                                const int tx = tt + j * dil - p1;
+                                if (tx >= 0 && tx < T) s += (double)xa[((size_t)b * C + ci) * T + tx] * w1r[((size_t)c * C + ci) * K + j];
+                            }
+                        float v = (float)s; v = v > 0 ? v : v * 0.1f; o = tf32_rn_host(v);
+                    }
+                    xt[(size_t)c * K + j2] = o;
+                }
+            for (int co = 0; co < C; co++) {
+                double s = b2[co];
+                for (int c = 0; c < C; c++)
+                    for (int j2 = 0; j2 < K; j2++) s += (double)xt[(size_t)c * K + j2] * w2r[((size_t)co * C + c) * K + j2];
+                s += x[((size_t)b * C + co) * T + t];
+                if (acc) s += y0[((size_t)b * C + co) * T + t];
+                s *= scale;
+                const double g = got[(((size_t)b * (C / 4) + co / 4) * T + t) * 4 + (co & 3)];
+                maxerr = std::max(maxerr, std::fabs(g - s)); maxref = std::max(maxref, std::fabs(s));
+            }
+        }
+    float ms = 0, ms2 = 0;
+    if (iters > 0) {
+        cudaEvent_t a, c; cudaEventCreate(&a); cudaEventCreate(&c);
+        for (int i = 0; i < 3; i++) tc_pair(tw1, tw2, db1, db2, ax, ay, dil, scale, 0, 0);
+        cudaEventRecord(a);
+        for (int i = 0; i < iters; i++) tc_pair(tw1, tw2, db1, db2, ax, ay, dil, scale, 0, 0);
+        cudaEventRecord(c); cudaEventSynchronize(c); cudaEventElapsedTime(&ms, a, c); ms /= iters;
+        // the two-launch path it replaces
+        Act am; am.B = B; am.C = C; am.T = T; am.p = up(std::vector<float>((size_t)B * C * T));
+        TcEpi e1; e1.in_slope = 0.1f; e1.dil = dil;
+        TcEpi e2; e2.in_slope = 0.1f; e2.dil = 1; e2.res = ax.p; e2.res_mode = 1; e2.out_scale = scale;
+        for (int i = 0; i < 3; i++) { tc_conv1d(tw1, db1, ax, am, e1, 0, 148); tc_conv1d(tw2, db2, am, ay, e2, 0, 148); }
+        cudaEventRecord(a);
+        for (int i = 0; i < iters; i++) { tc_conv1d(tw1, db1, ax, am, e1, 0, 148); tc_conv1d(tw2, db2, am, ay, e2, 0, 148); }
+        cudaEventRecord(c); cudaEventSynchronize(c); cudaEventElapsedTime(&ms2, a, c); ms2 /= iters;
+    }
+    bool ok = maxerr < 2e-3 * std::max(1.0, maxref);
+    printf("%s PAIR C=%3d K=%2d dil=%d T=%6d B=%d acc=%d kc=%d : maxerr %.3e (ref max %.2f)", ok ? "PASS" : "FAIL", C, K, dil, T, B, (int)acc, tw1.KC, maxerr, maxref);
+    if (iters > 0) printf("  | fused %.3f ms  vs two launches %.3f ms  (%.2fx)", ms, ms2, ms2 / ms);
+    printf("\n");
+    fflush(stdout);
+    return ok ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
     int fails = 0;
     bool perf = argc > 1;
@@ -205,6 +293,12 @@ int main(int argc, char** argv) {
         fails += run_case(32, 32, 7, 3, 20000, 3, 0.1f, true, false, 1.f, 0);        // persistent kernel (narrow, many tiles), batched
         fails += run_case(16, 16, 11, 5, 40001, 1, 0.1f, true, true, 1.f / 3, 0);    // persistent kernel, residual + accumulate + scale
         fails += run_case(32, 32, 3, 1, 38000, 2, 0.1f, false, false, 1.f, 0);
+        fails += run_pair(16, 3, 1, 300, 1, false, 1.f, 0);
+        fails += run_pair(32, 7, 3, 1000, 2, false, 1.f, 0);
+        fails += run_pair(64, 11, 5, 700, 1, true, 1.f / 3, 0);
+        fails += run_pair(128, 3, 5, 517, 1, false, 1.f, 0);
+        fails += run_pair(128, 11, 5, 1300, 2, true, 1.f / 3, 0);
+        fails += run_pair(64, 7, 1, 118, 1, false, 1.f, 0);
         fails += run_x3(32, 32, 1, 100, 32);
         fails += run_x3(192, 192, 3, 256, 32);
         fails += run_x3(768, 192, 3, 256, 32);
@@ -219,6 +313,14 @@ int main(int argc, char** argv) {
             fails += run_ups(128, 64, 8, 2, 1573 * 64, 1, 10);
             fails += run_ups(64, 32, 2, 2, 1573 * 128, 1, 10);
             fails += run_ups(32, 16, 2, 2, 1573 * 256, 1, 10);
+        }
+        if (perf) {
+            int F = 1573;
+            int Cs[4] = {128, 64, 32, 16}; int Ls[4] = {64, 128, 256, 512};
+            for (int s = 0; s < 4; s++)
+                for (int k : {3, 7, 11})
+                    for (int d : {1, 5}) fails += run_pair(Cs[s], k, d, Ls[s] * F, 1, false, 1.f, 10);
+            for (int k : {3, 11}) fails += run_pair(128, k, 3, 64 * F, 1, false, 1.f, 10, 16);
         }
         if (perf) {
             // Generator MRF shapes at F=1024 frames
