@@ -192,8 +192,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("BV2_PRECISION", "tf32"), choices=["fp32", "tf32"])
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--batched-steps", type=int, default=5, help="extra config-3 (B=32) measurement; 0 disables")
-    ap.add_argument("--gather-waveforms", action="store_true",
-                    help="N>1: also collect every rank's waveforms on rank 0 inside the timed region (optional exchange step)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl", "none"],
+                    help="N>1: how the finished waveforms reach rank 0 inside the timed region (see step_resident)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -228,31 +228,82 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    from bert_vits2_b200.sharding import gather_waveforms
+    from bert_vits2_b200.sharding import PeerWaveSlab, gather_waveforms
 
-    def gather_wave(o, ylen):
-        # The path shards by utterance with NO data-path collective: every rank returns its own waveforms to its own caller
-        # (one server replica per GPU).  --gather-waveforms adds the optional collection of all waveforms on rank 0 over
-        # NVLink (NCCL; shapes may differ per rank) for jobs that write one output set from a single process.
-        if world == 1 or not args.gather_waveforms:
-            return
-        gather_waveforms(o, torch.as_tensor(ylen, device=o.device) * HOP, dst=0)
+    # ---- multi-GPU exchange step.  Utterances shard with no data-path collective; the finished waveforms
+    # are collected on rank 0.  --exchange p2p (default): the Generator's conv_post+tanh epilogue stores straight into a
+    # CUDA-IPC mapped slab in rank 0's HBM over NVLink/NVSwitch (fused compute + transfer, NCCL carries a 4-byte flag);
+    # --exchange nccl: padded NCCL gather of the finished tensors (baseline); --exchange none: every rank keeps its output.
+    exchange = args.exchange if world > 1 else "none"
+    slab = None
+    step_no = [0]
+    if exchange == "p2p":
+        _, F0 = eng.infer_begin(d_inp["x"], d_inp["x_lengths"], d_inp["sid"], d_inp["tone"], d_inp["language"], d_inp["bert"],
+                                d_inp["ja_bert"], d_inp["en_bert"], d_nw, INFER_KW["noise_scale_w"], INFER_KW["length_scale"],
+                                INFER_KW["sdp_ratio"])
+        eng.infer_finish(B, T, F0, d_nz, INFER_KW["noise_scale"])
+        fcap = torch.tensor([F0], device=dev); dist.all_reduce(fcap, op=dist.ReduceOp.MAX)
+        try:
+            slab = PeerWaveSlab(dev, B, 2 * int(fcap) * HOP, dst=0, slots=2)
+        except RuntimeError as ex:  # raised on every rank together (collective constructor): fall back to the NCCL gather
+            if rank == 0:
+                print(f"[bench] peer slab unavailable ({ex}); using the NCCL gather", file=sys.stderr, flush=True)
+            exchange = "nccl"
 
     def step_resident():
         ylen, F = eng.infer_begin(d_inp["x"], d_inp["x_lengths"], d_inp["sid"], d_inp["tone"], d_inp["language"], d_inp["bert"],
                                   d_inp["ja_bert"], d_inp["en_bert"], d_nw, INFER_KW["noise_scale_w"], INFER_KW["length_scale"],
                                   INFER_KW["sdp_ratio"])
-        o, attn, y_mask, aux = eng.infer_finish(B, T, F, d_nz, INFER_KW["noise_scale"])
-        gather_wave(o, ylen)
+        if slab is not None:
+            slot = step_no[0] % 2; step_no[0] += 1
+            slab.wait(slot)  # slot reuse: ordered after the completion flag of the step that used it last
+            if not slab.fits(B, F * HOP):
+                raise RuntimeError("waveform batch exceeds the peer slab slot")
+            o, attn, y_mask, aux = eng.infer_finish(B, T, F, d_nz, INFER_KW["noise_scale"], out_ptr=slab.wave_ptr(slot))
+            slab.publish(slot, B, F * HOP, ylen * HOP)
+        else:
+            o, attn, y_mask, aux = eng.infer_finish(B, T, F, d_nz, INFER_KW["noise_scale"])
+            if exchange == "nccl":
+                gather_waveforms(o, torch.as_tensor(ylen, device=o.device) * HOP, dst=0)
         return int(ylen.sum()), o
 
     def step_e2e():
         dd = {k: v.to(dev, non_blocking=True) for k, v in h_inp.items()}
         o, attn, y_mask, aux = net.infer(dd["x"], dd["x_lengths"], dd["sid"], dd["tone"], dd["language"], dd["bert"], dd["ja_bert"],
                                          dd["en_bert"], **INFER_KW)
-        gather_wave(o, net.last_y_lengths)
+        if slab is not None:  # API-level variant: the caller holds the tensor, one peer copy puts it into rank 0's slab
+            slot = step_no[0] % 2; step_no[0] += 1
+            slab.wait(slot)
+            slab.publish(slot, B, o.shape[-1], net.last_y_lengths * HOP, wave=o)
+        elif exchange == "nccl":
+            gather_waveforms(o, torch.as_tensor(net.last_y_lengths, device=o.device) * HOP, dst=0)
         wav = o[:, 0].cpu()  # D2H of the step's result, as infer.py:315-318 does
         return int(net.last_y_lengths.sum()), wav
+
+    def check_exchange():
+        """After the timed loops: rank 0 reads every rank's last waveform out of the slab and compares its checksum with the
+        one the producing rank computes from a local, un-exchanged run of the same inputs (bit-exact path)."""
+        ylen, F = eng.infer_begin(d_inp["x"], d_inp["x_lengths"], d_inp["sid"], d_inp["tone"], d_inp["language"], d_inp["bert"],
+                                  d_inp["ja_bert"], d_inp["en_bert"], d_nw, INFER_KW["noise_scale_w"], INFER_KW["length_scale"],
+                                  INFER_KW["sdp_ratio"])
+        o_loc = eng.infer_finish(B, T, F, d_nz, INFER_KW["noise_scale"])[0]
+        eng.infer_begin(d_inp["x"], d_inp["x_lengths"], d_inp["sid"], d_inp["tone"], d_inp["language"], d_inp["bert"],
+                        d_inp["ja_bert"], d_inp["en_bert"], d_nw, INFER_KW["noise_scale_w"], INFER_KW["length_scale"], INFER_KW["sdp_ratio"])
+        slab.wait(0)
+        eng.infer_finish(B, T, F, d_nz, INFER_KW["noise_scale"], out_ptr=slab.wave_ptr(0))
+        slab.publish(0, B, F * HOP, ylen * HOP)
+        mine = torch.stack([o_loc.double().abs().sum(), torch.tensor(float(F * HOP), device=dev, dtype=torch.float64)])
+        allsum = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allsum, mine)
+        waves, counts = slab.collect(0)
+        ok = True
+        if rank == 0:
+            for r in range(world):
+                got = waves[r].double().abs().sum()
+                ok &= bool(waves[r].shape[-1] == int(allsum[r][1])) and bool(torch.isfinite(waves[r]).all())
+                ok &= bool(torch.allclose(got, allsum[r][0], rtol=1e-9, atol=0.0)) and float(got) > 0.0
+            ok &= bool(torch.equal(waves[0], o_loc))
+        return ok
 
     # ---------------- device-resident value
     for _ in range(args.warmup):
@@ -291,6 +342,10 @@ def main():
     ms_e = t0.elapsed_time(t1)
     h2d = sum(v.numel() * v.element_size() for v in h_inp.values())
     d2h = wav.numel() * wav.element_size()
+    exchange_ok = None
+    if slab is not None:
+        exchange_ok = check_exchange()
+        slab.close()
     # ---------------- max over ranks
     stats = torch.tensor([ms, ms_e, float(frames), float(frames_e)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -315,13 +370,15 @@ def main():
             "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": "config2: B=1, T=256 ZH phonemes per GPU, full SynthesizerTrn.infer path (transformer flow)",
                        "global_batch": world * B, "frames_per_utterance": fpu, "audio_seconds_per_step": audio / args.steps,
-                       "parallelism": (f"dp{world} (utterance sharding, " + ("NCCL gather of waveforms to rank 0)" if args.gather_waveforms
-                                                                                 else "no data-path collective)")) if world > 1 else "single GPU",
+                       "parallelism": (f"dp{world} (utterance sharding; waveforms to rank 0: " +
+                                       {"p2p": "Generator epilogue stores into a CUDA-IPC slab over NVLink, 4-byte NCCL flag)",
+                                        "nccl": "padded NCCL gather)", "none": "none)"}[exchange]) if world > 1 else "single GPU",
                        "precision": args.precision,
                        "l2": "no explicit flush: each step streams ~0.7 GB of fp32 activations (> 126 MB L2)"},
             "e2e": {"value": e2e_v, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e / args.steps},
             "gpu_launches": int(launches),
+            **({"exchange": {"kind": exchange, "verified": exchange_ok}} if world > 1 else {}),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "Generator stage (conv_pre .. conv_post+tanh, 98 convolutions)", "achieved": ach, "peak": hbm,
                          "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "peak_source": how, "stage_ms": g_ms,

@@ -50,6 +50,11 @@ SYMBOLS = {
     "bv2_stage_ms": (C.c_float, [P, C.c_char_p]),
     "bv2_launch_count": (C.c_int64, [P]),
     "bv2_workspace_bytes": (C.c_int64, [P]),
+    "bv2_peer_slab_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "bv2_peer_slab_open": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bv2_peer_slab_close": (C.c_int, [C.c_int, C.c_void_p]),
+    "bv2_peer_slab_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "bv2_peer_write": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "bv2_last_error": (C.c_char_p, [P]),
     "bv2_destroy": (None, [P]),
 }

@@ -1061,6 +1061,49 @@ float bv2_stage_ms(bv2_engine* e, const char* stage) {
 
 int64_t bv2_launch_count(const bv2_engine* e) { return e ? e->launches : 0; }
 int64_t bv2_workspace_bytes(const bv2_engine* e) { return e ? (int64_t)(e->ws.cap() + e->persist.cap()) : 0; }
+// ---- peer output slab (multi-GPU exchange step): plain CUDA IPC plumbing, no engine state
+static_assert(sizeof(cudaIpcMemHandle_t) == BV2_IPC_HANDLE_BYTES, "IPC handle size");
+int bv2_peer_slab_alloc(int dev, int64_t bytes, void** dptr, unsigned char* handle_out) {
+    if (!dptr || !handle_out || bytes <= 0) return BV2_ERR_ARG;
+    *dptr = nullptr;
+    if (cudaSetDevice(dev) != cudaSuccess) return BV2_ERR_CUDA;
+    void* p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) return BV2_ERR_CUDA;
+    cudaIpcMemHandle_t h;
+    if (cudaMemset(p, 0, (size_t)bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+        cudaIpcGetMemHandle(&h, p) != cudaSuccess) { cudaFree(p); return BV2_ERR_CUDA; }
+    memcpy(handle_out, &h, sizeof(h));
+    *dptr = p;
+    return BV2_OK;
+}
+int bv2_peer_slab_open(int dev, const unsigned char* handle, void** dptr) {
+    if (!dptr || !handle) return BV2_ERR_ARG;
+    *dptr = nullptr;
+    if (cudaSetDevice(dev) != cudaSuccess) return BV2_ERR_CUDA;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return BV2_ERR_CUDA; }
+    *dptr = p;
+    return BV2_OK;
+}
+int bv2_peer_slab_close(int dev, void* dptr) {
+    if (!dptr) return BV2_ERR_ARG;
+    if (cudaSetDevice(dev) != cudaSuccess || cudaIpcCloseMemHandle(dptr) != cudaSuccess) return BV2_ERR_CUDA;
+    return BV2_OK;
+}
+int bv2_peer_slab_free(int dev, void* dptr) {
+    if (!dptr) return BV2_ERR_ARG;
+    if (cudaSetDevice(dev) != cudaSuccess || cudaFree(dptr) != cudaSuccess) return BV2_ERR_CUDA;
+    return BV2_OK;
+}
+int bv2_peer_write(int dev, void* dst, const void* src, int64_t bytes, void* stream) {
+    if (!dst || !src || bytes < 0) return BV2_ERR_ARG;
+    if (cudaSetDevice(dev) != cudaSuccess) return BV2_ERR_CUDA;
+    if (bytes && cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) return BV2_ERR_CUDA;
+    return BV2_OK;
+}
+
 const char* bv2_last_error(const bv2_engine* e) { return e ? e->err.c_str() : "null engine"; }
 void bv2_destroy(bv2_engine* e) { delete e; }
 

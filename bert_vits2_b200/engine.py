@@ -122,18 +122,22 @@ class Engine:
                                              float(sdp_ratio), _ptr(k[9]), self._stream(), ylen, C.byref(fmax)))
         return np.frombuffer(ylen, dtype=np.int64).copy(), int(fmax.value)
 
-    def infer_finish(self, B, T, F, noise_z, noise_scale, max_len=None, want_attn=True):
+    def infer_finish(self, B, T, F, noise_z, noise_scale, max_len=None, want_attn=True, out_ptr: Optional[int] = None):
+        """`out_ptr`: raw device address that receives the waveform batch [B,1,Fg*hop] instead of a fresh tensor -- e.g. a
+        slice of a peer-mapped slab (sharding.PeerWaveSlab) so the Generator epilogue stores straight into the root GPU's
+        memory over NVLink; the returned `o` is then None."""
         I, hop = self.cfg.inter_channels, self.cfg.hop
         noise_z = self._f32(noise_z)
         assert noise_z.shape[0] == B and noise_z.shape[1] == I and noise_z.shape[2] >= F
         Fg = F if (max_len is None or max_len >= F) else int(max_len)
         dev = self.device
-        o = torch.empty(B, 1, Fg * hop, device=dev, dtype=torch.float32)
+        o = torch.empty(B, 1, Fg * hop, device=dev, dtype=torch.float32) if out_ptr is None else None
         attn = torch.empty(B, 1, F, T, device=dev, dtype=torch.float32) if want_attn else None
         y_mask = torch.empty(B, 1, F, device=dev, dtype=torch.float32)
         z, z_p, m_p, logs_p = (torch.empty(B, I, F, device=dev, dtype=torch.float32) for _ in range(4))
         self._check(self.lib.bv2_infer_finish(self._h, _ptr(noise_z), noise_z.shape[2], float(noise_scale),
-                                              -1 if max_len is None else int(max_len), _ptr(o), _ptr(attn), _ptr(y_mask), _ptr(z),
+                                              -1 if max_len is None else int(max_len), _ptr(o) if out_ptr is None else C.c_void_p(int(out_ptr)),
+                                              _ptr(attn), _ptr(y_mask), _ptr(z),
                                               _ptr(z_p), _ptr(m_p), _ptr(logs_p), self._stream()))
         return o, attn, y_mask, (z, z_p, m_p, logs_p)
 

@@ -112,6 +112,23 @@ float bv2_stage_ms(bv2_engine* e, const char* stage);
 int64_t bv2_launch_count(const bv2_engine* e);
 int64_t bv2_workspace_bytes(const bv2_engine* e);
 
+/* Peer output slab -- the path's one exchange step on a multi-GPU node (the reference has no equivalent:
+ * its inference is single-device, webui.py:31, 397-399).  The root rank owns a device slab and exports its CUDA IPC
+ * handle; every other rank (one process per GPU) opens it and passes a slice of the mapped address as the `o` output
+ * pointer of bv2_infer_finish / bv2_generator, so the conv_post+tanh epilogue stores the finished waveform straight
+ * into the root's memory over NVLink/NVSwitch (peer stores, no staging copy, no NCCL payload).
+ *   bv2_peer_slab_alloc : cudaMalloc `bytes` on `cuda_device`, zero it, return the pointer and the 64-byte IPC handle
+ *   bv2_peer_slab_open  : map a slab exported by another process into this one (lazy peer access)
+ *   bv2_peer_slab_close : unmap (opener side);  bv2_peer_slab_free : release (owner side)
+ *   bv2_peer_write      : async device->device copy of `bytes` into a (possibly peer-mapped) slab address on `stream`
+ * All return BV2_OK or a negative status; none of them needs an engine. */
+#define BV2_IPC_HANDLE_BYTES 64
+int bv2_peer_slab_alloc(int cuda_device, int64_t bytes, void** dptr, unsigned char* handle_out);
+int bv2_peer_slab_open(int cuda_device, const unsigned char* handle, void** dptr);
+int bv2_peer_slab_close(int cuda_device, void* dptr);
+int bv2_peer_slab_free(int cuda_device, void* dptr);
+int bv2_peer_write(int cuda_device, void* dst, const void* src, int64_t bytes, void* stream);
+
 const char* bv2_last_error(const bv2_engine* e);
 const char* bv2_version(void);
 void bv2_destroy(bv2_engine* e);

@@ -193,6 +193,41 @@ def test_single_token_and_determinism(engines):
     assert ref.shape == outs[0].shape and rms(outs[0], ref) < 5e-5
 
 
+def test_peer_slab_output_pointer_world1(engines):
+    """SURVEY.md section 8e exchange step, single-process part: the engine stores the waveform batch through a raw output
+    pointer into a libbv2-owned slab (the address a peer rank would have mapped with CUDA IPC), the meta record follows by
+    bv2_peer_write, and the root-side views equal an ordinary infer() bit for bit.  Both the fused (out_ptr) and the
+    API-level (copy of a finished tensor) variants, two slots."""
+    from bert_vits2_b200.sharding import PeerWaveSlab
+    cfg, sd = model_for(True, 0)
+    eng = engines(True, "tf32")
+    inp = synth.synthetic_inputs(cfg, [7, 12], [0, 2], seed=31)
+    nw, nz = synth.synthetic_noise(cfg, 2, 12, 512, seed=32)
+    ylen, F = eng.infer_begin(inp["x"], inp["x_lengths"], inp["sid"], inp["tone"], inp["language"], inp["bert"], inp["ja_bert"],
+                              inp["en_bert"], nw, 0.9, 1.0, 0.5)
+    o_ref, *_ = eng.infer_finish(2, 12, F, nz, 0.6)
+    L = F * cfg.hop
+    slab = PeerWaveSlab("cuda:0", 2, 2 * L, slots=2)
+    try:
+        assert slab.fits(2, L) and not slab.fits(3, L) and not slab.fits(2, 5 * L)
+        ylen2, F2 = eng.infer_begin(inp["x"], inp["x_lengths"], inp["sid"], inp["tone"], inp["language"], inp["bert"], inp["ja_bert"],
+                                    inp["en_bert"], nw, 0.9, 1.0, 0.5)
+        assert F2 == F
+        o_none, *_ = eng.infer_finish(2, 12, F, nz, 0.6, out_ptr=slab.wave_ptr(0))
+        assert o_none is None
+        slab.publish(0, 2, L, ylen2 * cfg.hop)
+        slab.publish(1, 2, L, ylen * cfg.hop, wave=o_ref)
+        for slot in (0, 1):
+            waves, counts = slab.collect(slot)
+            assert len(waves) == 1 and tuple(waves[0].shape) == (2, 1, L)
+            assert torch.equal(waves[0], o_ref)
+            assert counts[0].tolist() == [int(v) * cfg.hop for v in ylen]
+        with pytest.raises(ValueError):
+            slab.publish(0, 3, L, [1, 2, 3])
+    finally:
+        slab.close()
+
+
 @pytest.mark.parametrize("precision", PRECISIONS)
 def test_config2_full_size_against_oracle(engines, precision):
     """BASELINE.json config 2: B=1, 256-phoneme ZH utterance, full path; waveform RMS vs the CPU oracle < 1e-3."""
