@@ -1272,4 +1272,256 @@ inline bool tc_pair(const TcConvW& w1, const TcConvW& w2, const float* b1, const
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Persistent fused ResBlock pair (round-2 form of k_tc_pair; C <= 32): both weight tensors stay resident in shared
+// memory, each CTA walks tiles g = blockIdx.x, +gridDim.x, ... and software-pipelines them across the roles:
+//   warp 0      TMA producer: x tile i+2 while ...
+//   warps 2-5   operand prologue (lrelu + RN-TF32) of x tile i+1
+//   warp 1      MMA: conv1(tile i+1) into D1[(i+1)&1], then conv2(tile i) from XT[i&1] into D2[i&1]
+//   warps 6-9   D2 init (bias2 + residual [+ y_old]) of tile i+1, D1 -> XT of tile i+1, tail (D2 -> HBM) of tile i
+// D1, D2 and XT are double-buffered, so conv2 of a tile overlaps conv1 of the next and both overlap the epilogues.
+struct TcPairPParams {
+    const float* x; float* y; const float* w1; const float* w2; const float* b1; const float* b2;
+    int C, T, B, K, dil, R1, RT, TO, nas, tiles_per_b, total_tiles;
+    uint32_t a_stage_bytes, w_bytes, xt_bytes, tmem_cols, idesc;
+    float out_scale; int accumulate;
+};
+
+__global__ void __launch_bounds__(320, 2) k_tc_pair_persist(TcPairPParams p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int C = p.C, NAS = p.nas, R = p.R1, RT = p.RT, ncg = C / 4;
+    const int p2 = (p.K - 1) / 2, p1 = p2 * p.dil;
+    uint8_t* sW1 = smem;
+    uint8_t* sW2 = sW1 + p.w_bytes;
+    uint8_t* sA = sW2 + p.w_bytes;
+    uint8_t* sXT = sA + (size_t)NAS * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sXT + 2 * (size_t)p.xt_bytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    const int B_AFULL = 0, B_AREADY = NAS, B_AEMPTY = 2 * NAS, B_W = 3 * NAS, B_D1FULL = B_W + 1, B_D1EMPTY = B_W + 3, B_XTFULL = B_W + 5,
+              B_D2FULL = B_W + 7, NBARS = B_W + 9;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NAS; i++) { mbar_init(BAR(B_AFULL + i), 1); mbar_init(BAR(B_AREADY + i), 128); mbar_init(BAR(B_AEMPTY + i), 1); }
+        mbar_init(BAR(B_W), 1);
+        for (int i = 0; i < 2; i++) {
+            mbar_init(BAR(B_D1FULL + i), 1); mbar_init(BAR(B_D1EMPTY + i), 128); mbar_init(BAR(B_XTFULL + i), 128); mbar_init(BAR(B_D2FULL + i), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int ntl = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
+    // tile i of this CTA -> (batch, first output row)
+    auto tile_bt = [&](int i, int& b, int& t0) {
+        const int g = (int)blockIdx.x + i * (int)gridDim.x;
+        b = g / p.tiles_per_b;
+        t0 = (g - b * p.tiles_per_b) * p.TO;
+    };
+
+    if (warp == 0) {
+        // resident weights: independent of the upstream kernel, so they load before the PDL wait
+        if (lane == 0) {
+            mbar_expect_tx(BAR(B_W), 2 * p.w_bytes);
+            bulk_g2s(smem_u32(sW1), p.w1, p.w_bytes, BAR(B_W));
+            bulk_g2s(smem_u32(sW2), p.w2, p.w_bytes, BAR(B_W));
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        for (int i = 0; i < ntl; i++) {
+            int b, t0; tile_bt(i, b, t0);
+            const int tx0 = t0 - p2 - p1;
+            const int r_lo = max(0, -tx0), r_hi = min(R, p.T - tx0);
+            const uint32_t row_bytes = (uint32_t)(r_hi - r_lo) * 16u;
+            const int sa = i % NAS;
+            if (lane == 0) {
+                mbar_wait(BAR(B_AEMPTY + sa), ((i / NAS) & 1) ^ 1);
+                mbar_expect_tx(BAR(B_AFULL + sa), row_bytes * ncg);
+            }
+            __syncwarp();
+            if (lane < ncg) {
+                const float* src = p.x + (((size_t)b * ncg + lane) * p.T + (tx0 + r_lo)) * 4;
+                bulk_g2s(smem_u32(sA + (size_t)sa * p.a_stage_bytes) + ((uint32_t)lane * R + (uint32_t)r_lo) * 16u, src, row_bytes, BAR(B_AFULL + sa));
+            }
+        }
+    } else if (warp == 1) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (lane == 0) {
+            const uint32_t b_lbo = (uint32_t)C * 16u;
+            const uint64_t b_kstep = (uint64_t)(2u * (uint32_t)C);
+            const int nk = C / 8;
+            const uint32_t tap_bytes = (uint32_t)C * (uint32_t)C * 4u;
+            mbar_wait(BAR(B_W), 0);
+            auto conv2 = [&](int i) {  // D2[i&1] += conv2(XT[i&1])
+                const int buf = i & 1;
+                mbar_wait(BAR(B_XTFULL + buf), (i >> 1) & 1);
+                fence_after();
+                const uint64_t xt0 = make_desc(smem_u32(sXT + (size_t)buf * p.xt_bytes), (uint32_t)RT * 16u, 128u);
+                const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)RT);
+                const uint32_t d2 = tmem + (uint32_t)(2 * C + buf * C);
+                for (int j = 0; j < p.K; j++) {
+                    uint64_t ad = xt0 + (uint64_t)(uint32_t)j;
+                    uint64_t bd = make_desc(smem_u32(sW2) + (uint32_t)j * tap_bytes, b_lbo, 128u);
+                    for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_tf32(d2, ad, bd, p.idesc, 1u);
+                }
+                umma_commit(BAR(B_D2FULL + buf));
+            };
+            for (int i = 0; i < ntl; i++) {
+                const int sa = i % NAS, buf = i & 1;
+                mbar_wait(BAR(B_AREADY + sa), (i / NAS) & 1);
+                mbar_wait(BAR(B_D1EMPTY + buf), ((i >> 1) & 1) ^ 1);
+                fence_after();
+                const uint64_t a0 = make_desc(smem_u32(sA + (size_t)sa * p.a_stage_bytes), (uint32_t)R * 16u, 128u);
+                const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R);
+                const uint32_t d1 = tmem + (uint32_t)(buf * C);
+                for (int j = 0; j < p.K; j++) {
+                    uint64_t ad = a0 + (uint64_t)(uint32_t)(j * p.dil);
+                    uint64_t bd = make_desc(smem_u32(sW1) + (uint32_t)j * tap_bytes, b_lbo, 128u);
+                    for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_tf32(d1, ad, bd, p.idesc, (j | kk) ? 1u : 0u);
+                }
+                umma_commit(BAR(B_AEMPTY + sa));
+                umma_commit(BAR(B_D1FULL + buf));
+                if (i > 0) conv2(i - 1);
+            }
+            if (ntl > 0) conv2(ntl - 1);
+        }
+    } else if (warp < 6) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        const int tid2 = threadIdx.x - 64;
+        for (int i = 0; i < ntl; i++) {
+            int b, t0; tile_bt(i, b, t0);
+            const int tx0 = t0 - p2 - p1;
+            const int r_lo = max(0, -tx0), r_hi = min(R, p.T - tx0);
+            const int sa = i % NAS;
+            mbar_wait(BAR(B_AFULL + sa), (i / NAS) & 1);
+            xform_stage(reinterpret_cast<float4*>(sA + (size_t)sa * p.a_stage_bytes), ncg, R, r_lo, r_hi, 0.1f, tid2);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(BAR(B_AREADY + sa));
+        }
+    } else {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        const int q = warp & 3, m = q * 32 + lane;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        // rows 128..RT-1 of both XT buffers feed only discarded output rows; zero them once so they stay finite
+        if (m < p.K - 1)
+            for (int buf = 0; buf < 2; buf++) {
+                float4* XT = reinterpret_cast<float4*>(sXT + (size_t)buf * p.xt_bytes);
+                for (int cg = 0; cg < ncg; cg++) XT[(size_t)cg * RT + 128 + m] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        auto tail = [&](int i) {  // D2[i&1] -> scale -> HBM
+            int b, t0; tile_bt(i, b, t0);
+            const int buf = i & 1, t_out = t0 + m;
+            const bool ok_out = m < p.TO && t_out < p.T;
+            float4* yb = reinterpret_cast<float4*>(p.y) + (size_t)b * ncg * p.T;
+            mbar_wait(BAR(B_D2FULL + buf), (i >> 1) & 1);
+            fence_after();
+            for (int col = 0; col < C; col += 16) {
+                uint32_t v[16];
+                tmem_ld16(trow + (uint32_t)(2 * C + buf * C + col), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (!ok_out) continue;
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+                    yb[(size_t)((col >> 2) + g) * p.T + t_out] = make_float4(__uint_as_float(v[4 * g]) * p.out_scale, __uint_as_float(v[4 * g + 1]) * p.out_scale,
+                                                                             __uint_as_float(v[4 * g + 2]) * p.out_scale, __uint_as_float(v[4 * g + 3]) * p.out_scale);
+            }
+            fence_before();
+        };
+        for (int i = 0; i < ntl; i++) {
+            int b, t0; tile_bt(i, b, t0);
+            const int buf = i & 1, t_out = t0 + m;
+            const bool ok_out = m < p.TO && t_out < p.T;
+            const float4* xb = reinterpret_cast<const float4*>(p.x) + (size_t)b * ncg * p.T;
+            const float4* yb = reinterpret_cast<const float4*>(p.y) + (size_t)b * ncg * p.T;
+            // ---- D2[buf] = bias2 + x (+ y_old): its previous user (tile i-2) was drained by tail(i-2) in program order
+            for (int col = 0; col < C; col += 16) {
+                uint32_t v2[16];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const int cg = (col >> 2) + g;
+                    float4 o = *reinterpret_cast<const float4*>(p.b2 + cg * 4);
+                    if (ok_out) {
+                        const float4 r = xb[(size_t)cg * p.T + t_out];
+                        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                        if (p.accumulate) { const float4 a = yb[(size_t)cg * p.T + t_out]; o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+                    }
+                    v2[4 * g] = __float_as_uint(o.x); v2[4 * g + 1] = __float_as_uint(o.y); v2[4 * g + 2] = __float_as_uint(o.z); v2[4 * g + 3] = __float_as_uint(o.w);
+                }
+                tmem_st16(trow + (uint32_t)(2 * C + buf * C + col), v2);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            // ---- D1[buf] -> + bias1 -> lrelu -> TF32 -> XT[buf]   (XT[buf]'s previous reader, conv2(i-2), finished before tail(i-2) returned)
+            float4* XT = reinterpret_cast<float4*>(sXT + (size_t)buf * p.xt_bytes);
+            const int t_xt = t0 - p2 + m;
+            const bool xt_in = t_xt >= 0 && t_xt < p.T;
+            mbar_wait(BAR(B_D1FULL + buf), (i >> 1) & 1);
+            fence_after();
+            for (int col = 0; col < C; col += 16) {
+                uint32_t v[16];
+                tmem_ld16(trow + (uint32_t)(buf * C + col), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (xt_in) {
+                        const float4 bb = *reinterpret_cast<const float4*>(p.b1 + ((col >> 2) + g) * 4);
+                        o.x = to_tf32(lrelu(__uint_as_float(v[4 * g]) + bb.x, 0.1f)); o.y = to_tf32(lrelu(__uint_as_float(v[4 * g + 1]) + bb.y, 0.1f));
+                        o.z = to_tf32(lrelu(__uint_as_float(v[4 * g + 2]) + bb.z, 0.1f)); o.w = to_tf32(lrelu(__uint_as_float(v[4 * g + 3]) + bb.w, 0.1f));
+                    }
+                    XT[(size_t)((col >> 2) + g) * RT + m] = o;
+                }
+            }
+            fence_before();
+            mbar_arrive(BAR(B_D1EMPTY + buf));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(BAR(B_XTFULL + buf));
+            if (i > 0) tail(i - 1);
+        }
+        if (ntl > 0) tail(ntl - 1);
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+inline bool tc_pair_persist(const TcConvW& w1, const TcConvW& w2, const float* b1, const float* b2, const Act& x, const Act& y, int dil, float out_scale,
+                            int accumulate, cudaStream_t st, int num_sms) {
+    const int C = w1.Cin;
+    if (!(w1.Cout == C && w2.Cin == C && w2.Cout == C && w1.K == w2.K && w1.KC == C && w2.KC == C && w1.nt == C && w2.nt == C && !w1.x3 && !w1.ups_u &&
+          C <= 32 && C % 16 == 0 && (w1.K & 1)))
+        return false;
+    TcPairPParams p{};
+    p.x = x.p; p.y = y.p; p.w1 = w1.w; p.w2 = w2.w; p.b1 = b1; p.b2 = b2;
+    p.C = C; p.T = x.T; p.B = x.B; p.K = w1.K; p.dil = dil;
+    p.R1 = 128 + (p.K - 1) * dil; p.RT = 128 + p.K - 1; p.TO = 128 - (p.K - 1);
+    p.a_stage_bytes = (uint32_t)(C * p.R1 * 4); p.w_bytes = (uint32_t)(p.K * C * C * 4); p.xt_bytes = (uint32_t)(C * p.RT * 4);
+    p.nas = 3;
+    p.tiles_per_b = cdiv(p.T, p.TO); p.total_tiles = p.tiles_per_b * p.B;
+    uint32_t cols = 32; while ((int)cols < 4 * C) cols <<= 1;
+    p.tmem_cols = cols;
+    p.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((128u >> 4) << 24);
+    p.out_scale = out_scale; p.accumulate = accumulate;
+    const size_t smem = 2 * (size_t)p.w_bytes + (size_t)p.nas * p.a_stage_bytes + 2 * (size_t)p.xt_bytes + (size_t)(3 * p.nas + 9) * 8 + 16;
+    if (smem > 227 * 1024) return false;
+    static bool attr = false;
+    if (!attr) { BV2_CUDA(cudaFuncSetAttribute(k_tc_pair_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    int occ = 1;
+    BV2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tc_pair_persist, 320, smem));
+    occ = std::max(1, std::min(occ, (int)(512 / p.tmem_cols)));
+    const int grid = std::min(p.total_tiles, num_sms * occ);
+    launch_pdl(k_tc_pair_persist, dim3(grid), dim3(320), smem, st, p);
+    return true;
+}
+
 }  // namespace bv2

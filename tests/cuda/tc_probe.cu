@@ -184,7 +184,10 @@ static int run_x3(int Cin, int Cout, int K, int T, int nt) {
 }
 
 // Fused ResBlock pair: y = (conv2(lrelu(conv1(lrelu(x)))) + x [+ y0]) * scale, checked at sampled time steps.
-static int run_pair(int C, int K, int dil, int T, int B, bool acc, float scale, int iters, int kc = 0) {
+static int run_pair(int C, int K, int dil, int T, int B, bool acc, float scale, int iters, int kc = 0, int persist = 0) {
+    auto launch = [&](const TcConvW& a, const TcConvW& b, const float* b1, const float* b2, const Act& x, const Act& y, int acc_) {
+        return persist ? tc_pair_persist(a, b, b1, b2, x, y, dil, scale, acc_, 0, 148) : tc_pair(a, b, b1, b2, x, y, dil, scale, acc_, 0);
+    };
     std::mt19937 rng(C * 31 + K * 7 + dil + T);
     std::normal_distribution<float> nd(0.f, 1.f);
     std::vector<float> x((size_t)B * C * T), w1((size_t)C * C * K), w2((size_t)C * C * K), b1(C), b2(C), y0((size_t)B * C * T);
@@ -205,7 +208,7 @@ static int run_pair(int C, int K, int dil, int T, int B, bool acc, float scale, 
     Act ax; ax.B = B; ax.C = C; ax.T = T; ax.p = up(to_c4(x));
     Act ay; ay.B = B; ay.C = C; ay.T = T; ay.p = up(to_c4(y0));
     float* db1 = up(b1); float* db2 = up(b2);
-    if (!tc_pair(tw1, tw2, db1, db2, ax, ay, dil, scale, acc ? 1 : 0, 0)) { printf("SKIP pair C=%d K=%d (does not fit)\n", C, K); return 0; }
+    if (!launch(tw1, tw2, db1, db2, ax, ay, acc ? 1 : 0)) { printf("SKIP pair C=%d K=%d (does not fit)\n", C, K); return 0; }
     cudaError_t er = cudaDeviceSynchronize();
     if (er != cudaSuccess) { printf("CUDA error (pair C=%d K=%d d=%d): %s\n", C, K, dil, cudaGetErrorString(er)); return 1; }
     std::vector<float> got((size_t)B * C * T);
@@ -250,9 +253,9 @@ static int run_pair(int C, int K, int dil, int T, int B, bool acc, float scale, 
     float ms = 0, ms2 = 0;
     if (iters > 0) {
         cudaEvent_t a, c; cudaEventCreate(&a); cudaEventCreate(&c);
-        for (int i = 0; i < 3; i++) tc_pair(tw1, tw2, db1, db2, ax, ay, dil, scale, 0, 0);
+        for (int i = 0; i < 3; i++) launch(tw1, tw2, db1, db2, ax, ay, 0);
         cudaEventRecord(a);
-        for (int i = 0; i < iters; i++) tc_pair(tw1, tw2, db1, db2, ax, ay, dil, scale, 0, 0);
+        for (int i = 0; i < iters; i++) launch(tw1, tw2, db1, db2, ax, ay, 0);
         cudaEventRecord(c); cudaEventSynchronize(c); cudaEventElapsedTime(&ms, a, c); ms /= iters;
         // the two-launch path it replaces
         Act am; am.B = B; am.C = C; am.T = T; am.p = up(std::vector<float>((size_t)B * C * T));
@@ -264,7 +267,7 @@ static int run_pair(int C, int K, int dil, int T, int B, bool acc, float scale, 
         cudaEventRecord(c); cudaEventSynchronize(c); cudaEventElapsedTime(&ms2, a, c); ms2 /= iters;
     }
     bool ok = maxerr < 2e-3 * std::max(1.0, maxref);
-    printf("%s PAIR C=%3d K=%2d dil=%d T=%6d B=%d acc=%d kc=%d : maxerr %.3e (ref max %.2f)", ok ? "PASS" : "FAIL", C, K, dil, T, B, (int)acc, tw1.KC, maxerr, maxref);
+    printf("%s %s C=%3d K=%2d dil=%d T=%6d B=%d acc=%d kc=%d : maxerr %.3e (ref max %.2f)", ok ? "PASS" : "FAIL", persist ? "PPAIR" : "PAIR", C, K, dil, T, B, (int)acc, tw1.KC, maxerr, maxref);
     if (iters > 0) printf("  | fused %.3f ms  vs two launches %.3f ms  (%.2fx)", ms, ms2, ms2 / ms);
     printf("\n");
     fflush(stdout);
@@ -299,6 +302,21 @@ int main(int argc, char** argv) {
         fails += run_pair(128, 3, 5, 517, 1, false, 1.f, 0);
         fails += run_pair(128, 11, 5, 1300, 2, true, 1.f / 3, 0);
         fails += run_pair(64, 7, 1, 118, 1, false, 1.f, 0);
+        if (getenv("PROBE_PPAIR")) {  // persistent pair kernel (experimental)
+            fails += run_pair(16, 3, 1, 300, 1, false, 1.f, 0, 0, 1);
+            fails += run_pair(32, 7, 3, 1000, 2, false, 1.f, 0, 0, 1);
+            fails += run_pair(16, 11, 5, 40001, 1, true, 1.f / 3, 0, 0, 1);
+            fails += run_pair(32, 11, 5, 5000, 3, true, 1.f / 3, 0, 0, 1);
+            fails += run_pair(32, 3, 1, 117, 1, false, 1.f, 0, 0, 1);
+            if (perf) {
+                int F = 1573;
+                for (int C : {32, 16})
+                    for (int k : {3, 7, 11})
+                        for (int d : {1, 5}) fails += run_pair(C, k, d, (C == 32 ? 256 : 512) * F, 1, false, 1.f, 10, 0, 1);
+            }
+            printf("%s (%d failing)\n", fails ? "PROBE FAILED" : "PROBE OK", fails);
+            return fails ? 1 : 0;
+        }
         fails += run_x3(32, 32, 1, 100, 32);
         fails += run_x3(192, 192, 3, 256, 32);
         fails += run_x3(768, 192, 3, 256, 32);
