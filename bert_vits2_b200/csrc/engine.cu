@@ -677,8 +677,8 @@ void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_
     ConvArgs a; a.bias_b = gdec; a.bias_b_stride = g_stride;
     if (lens) { a.in_mask = 1; a.lens = lens; }
     const bool tc = cfg.generator_precision != 0;
-    static const int pair_fusion = getenv("BV2_PAIR") ? atoi(getenv("BV2_PAIR")) : 0;  // max channel count run through the fused pair kernels
-    static const int pair_persist = getenv("BV2_PAIR_PERSIST") ? atoi(getenv("BV2_PAIR_PERSIST")) : 32;  // ... of which the persistent form (C <= 32)
+    static const int pair_fusion = getenv("BV2_PAIR") ? atoi(getenv("BV2_PAIR")) : 0;  // max C for k_tc_pair (one tile per CTA; measured slower)
+    static const int pair_persist = getenv("BV2_PAIR_PERSIST") ? atoi(getenv("BV2_PAIR_PERSIST")) : 32;  // max C for k_tc_pair_persist (0 disables)
     conv(conv_pre, z, x, s, a, 0, 0, tc);
     const int nk = cfg.n_resblock_kernels, nd = cfg.n_dilations;
     BV2_CHECK(nk <= 4, "at most 4 resblock kernels");
@@ -710,14 +710,16 @@ void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_
             for (int d = 0; d < nd; d++) {
                 const bool last = d == nd - 1;
                 Act nxt = last ? S : (cur.p == ra.p ? rb : ra);
-                if (tc && pair_fusion && u.Cout <= pair_fusion) {
-                    // fused ResBlock pair: conv1 -> lrelu -> conv2 + residual in one kernel, intermediate in shared memory
+                if (tc && (u.Cout <= pair_persist || u.Cout <= pair_fusion)) {
+                    // fused ResBlock pair: conv1 -> lrelu -> conv2 + residual in one kernel, intermediate in shared memory.
+                    // Persistent form first (declines when fewer than 2 CTAs fit per SM), then the one-tile-per-CTA form if enabled.
                     if (last && j > 0) BV2_CUDA(cudaStreamWaitEvent(sj, ev_rb[j - 1], 0));
                     const float sc = (last && j == nk - 1) ? 1.f / nk : 1.f;
-                    if ((u.Cout <= pair_persist && tc_pair_persist(R.c1[d].tc, R.c2[d].tc, R.c1[d].b, R.c2[d].b, cur, nxt, R.dil[d], sc, last && j > 0, sj, num_sms)) ||
-                        tc_pair(R.c1[d].tc, R.c2[d].tc, R.c1[d].b, R.c2[d].b, cur, nxt, R.dil[d], sc, last && j > 0, sj)) {
-                        launches++; cur = nxt; continue;
-                    }
+                    bool fused = u.Cout <= pair_persist &&
+                                 tc_pair_persist(R.c1[d].tc, R.c2[d].tc, R.c1[d].b, R.c2[d].b, cur, nxt, R.dil[d], sc, last && j > 0, sj, num_sms);
+                    if (!fused && u.Cout <= pair_fusion)
+                        fused = tc_pair(R.c1[d].tc, R.c2[d].tc, R.c1[d].b, R.c2[d].b, cur, nxt, R.dil[d], sc, last && j > 0, sj);
+                    if (fused) { launches++; cur = nxt; continue; }
                 }
                 if (tc) {
                     TcEpi e1; e1.in_slope = 0.1f; e1.dil = R.dil[d];

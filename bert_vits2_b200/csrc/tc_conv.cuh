@@ -1516,9 +1516,14 @@ inline bool tc_pair_persist(const TcConvW& w1, const TcConvW& w2, const float* b
     if (smem > 227 * 1024) return false;
     static bool attr = false;
     if (!attr) { BV2_CUDA(cudaFuncSetAttribute(k_tc_pair_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
-    int occ = 1;
-    BV2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tc_pair_persist, 320, smem));
-    occ = std::max(1, std::min(occ, (int)(512 / p.tmem_cols)));
+    // resident CTAs per SM: shared memory (228 KB/SM, 1 KB reserved per CTA), registers (64K/SM), TMEM columns (512/SM)
+    static cudaFuncAttributes fa = [] { cudaFuncAttributes a{}; cudaFuncGetAttributes(&a, k_tc_pair_persist); return a; }();
+    static const int min_occ = getenv("BV2_PPAIR_MINOCC") ? atoi(getenv("BV2_PPAIR_MINOCC")) : 2;
+    int occ = (int)((228 * 1024) / (smem + 1024));
+    occ = std::min(occ, 65536 / (320 * std::max(fa.numRegs, 1)));
+    occ = std::min(occ, (int)(512 / p.tmem_cols));
+    occ = std::min(occ, 4);
+    if (occ < min_occ) return false;  // one CTA per SM cannot hide the per-tile latency chain: the two-launch path is faster
     const int grid = std::min(p.total_tiles, num_sms * occ);
     launch_pdl(k_tc_pair_persist, dim3(grid), dim3(320), smem, st, p);
     return true;
