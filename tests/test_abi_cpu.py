@@ -67,3 +67,31 @@ def test_unsupported_configurations_raise():
         SynthesizerTrn(*args, n_speakers=0, gin_channels=512, init_seed=None)
     with pytest.raises(ValueError):
         SynthesizerTrn(*args, n_speakers=4, gin_channels=512, flow_share_parameter=True, init_seed=None)
+
+
+def _mk(**kw):
+    from bert_vits2_b200.models import SynthesizerTrn
+    args = dict(n_speakers=850, gin_channels=512, init_seed=None)
+    args.update(kw)
+    return SynthesizerTrn(112, 1025, 32, 192, 192, 768, 2, 6, 3, 0.1, "1", [3, 7, 11], [[1, 3, 5]] * 3, [8, 8, 2, 2, 2], 512,
+                          [16, 16, 8, 2, 2], **args)
+
+
+def test_dropin_error_behaviour_without_gpu():
+    """Unsupported configurations raise ValueError at construction like the reference's own checks; a CPU module refuses to
+    infer (no CPU path exists) and forward() is out of scope."""
+    from bert_vits2_b200.engine import Bv2Error
+    with pytest.raises(ValueError):
+        _mk(n_speakers=0)
+    with pytest.raises(ValueError):
+        _mk(flow_share_parameter=True)
+    with pytest.raises(ValueError):
+        _mk(use_spk_conditioned_encoder=False)
+    net = _mk().eval()
+    T = 5
+    x = torch.zeros(1, T, dtype=torch.int64)
+    f = torch.zeros(1, 1024, T)
+    with pytest.raises(Bv2Error):
+        net.infer(x, torch.tensor([T]), torch.zeros(1, dtype=torch.int64), x, x, f, f, f)
+    with pytest.raises(NotImplementedError):
+        net(x)
