@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Pin the oracle against the LIVE, unmodified reference on fresh seeds (not the committed golden cases).
+
+TEST INFRASTRUCTURE ONLY; build container only (/root/reference does not exist on the GPU box).
+    python oracle/validate_against_reference.py            # prints max-abs error per stage for a few fresh cases
+tests/test_oracle_golden.py::test_oracle_vs_live_reference_fresh_seeds runs `validate()` when the reference is present,
+so a drift between the restatement (oracle/vits2_oracle.py) and reference models.py:1026-1074 shows up in the CPU suite
+even for inputs nobody committed a fixture for (different lengths, languages, sdp_ratio, length_scale, max_len).
+"""
+import importlib.util
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from bert_vits2_b200 import synth  # noqa: E402
+from bert_vits2_b200.spec import ModelConfig  # noqa: E402
+from oracle import ref_import, vits2_oracle as O  # noqa: E402
+
+STAGES = ["x", "m_p_tok", "logs_p_tok", "logw_sdp", "logw_dp", "m_p", "logs_p", "z_p", "z", "o", "y_mask"]
+
+#: (use_transformer_flow, lengths, languages, infer kwargs, seeds (weights, inputs, noise))
+FRESH_CASES = [
+    (True, [13, 20], [1, 0], dict(sdp_ratio=0.2, noise_scale=0.667, noise_scale_w=0.8, length_scale=1.1), (5, 6, 7)),
+    (False, [18], [2], dict(sdp_ratio=1.0, noise_scale=0.3, noise_scale_w=0.5, length_scale=0.9), (8, 9, 10)),
+    (True, [1], [0], dict(sdp_ratio=0.0, noise_scale=0.6, noise_scale_w=0.9, length_scale=1.0), (11, 12, 13)),
+]
+
+
+def _golden_tools():
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def validate(cases=FRESH_CASES, f_cap=512):
+    """Returns [(case index, {stage: max abs error}, durations_equal)]."""
+    mg = _golden_tools()
+    out = []
+    for ci, (tflow, lengths, langs, kw, (ws, is_, ns)) in enumerate(cases):
+        net, hps = ref_import.build_reference_net(tflow)
+        cfg = ModelConfig.from_hps_model(hps.model, use_transformer_flow=tflow)
+        sd = synth.synthetic_state_dict(cfg, ws)
+        missing, unexpected = net.load_state_dict(sd, strict=False)
+        assert not unexpected and all(k.startswith("enc_q.") for k in missing)
+        inp = synth.synthetic_inputs(cfg, lengths, langs, seed=is_)
+        nw, nz = synth.synthetic_noise(cfg, len(lengths), max(lengths), f_cap, seed=ns)
+        ref = mg.run_reference(net, inp, nw, nz, **kw)
+        st = O.infer(sd, cfg, **inp, noise_w=nw, noise_z=nz, return_stages=True, **kw)
+        errs = {}
+        for k in STAGES:
+            assert st[k].shape == ref[k].shape, (ci, k, st[k].shape, ref[k].shape)
+            errs[k] = float((st[k] - ref[k]).abs().max())
+        out.append((ci, errs, bool(torch.equal(st["w_ceil"], ref["w_ceil"]))))
+    return out
+
+
+if __name__ == "__main__":
+    if not ref_import.available():
+        sys.exit("reference not present at " + ref_import.REF)
+    for ci, errs, dur_ok in validate():
+        print(f"case {ci}: durations equal={dur_ok}  " + "  ".join(f"{k}={v:.1e}" for k, v in errs.items()))

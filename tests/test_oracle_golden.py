@@ -57,3 +57,15 @@ def test_spec_matches_reference_state_dict_keys(flow):
     cfg = ModelConfig(use_transformer_flow=(flow == "tflow"))
     mine = [[p.key, list(p.shape)] for p in param_specs(cfg)]
     assert mine == ref
+
+
+def test_oracle_vs_live_reference_fresh_seeds():
+    """Build container only: run the UNMODIFIED reference on inputs no fixture exists for and compare every stage."""
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present (GPU box)")
+    from oracle.validate_against_reference import validate
+    for ci, errs, dur_ok in validate():
+        assert dur_ok, f"case {ci}: ceil(durations) differ"
+        for k, e in errs.items():
+            assert e < TOL, (ci, k, e)
