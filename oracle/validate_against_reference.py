@@ -28,6 +28,8 @@ FRESH_CASES = [
     (True, [13, 20], [1, 0], dict(sdp_ratio=0.2, noise_scale=0.667, noise_scale_w=0.8, length_scale=1.1), (5, 6, 7)),
     (False, [18], [2], dict(sdp_ratio=1.0, noise_scale=0.3, noise_scale_w=0.5, length_scale=0.9), (8, 9, 10)),
     (True, [1], [0], dict(sdp_ratio=0.0, noise_scale=0.6, noise_scale_w=0.9, length_scale=1.0), (11, 12, 13)),
+    # train_ms.evaluate-style call: the decoder input is cut to max_len frames (models.py:1073)
+    (False, [15, 11], [0, 1], dict(sdp_ratio=0.5, noise_scale=0.6, noise_scale_w=0.9, length_scale=1.0, max_len=20), (14, 15, 16)),
 ]
 
 
