@@ -28,7 +28,7 @@ class Bv2Config(C.Structure):
         ("resblock_kernel_sizes", C.c_int32 * MAX_RK), ("resblock_dilation_sizes", (C.c_int32 * MAX_DIL) * MAX_RK),
         ("sdp_filter", C.c_int32), ("sdp_kernel", C.c_int32), ("sdp_n_flows", C.c_int32), ("sdp_dds_layers", C.c_int32),
         ("sdp_num_bins", C.c_int32), ("sdp_tail_bound", C.c_float), ("dp_filter", C.c_int32), ("dp_kernel", C.c_int32),
-        ("cond_layer_idx", C.c_int32), ("generator_precision", C.c_int32)]
+        ("cond_layer_idx", C.c_int32), ("generator_precision", C.c_int32), ("n_flows", C.c_int32)]
 
 
 #: every symbol include/bv2.h declares -> (restype, argtypes)

@@ -44,15 +44,19 @@ class Arena {
 public:
     ~Arena() { if (base_) cudaFree(base_); }
     void reset() { off_ = 0; }
+    // Sticky high-water mark: the arena only ever grows, and when it must it grows to 1.5x the request (the frame count of an
+    // utterance varies with the duration noise), so a steady workload allocates during its first call(s) and never again.
+    // Regrowth is a device-wide sync + cudaFree + cudaMalloc (round 1 measured it inside a timed e2e loop: 10.4 vs 8.4 ms per
+    // step at N=4); bv2_reserve() sizes the arenas up front so that serving loops never hit it.
     void ensure(size_t bytes) {
         if (bytes <= cap_) return;
-        // grow with 25 % headroom: the frame count of an utterance varies with the duration noise, and every regrowth is a
-        // device-wide sync + cudaFree + cudaMalloc (measured: it cut the end-to-end rate 5x when hit every few steps)
-        bytes += bytes / 4;
+        bytes += bytes / 2;
         if (base_) { cudaDeviceSynchronize(); cudaFree(base_); base_ = nullptr; cap_ = 0; }
         BV2_CUDA(cudaMalloc(&base_, bytes));
         cap_ = bytes;
+        grows_++;
     }
+    int grows() const { return grows_; }
     float* alloc(size_t nfloats) {
         size_t bytes = (nfloats * sizeof(float) + 255) & ~(size_t)255;
         BV2_CHECK(off_ + bytes <= cap_, "workspace overflow");
@@ -65,7 +69,7 @@ public:
     size_t used() const { return off_; }
     void release(size_t mark) { off_ = mark; }  // stack discipline; safe because all users are stream-ordered
 private:
-    void* base_ = nullptr; size_t cap_ = 0, off_ = 0;
+    void* base_ = nullptr; size_t cap_ = 0, off_ = 0; int grows_ = 0;
 };
 
 }  // namespace bv2
@@ -105,6 +109,7 @@ struct bv2_engine {
         float* gproj = nullptr; float* w_ceil = nullptr;
     } st;
     long long* h_ylen = nullptr;  // pinned
+    int* h_err = nullptr;         // pinned + mapped: device-side error flag (barrier timeouts), see tc_conv.cuh
     // side streams: the MRF's resblocks (k = 3, 7, 11) of one Generator stage are independent chains of 6 convs
     cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_rb[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -131,6 +136,7 @@ struct bv2_engine {
     ~bv2_engine() {
         for (void* p : dev_allocs) cudaFree(p);
         if (h_ylen) cudaFreeHost(h_ylen);
+        if (h_err) cudaFreeHost(h_err);
         for (int i = 0; i < 4; i++) { if (side[i]) cudaStreamDestroy(side[i]); if (ev_rb[i]) cudaEventDestroy(ev_rb[i]); }
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (auto& kv : stage_ev) { if (kv.second.a) cudaEventDestroy(kv.second.a); if (kv.second.b) cudaEventDestroy(kv.second.b); }
@@ -177,7 +183,7 @@ struct bv2_engine {
         std::vector<float> b(c.Cout, 0.f);
         if (bias) for (int co = 0; co < Cout; co++) b[co] = (*bias)[co];
         c.b = upload(b);
-        if (tc_mode && Cout % 16 == 0) c.tc = tc_pack_weights(*this_uploader(), w, Cout, Cin, K, tc_nt, tc_mode == 2 ? 1 : 0, tc_kc);
+        if (tc_mode && Cout % 16 == 0) c.tc = tc_pack_weights(*this_uploader(), w, Cout, Cin, K, tc_nt, tc_mode == 2 ? 1 : 0, tc_kc);  // tc_mode: 1 = TF32, 2 = FP16 operands
         return c;
     }
     // uploader functor handed to tc_conv.cuh
@@ -219,13 +225,13 @@ struct bv2_engine {
                 for (int i2 = 0; i2 < H * H; i2++) w[(size_t)p * H * H + i2] = wt.data[i2] * s;
                 for (int i2 = 0; i2 < H; i2++) b[p * H + i2] = bt.data[i2] * s;
             }
-            L.qkv = make_conv(w, 3 * H, H, 1, &b, tc_mode, tc_mode == 2 ? 32 : 96, 64);
-            L.o = conv_from(a + ".conv_o", false, tc_mode, tc_mode == 2 ? 32 : 48, 64);
+            L.qkv = make_conv(w, 3 * H, H, 1, &b, tc_mode, 96, 64);
+            L.o = conv_from(a + ".conv_o", false, tc_mode, 48, 64);
             L.relk = upload(W(a + ".emb_rel_k").data);
             L.relv = upload(W(a + ".emb_rel_v").data);
             L.n1 = ln_from(name + ".norm_layers_1." + std::to_string(i));
-            L.f1 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_1", false, tc_mode, tc_mode == 2 ? 32 : 128, 64);
-            L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2", false, tc_mode, tc_mode == 2 ? 32 : (getenv("BV2_F2_NT") ? atoi(getenv("BV2_F2_NT")) : 32), 64);
+            L.f1 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_1", false, tc_mode, 128, 64);
+            L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2", false, tc_mode, tune_env("BV2_F2_NT", 32), 64);
             L.n2 = ln_from(name + ".norm_layers_2." + std::to_string(i));
             e.layers.push_back(L);
         }
@@ -313,6 +319,42 @@ struct bv2_engine {
     void run_flow(Act z, const int* lens, const float* gproj, cudaStream_t s);
     void run_generator(Act z, const int* lens_or_null, const float* gdec, int g_stride, float* o, cudaStream_t s);
     int* lens_to_device(const int64_t* x_lengths_dev, int B, Arena& ar, cudaStream_t s);
+    // ids inside their tables, 1 <= lengths <= T (the reference raises IndexError / a shape error): device-side check into *err_dev
+    void launch_validate(int B, int T, const int64_t* x, const int64_t* tone, const int64_t* lang, const int64_t* sid, const int64_t* lens,
+                         int* err_dev, cudaStream_t s) {
+        BV2_CUDA(cudaMemsetAsync(err_dev, 0, sizeof(int), s));
+        const int n = B * std::max(T, 1);
+        k_validate_inputs<<<std::min(cdiv(n, 256), 64), 256, 0, s>>>(reinterpret_cast<const long long*>(x), reinterpret_cast<const long long*>(tone),
+                                                                   reinterpret_cast<const long long*>(lang), reinterpret_cast<const long long*>(sid),
+                                                                   reinterpret_cast<const long long*>(lens), B, T, cfg.n_vocab, cfg.num_tones,
+                                                                   cfg.num_languages, cfg.n_speakers, err_dev);
+        BV2_CUDA(cudaGetLastError()); launches++;
+    }
+    static void throw_if_bad_inputs(int mask) {
+        if (!mask) return;
+        std::string m = "index out of range:";
+        if (mask & 1) m += " phoneme id (n_vocab)";
+        if (mask & 2) m += " tone id";
+        if (mask & 4) m += " language id";
+        if (mask & 8) m += " speaker id (n_speakers)";
+        if (mask & 16) m += " x_lengths (need 1 <= len <= T)";
+        throw Error(BV2_ERR_ARG, m);
+    }
+    // stage entry points (not on the hot path): validate, read the verdict back synchronously
+    void validate_sync(int B, int T, const int64_t* x, const int64_t* tone, const int64_t* lang, const int64_t* sid, const int64_t* lens, cudaStream_t s) {
+        int* d = reinterpret_cast<int*>(ws.alloc(4));
+        launch_validate(B, T, x, tone, lang, sid, lens, d, s);
+        int h = 0;
+        BV2_CUDA(cudaMemcpyAsync(&h, d, sizeof(int), cudaMemcpyDeviceToHost, s));
+        BV2_CUDA(cudaStreamSynchronize(s));
+        throw_if_bad_inputs(h);
+    }
+    void check_device_error() {
+        if (h_err && *reinterpret_cast<volatile int*>(h_err)) {
+            *h_err = 0;
+            throw Error(BV2_ERR_INTERNAL, "device-side barrier timeout in a tcgen05 kernel (results of this call are invalid)");
+        }
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -337,14 +379,17 @@ void bv2_engine::finalize() {
     const int H = c.hidden_channels, I = c.inter_channels;
     BV2_CHECK(H % 4 == 0 && I % 8 == 0 && c.filter_channels % 4 == 0 && c.gin_channels % 4 == 0, "channel multiples of 4");
     BV2_CHECK(H / c.n_heads == 96, "head dim 96 is the only instantiated attention kernel");
-    BV2_CHECK(c.window_size <= 5, "window");
+    BV2_CHECK(c.window_size <= 4, "window_size <= 4 (relative-position tables of the attention kernels hold 9 slots)");
+    BV2_CHECK(c.n_flows >= 1 && c.n_flows <= 16, "n_flows");
     BV2_CHECK(c.sdp_num_bins == 10 && c.sdp_kernel == 3, "sdp spline bins/kernel");
     std::vector<float> gw, gb;
-    // Precision policy: stages that feed ceil(durations) never run on the TF32 tensor-core path.  Error-compensated
-    // 3xTF32 was measured (tests/cuda/tc_probe.cu run_x3): the tcgen05 FP32 accumulator truncates, so the error grows
-    // linearly with the reduction length (~6.6e-8 per accumulated product: 1.5e-4 at Cin*K = 2304) and misses the
-    // fp32-class accuracy ceil() needs.  These stages therefore stay on FP32 FMA (SIMT) in both engines.
+    // Precision policy: stages that feed ceil(durations) never run on the tensor-core path.  Error-compensated 3xTF32
+    // was measured in round 1: the tcgen05 FP32 accumulator truncates, so the error grows linearly with the reduction length
+    // (~6.6e-8 per accumulated product: 1.5e-4 at Cin*K = 2304) and misses the fp32-class accuracy ceil() needs.  These
+    // stages therefore stay on FP32 FMA (SIMT) in every engine (x3 = 0: no tensor-core weight image is packed for them).
     const int x3 = 0;
+    BV2_CUDA(cudaSetDevice(device));
+    if (!h_err) h_err = tc_init_device();  // > 48 KB dynamic shared memory opt-in (a per-device function attribute) + device error flag
     // ---- enc_p (reference models.py:333-375)
     emb = upload(W("enc_p.emb.weight").data);
     temb = upload(W("enc_p.tone_emb.weight").data);
@@ -388,9 +433,12 @@ void bv2_engine::finalize() {
     dp_n1 = ln_from("dp.norm_1"); dp_n2 = ln_from("dp.norm_2");
     goff_dp = append_gproj("dp.cond", gw, gb);
     // ---- flow (reference models.py:82-145 / 403-445): Flip folded into pre/post channel order
-    const int half = I / 2, n = c.n_flow_layer;
+    const int half = I / 2, n = c.n_flows;
     flows.resize(n);
+    // generator_precision: 0 = fp32 SIMT everywhere; 1 = TF32 tcgen05 (flow + Generator); 2 = FP16-operand tcgen05 Generator
+    // (same 11-bit significand as TF32, fp32 accumulate, fp32 activations in HBM) + TF32 flow
     const int tc = c.generator_precision ? 1 : 0;
+    const int gtc = c.generator_precision == 2 ? 2 : tc;
     for (int i = 0; i < n; i++) {
         CouplingW& fl = flows[i];
         std::string f = "flow.flows." + std::to_string(2 * i);
@@ -433,7 +481,7 @@ void bv2_engine::finalize() {
         }
     }
     // ---- dec (reference models.py:490-564)
-    conv_pre = conv_from("dec.conv_pre", false, tc, 128);
+    conv_pre = conv_from("dec.conv_pre", false, gtc, 128);
     goff_dec = append_gproj("dec.cond", gw, gb);
     int ch = c.upsample_initial_channel;
     for (int i = 0; i < c.n_ups; i++) {
@@ -446,7 +494,7 @@ void bv2_engine::finalize() {
             for (int co = 0; co < u.Cout; co++)
                 for (int j = 0; j < u.K; j++) p[((size_t)ci * u.K + j) * u.Cout + co] = w[((size_t)ci * u.Cout + co) * u.K + j];
         u.w = upload(p); u.b = upload(W("dec.ups." + std::to_string(i) + ".bias").data);
-        if (tc) u.tc = tc_pack_upsample(*this_uploader(), w, u.Cin, u.Cout, u.K, u.u, 32);
+        if (gtc) u.tc = tc_pack_upsample(*this_uploader(), w, u.Cin, u.Cout, u.K, u.u, 32, gtc == 2);
         ups.push_back(u);
         ch /= 2;
         for (int j = 0; j < c.n_resblock_kernels; j++) {
@@ -455,9 +503,9 @@ void bv2_engine::finalize() {
             for (int d = 0; d < c.n_dilations; d++) {
                 rb.dil.push_back(c.resblock_dilation_sizes[j][d]);
                 const int kc = 32;  // persistent kernels hide latency with deep rings: fewer, larger chunks
-                const int nt0 = (ch >= 256 && getenv("BV2_S0_NT")) ? atoi(getenv("BV2_S0_NT")) : 0;  // tuning knob (stage 0 N tile)
-                rb.c1.push_back(conv_from(r + ".convs1." + std::to_string(d), true, tc, nt0, kc));
-                rb.c2.push_back(conv_from(r + ".convs2." + std::to_string(d), true, tc, nt0, kc));
+                const int nt0 = ch >= 256 ? tune_env("BV2_S0_NT", 0) : 0;  // tuning knob (stage 0 N tile)
+                rb.c1.push_back(conv_from(r + ".convs1." + std::to_string(d), true, gtc, nt0, kc));
+                rb.c2.push_back(conv_from(r + ".convs2." + std::to_string(d), true, gtc, nt0, kc));
             }
             resblocks.push_back(rb);
         }
@@ -467,7 +515,7 @@ void bv2_engine::finalize() {
     emb_g = upload(W("emb_g.weight").data);
     gproj_n = (int)gb.size();
     gproj_w = upload(gw); gproj_b = upload(gb);
-    BV2_CUDA(cudaMallocHost(&h_ylen, 4096 * sizeof(long long)));
+    BV2_CUDA(cudaMallocHost(&h_ylen, 4100 * sizeof(long long)));
     host.clear();
     finalized = true;
 }
@@ -557,7 +605,7 @@ void bv2_engine::run_text_encoder(int B, int T, const int64_t* x, const int64_t*
     conv(bert_proj, bc, proj, s, ConvArgs(), 0, 0, true);
     k_embed_sum<<<grid_tcb(T, H, B), 128, 0, s>>>(proj.p, reinterpret_cast<const long long*>(x), reinterpret_cast<const long long*>(tone),
                                                   reinterpret_cast<const long long*>(lang), emb, temb, lemb, h.p, H, T, lens,
-                                                  std::sqrt((float)H));
+                                                  std::sqrt((float)H), cfg.n_vocab, cfg.num_tones, cfg.num_languages);
     BV2_CUDA(cudaGetLastError()); launches++;
     run_encoder(enc_p, h, lens, gproj, s, false);  // feeds ceil(durations): FP32 FMA only
     ConvArgs a; a.out_mask = 1; a.lens = lens;
@@ -632,7 +680,7 @@ void bv2_engine::run_flow(Act z, const int* lens, const float* gproj, cudaStream
     const bool tcf = cfg.generator_precision != 0;
     const size_t mark = ws.used();
     Act h = ws.act(B, H, F);
-    for (int i = cfg.n_flow_layer - 1; i >= 0; i--) {
+    for (int i = cfg.n_flows - 1; i >= 0; i--) {
         CouplingW& fl = flows[i];
         const int in_off = fl.s ? half : 0, out_off = fl.s ? 0 : half;
         ConvArgs a; a.out_mask = 1; a.lens = lens;
@@ -660,7 +708,7 @@ void bv2_engine::run_flow(Act z, const int* lens, const float* gproj, cudaStream
         p.out_mask = 1; p.lens = lens;
         conv(fl.post, m_in, z, s, p, 0, out_off, tcf);
     }
-    if (cfg.n_flow_layer % 2 == 1) {
+    if (cfg.n_flows % 2 == 1) {
         Act t = ws.act(B, z.C, F);
         k_flip_c4<<<grid_tcb(F, z.C, B), 128, 0, s>>>(z.p, t.p, z.C, F);
         BV2_CUDA(cudaMemcpyAsync(z.p, t.p, z.elems() * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -677,8 +725,7 @@ void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_
     ConvArgs a; a.bias_b = gdec; a.bias_b_stride = g_stride;
     if (lens) { a.in_mask = 1; a.lens = lens; }
     const bool tc = cfg.generator_precision != 0;
-    static const int pair_fusion = getenv("BV2_PAIR") ? atoi(getenv("BV2_PAIR")) : 0;  // max C for k_tc_pair (one tile per CTA; measured slower)
-    static const int pair_persist = getenv("BV2_PAIR_PERSIST") ? atoi(getenv("BV2_PAIR_PERSIST")) : 32;  // max C for k_tc_pair_persist (0 disables)
+    const int pair_persist = tune_env("BV2_PAIR_PERSIST", 32);  // max C for the fused ResBlock pair kernel (0 disables)
     conv(conv_pre, z, x, s, a, 0, 0, tc);
     const int nk = cfg.n_resblock_kernels, nd = cfg.n_dilations;
     BV2_CHECK(nk <= 4, "at most 4 resblock kernels");
@@ -710,16 +757,14 @@ void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_
             for (int d = 0; d < nd; d++) {
                 const bool last = d == nd - 1;
                 Act nxt = last ? S : (cur.p == ra.p ? rb : ra);
-                if (tc && (u.Cout <= pair_persist || u.Cout <= pair_fusion)) {
-                    // fused ResBlock pair: conv1 -> lrelu -> conv2 + residual in one kernel, intermediate in shared memory.
-                    // Persistent form first (declines when fewer than 2 CTAs fit per SM), then the one-tile-per-CTA form if enabled.
+                if (tc && u.Cout <= pair_persist) {
+                    // fused ResBlock pair: conv1 -> lrelu -> conv2 + residual in one kernel, intermediate in shared memory
+                    // (declines when fewer than 2 CTAs fit per SM: the two-launch path is faster there)
                     if (last && j > 0) BV2_CUDA(cudaStreamWaitEvent(sj, ev_rb[j - 1], 0));
                     const float sc = (last && j == nk - 1) ? 1.f / nk : 1.f;
-                    bool fused = u.Cout <= pair_persist &&
-                                 tc_pair_persist(R.c1[d].tc, R.c2[d].tc, R.c1[d].b, R.c2[d].b, cur, nxt, R.dil[d], sc, last && j > 0, sj, num_sms);
-                    if (!fused && u.Cout <= pair_fusion)
-                        fused = tc_pair(R.c1[d].tc, R.c2[d].tc, R.c1[d].b, R.c2[d].b, cur, nxt, R.dil[d], sc, last && j > 0, sj);
-                    if (fused) { launches++; cur = nxt; continue; }
+                    if (tc_pair_persist(R.c1[d].tc, R.c2[d].tc, R.c1[d].b, R.c2[d].b, cur, nxt, R.dil[d], sc, last && j > 0, sj, num_sms)) {
+                        launches++; cur = nxt; continue;
+                    }
                 }
                 if (tc) {
                     TcEpi e1; e1.in_slope = 0.1f; e1.dil = R.dil[d];
@@ -837,10 +882,13 @@ int bv2_infer_begin(bv2_engine* e, int B, int T, const int64_t* x, const int64_t
     auto& st = e->st;
     st.active = false; st.B = B; st.T = T;
     e->stage_begin("encoder_duration", s);
+    st.ylen = reinterpret_cast<long long*>(e->persist.alloc(2 * (size_t)B + 4));  // [B] y_lengths, then the input-validation mask
+    int* err_dev = reinterpret_cast<int*>(st.ylen + B);
+    e->launch_validate(B, T, x, tone, language, sid, x_lengths, err_dev, s);
     st.lens = e->lens_to_device(x_lengths, B, e->persist, s);
     float* g = e->persist.alloc((size_t)B * c.gin_channels);
     st.gproj = e->persist.alloc((size_t)B * e->gproj_n);
-    k_gather_rows<<<B, 128, 0, s>>>(e->emb_g, reinterpret_cast<const long long*>(sid), g, c.gin_channels);
+    k_gather_rows<<<B, 128, 0, s>>>(e->emb_g, reinterpret_cast<const long long*>(sid), g, c.gin_channels, c.n_speakers);
     BV2_CUDA(cudaGetLastError()); e->launches++;
     e->run_gproj(g, B, st.gproj, s);
     Act h = e->ws.act(B, H, T);
@@ -855,14 +903,15 @@ int bv2_infer_begin(bv2_engine* e, int B, int T, const int64_t* x, const int64_t
     float* lsdp = e->ws.alloc((size_t)B * T); float* ldp = e->ws.alloc((size_t)B * T);
     st.w_ceil = e->persist.alloc((size_t)B * T);
     st.cum = reinterpret_cast<int*>(e->persist.alloc((size_t)B * T));
-    st.ylen = reinterpret_cast<long long*>(e->persist.alloc(2 * (size_t)B + 2));
     k_durations<<<B, 1024, 0, s>>>(z, zch, e->ea_m[0], e->ea_logs[0], dp.p, sdp_ratio, length_scale, st.lens, T, lsdp, ldp, st.w_ceil,
                                    st.cum, st.ylen, w_ceil_override);
     BV2_CUDA(cudaGetLastError()); e->launches++;
     e->debug_plain("logw_sdp", lsdp, B, 1, T); e->debug_plain("logw_dp", ldp, B, 1, T); e->debug_plain("w_ceil", st.w_ceil, B, 1, T);
     e->stage_end("encoder_duration", s);
-    BV2_CUDA(cudaMemcpyAsync(e->h_ylen, st.ylen, (size_t)B * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    BV2_CUDA(cudaMemcpyAsync(e->h_ylen, st.ylen, ((size_t)B + 1) * sizeof(long long), cudaMemcpyDeviceToHost, s));
     BV2_CUDA(cudaStreamSynchronize(s));
+    bv2_engine::throw_if_bad_inputs((int)(e->h_ylen[B] & 0xffffffffll));
+    e->check_device_error();
     int fm = 1;
     for (int b = 0; b < B; b++) { y_lengths_host[b] = e->h_ylen[b]; fm = std::max<long long>(fm, e->h_ylen[b]); }
     *f_max = fm; st.F = fm;
@@ -928,12 +977,15 @@ int bv2_text_encoder(bv2_engine* e, int B, int T, const int64_t* x, const int64_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bv2_config& c = e->cfg;
     const int H = c.hidden_channels, I = c.inter_channels;
+    BV2_CHECK(B >= 1 && B <= 4096 && T >= 1 && x && x_lengths && sid && tone && language && bert && ja_bert && en_bert && x_out && m_out && logs_out,
+              "text_encoder args");
     e->dbg.clear(); e->st.active = false;
     e->ws.ensure(ws_bytes_for(c, B, T, 0)); e->ws.reset();
+    e->validate_sync(B, T, x, tone, language, sid, x_lengths, s);
     int* lens = e->lens_to_device(x_lengths, B, e->ws, s);
     float* g = e->ws.alloc((size_t)B * c.gin_channels);
     float* gp = e->ws.alloc((size_t)B * e->gproj_n);
-    k_gather_rows<<<B, 128, 0, s>>>(e->emb_g, reinterpret_cast<const long long*>(sid), g, c.gin_channels);
+    k_gather_rows<<<B, 128, 0, s>>>(e->emb_g, reinterpret_cast<const long long*>(sid), g, c.gin_channels, c.n_speakers);
     e->launches++;
     e->run_gproj(g, B, gp, s);
     Act h = e->ws.act(B, H, T), stats = e->ws.act(B, 2 * I, T);
@@ -952,12 +1004,14 @@ int bv2_duration(bv2_engine* e, int B, int T, const float* x, const int64_t* x_l
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bv2_config& c = e->cfg;
     const int H = c.hidden_channels;
+    BV2_CHECK(B >= 1 && B <= 4096 && T >= 1 && x && x_lengths && sid && noise_w && logw_sdp && logw_dp, "duration args");
     e->dbg.clear(); e->st.active = false;
     e->ws.ensure(ws_bytes_for(c, B, T, 0)); e->ws.reset();
+    e->validate_sync(B, T, nullptr, nullptr, nullptr, sid, x_lengths, s);
     int* lens = e->lens_to_device(x_lengths, B, e->ws, s);
     float* g = e->ws.alloc((size_t)B * c.gin_channels);
     float* gp = e->ws.alloc((size_t)B * e->gproj_n);
-    k_gather_rows<<<B, 128, 0, s>>>(e->emb_g, reinterpret_cast<const long long*>(sid), g, c.gin_channels);
+    k_gather_rows<<<B, 128, 0, s>>>(e->emb_g, reinterpret_cast<const long long*>(sid), g, c.gin_channels, c.n_speakers);
     e->launches++;
     e->run_gproj(g, B, gp, s);
     Act h = e->ws.act(B, H, T);
@@ -982,12 +1036,14 @@ int bv2_flow_reverse(bv2_engine* e, int B, int F, const float* z_p, const int64_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bv2_config& c = e->cfg;
     const int I = c.inter_channels;
+    BV2_CHECK(B >= 1 && B <= 4096 && F >= 1 && z_p && y_lengths && sid && z_out, "flow_reverse args");
     e->dbg.clear(); e->st.active = false;
     e->ws.ensure(ws_bytes_for(c, B, 1, F)); e->ws.reset();
+    e->validate_sync(B, F, nullptr, nullptr, nullptr, sid, y_lengths, s);
     int* lens = e->lens_to_device(y_lengths, B, e->ws, s);
     float* g = e->ws.alloc((size_t)B * c.gin_channels);
     float* gp = e->ws.alloc((size_t)B * e->gproj_n);
-    k_gather_rows<<<B, 128, 0, s>>>(e->emb_g, reinterpret_cast<const long long*>(sid), g, c.gin_channels);
+    k_gather_rows<<<B, 128, 0, s>>>(e->emb_g, reinterpret_cast<const long long*>(sid), g, c.gin_channels, c.n_speakers);
     e->launches++;
     e->run_gproj(g, B, gp, s);
     Act z = e->ws.act(B, I, F);

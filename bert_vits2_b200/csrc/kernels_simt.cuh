@@ -404,9 +404,35 @@ __global__ void k_linear_g(const float* __restrict__ W, const float* __restrict_
     if (lane == 0) y[(size_t)b * Cout + co] = s + bias[co];
 }
 
-__global__ void k_gather_rows(const float* __restrict__ table, const long long* __restrict__ idx, float* __restrict__ out, int C) {
+__global__ void k_gather_rows(const float* __restrict__ table, const long long* __restrict__ idx, float* __restrict__ out, int C, int nrows) {
     int b = blockIdx.x;
-    for (int i = threadIdx.x; i < C; i += blockDim.x) out[(size_t)b * C + i] = table[(size_t)idx[b] * C + i];
+    const long long r = min(max(idx[b], 0ll), (long long)nrows - 1);  // out-of-range ids are reported by k_validate_inputs; never read out of bounds
+    for (int i = threadIdx.x; i < C; i += blockDim.x) out[(size_t)b * C + i] = table[(size_t)r * C + i];
+}
+
+// Input validation (the reference raises IndexError from nn.Embedding / a shape error for bad lengths; reference
+// models.py:378-384, 1046): ids must lie inside their tables and 1 <= x_lengths[b] <= T.  Writes a bit mask into *err
+// (read back together with y_lengths: no extra synchronisation): 1 = phoneme id, 2 = tone, 4 = language, 8 = speaker id,
+// 16 = x_lengths.  Gather kernels clamp, so a bad id can never become an out-of-bounds access.
+__global__ void k_validate_inputs(const long long* __restrict__ x, const long long* __restrict__ tone, const long long* __restrict__ lang,
+                                  const long long* __restrict__ sid, const long long* __restrict__ lens, int B, int T, int n_vocab,
+                                  int n_tones, int n_langs, int n_spk, int* __restrict__ err) {
+    int bad = 0;
+    const int n = B * T;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int b = i / T, t = i - b * T;
+        const long long l = lens ? lens[b] : T;
+        if (t >= l) continue;  // padding positions are never read as ids with an effect (masked)
+        if (x && (x[i] < 0 || x[i] >= n_vocab)) bad |= 1;
+        if (tone && (tone[i] < 0 || tone[i] >= n_tones)) bad |= 2;
+        if (lang && (lang[i] < 0 || lang[i] >= n_langs)) bad |= 4;
+    }
+    if (blockIdx.x == 0)
+        for (int b = threadIdx.x; b < B; b += blockDim.x) {
+            if (sid && (sid[b] < 0 || sid[b] >= n_spk)) bad |= 8;
+            if (lens && (lens[b] < 1 || lens[b] > T)) bad |= 16;
+        }
+    if (bad) atomicOr(err, bad);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -416,13 +442,14 @@ __global__ void k_gather_rows(const float* __restrict__ table, const long long* 
 __global__ void k_embed_sum(const float* __restrict__ proj, const long long* __restrict__ x, const long long* __restrict__ tone,
                             const long long* __restrict__ lang, const float* __restrict__ emb, const float* __restrict__ temb,
                             const float* __restrict__ lemb, float* __restrict__ out, int H, int T, const int* __restrict__ lens,
-                            float scale) {
+                            float scale, int n_vocab, int n_tones, int n_langs) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int cg = blockIdx.y, b = blockIdx.z;
     if (t >= T) return;
     size_t idx = ((size_t)b * (H / 4) + cg) * T + t;
     float4 p = reinterpret_cast<const float4*>(proj)[idx];
     long long xi = x[(size_t)b * T + t], ti = tone[(size_t)b * T + t], li = lang[(size_t)b * T + t];
+    xi = min(max(xi, 0ll), (long long)n_vocab - 1); ti = min(max(ti, 0ll), (long long)n_tones - 1); li = min(max(li, 0ll), (long long)n_langs - 1);
     float4 e = *reinterpret_cast<const float4*>(emb + xi * H + cg * 4);
     float4 te = *reinterpret_cast<const float4*>(temb + ti * H + cg * 4);
     float4 le = *reinterpret_cast<const float4*>(lemb + li * H + cg * 4);
@@ -605,33 +632,6 @@ __global__ void __launch_bounds__(128) k_attention_rel(const float* __restrict__
         }
         o4[(size_t)((sub * DPT) / 4 + d4) * T + qi] = make_float4(o[0], o[1], o[2], o[3]);
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// DDSConv depthwise dilated conv (reference modules.py:122: convs_sep[i](x * x_mask)), c4.
-// w: [C][K] , K=3.
-// ------------------------------------------------------------------------------------------------
-__global__ void k_dwconv3_c4(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                             float* __restrict__ y, int C, int T, int dil, const int* __restrict__ lens) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int cg = blockIdx.y, b = blockIdx.z;
-    if (t >= T) return;
-    const int len = lens[b];
-    const float4* x4 = reinterpret_cast<const float4*>(x) + ((size_t)b * (C / 4) + cg) * T;
-    float4 acc = *reinterpret_cast<const float4*>(bias + cg * 4);
-    const float* wc = w + cg * 4 * 3;
-#pragma unroll
-    for (int j = 0; j < 3; j++) {
-        int tt = t + (j - 1) * dil;
-        if (tt >= 0 && tt < T && tt < len) {
-            float4 v = x4[tt];
-            acc.x = fmaf(v.x, wc[0 * 3 + j], acc.x);
-            acc.y = fmaf(v.y, wc[1 * 3 + j], acc.y);
-            acc.z = fmaf(v.z, wc[2 * 3 + j], acc.z);
-            acc.w = fmaf(v.w, wc[3 * 3 + j], acc.w);
-        }
-    }
-    reinterpret_cast<float4*>(y)[((size_t)b * (C / 4) + cg) * T + t] = acc;
 }
 
 // ConvFlow.pre (Conv1d 1->C, k=1) fused with DDSConv's "x = x + g" (reference modules.py:488, 119-120):

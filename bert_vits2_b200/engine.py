@@ -15,6 +15,10 @@ class Bv2Error(RuntimeError):
     pass
 
 
+#: engine precision -> bv2_config.generator_precision (include/bv2.h)
+PRECISIONS = {"fp32": 0, "tf32": 1, "fp16": 2}
+
+
 def _cfg_struct(cfg: ModelConfig, precision: int) -> _lib.Bv2Config:
     c = _lib.Bv2Config()
     for n in ("n_vocab", "num_tones", "num_languages", "bert_dim", "inter_channels", "hidden_channels", "filter_channels",
@@ -35,6 +39,7 @@ def _cfg_struct(cfg: ModelConfig, precision: int) -> _lib.Bv2Config:
         for d, v in enumerate(ds):
             c.resblock_dilation_sizes[j][d] = v
     c.generator_precision = precision
+    c.n_flows = int(cfg.n_flows)
     if cfg.resblock != "1":
         raise ValueError("only resblock='1' (ResBlock1) is supported, as configs/config.json sets")
     return c
@@ -45,7 +50,9 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class Engine:
-    """One engine per CUDA device.  precision: 'fp32' (SIMT) or 'tf32' (tcgen05 implicit-GEMM Generator convs)."""
+    """One engine per CUDA device.  precision: 'fp32' (SIMT FMA everywhere), 'tf32' (tcgen05 implicit-GEMM convs with TF32
+    operands) or 'fp16' (tcgen05 with FP16 operands -- same 11-bit significand as TF32, twice the tensor rate, half the
+    operand traffic; fp32 accumulate and fp32 activations in HBM).  Everything that feeds ceil(durations) is FP32 FMA in all three."""
 
     def __init__(self, cfg: ModelConfig, state_dict: Dict[str, torch.Tensor], device="cuda:0", precision: str = "tf32"):
         self.lib = _lib.load()
@@ -55,7 +62,7 @@ class Engine:
             raise Bv2Error("bert_vits2_b200 has no CPU path: a CUDA (sm_100) device is required")
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.device = torch.device("cuda", idx)
-        self.precision = {"fp32": 0, "tf32": 1}[precision]
+        self.precision = PRECISIONS[precision]
         self._h = C.c_void_p()
         cs = _cfg_struct(cfg, self.precision)
         rc = self.lib.bv2_create(C.byref(self._h), C.byref(cs), idx)

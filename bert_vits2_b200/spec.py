@@ -74,6 +74,13 @@ class ModelConfig:
         return c
 
     @property
+    def n_flows(self) -> int:
+        """Couplings in `flow`: TransformerCouplingBlock builds n_flow_layer of them (reference models.py:82-145);
+        ResidualCouplingBlock is constructed as (inter, hidden, 5, 1, n_flow_layer, gin_channels=...) so n_flow_layer lands
+        in its n_layers (WN depth) and n_flows keeps its default 4 (reference models.py:403-445, 918-919)."""
+        return self.n_flow_layer if self.use_transformer_flow else 4
+
+    @property
     def hop(self) -> int:
         h = 1
         for u in self.upsample_rates:
@@ -193,7 +200,7 @@ def param_specs(cfg: ModelConfig) -> List[ParamSpec]:
     _conv(out, "dec.cond", C0, G, 1)
     # ---- flow (reference models.py:903-926)
     half = I // 2
-    for i in range(cfg.n_flow_layer):
+    for i in range(cfg.n_flows):
         f = f"flow.flows.{2 * i}"
         _conv(out, f"{f}.pre", H, half, 1)
         if cfg.use_transformer_flow:

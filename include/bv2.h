@@ -51,7 +51,10 @@ typedef struct {
     int32_t sdp_filter, sdp_kernel, sdp_n_flows, sdp_dds_layers, sdp_num_bins;
     float sdp_tail_bound;
     int32_t dp_filter, dp_kernel, cond_layer_idx;
-    int32_t generator_precision; /* 0 = fp32 SIMT convs, 1 = TF32 tcgen05 implicit-GEMM convs (fp32 accumulate) */
+    int32_t generator_precision; /* 0 = fp32 SIMT convs; 1 = TF32 tcgen05 implicit-GEMM convs (flow + Generator); 2 = FP16-operand
+                                    tcgen05 convs (same 11-bit significand as TF32, fp32 accumulate, fp32 activations in HBM) */
+    int32_t n_flows;             /* couplings in `flow`: n_flow_layer for TransformerCouplingBlock (models.py:82-145), always 4 for
+                                    ResidualCouplingBlock, whose n_layers argument receives n_flow_layer (models.py:403-445, 918-919) */
 } bv2_config;
 
 /* replaces: models.SynthesizerTrn(...).to(device) (reference infer.py:95-101) */

@@ -328,7 +328,7 @@ def flow_reverse(sd, cfg, z_p, y_mask, g):
     for flow in reversed([L0,Flip,L1,Flip,...]) -> Flip, L(n-1), Flip, L(n-2), ..., Flip, L0."""
     layer = transformer_coupling_reverse if cfg.use_transformer_flow else residual_coupling_reverse
     x = z_p
-    for i in range(cfg.n_flow_layer - 1, -1, -1):
+    for i in range(cfg.n_flows - 1, -1, -1):  # n_flow_layer (transformer flow) / 4 (WN flow: models.py:918-919 passes n_flow_layer as n_layers)
         x = torch.flip(x, [1])
         x = layer(sd, f"flow.flows.{2 * i}", x, y_mask, g, cfg)
     return x

@@ -40,8 +40,8 @@ def test_create_fails_loudly_without_gpu(lib):
 
 def test_config_struct_layout_matches_header():
     import ctypes as C
-    # 20 scalars + 2*8 + 2 + 4 + 16 + 5 + float + 4 = 69 int32-sized fields
-    assert C.sizeof(_lib.Bv2Config) == 4 * (20 + 16 + 2 + 4 + 16 + 5 + 1 + 4)
+    # 20 scalars + 2*8 + 2 + 4 + 16 + 5 + float + 4 + n_flows = 70 int32-sized fields
+    assert C.sizeof(_lib.Bv2Config) == 4 * (20 + 16 + 2 + 4 + 16 + 5 + 1 + 4 + 1)
 
 
 @pytest.mark.parametrize("flow", ["tflow", "wnflow"])

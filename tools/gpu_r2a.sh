@@ -1,0 +1,18 @@
+#!/bin/bash
+# round-2 call A: hardware probe of the FP16-operand conv family + existing GPU tests + A/B bench (tf32 vs fp16 engine)
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv | tail -1
+timeout 420 tests/cuda/tc_probe perf > gpurun_out/r2a_probe.log 2>&1; echo "probe exit $?"; grep -c PASS gpurun_out/r2a_probe.log; grep -E "FAIL|error|TIMEOUT|PROBE|MN-major" gpurun_out/r2a_probe.log | head -40
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2a_tests.log 2>&1; tail -5 gpurun_out/r2a_tests.log
+for prec in tf32 fp16; do
+  timeout 200 python bench.py --precision $prec --steps 10 --cpu-baseline-steps 0 --batched-steps 0 2> gpurun_out/r2a_bench_${prec}_err.log | tail -1 > gpurun_out/r2a_bench_${prec}.json
+  python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/r2a_bench_${prec}.json"))
+    print("${prec}", "value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "frac", round(d["roofline"]["frac"], 3), d["stage_ms"], "launches", d["gpu_launches"])
+except Exception as ex:
+    print("${prec} bench failed", ex)
+PY
+done
+tail -3 gpurun_out/r2a_bench_fp16_err.log
