@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("BV2_PRECISION", "tf32"), choices=["fp32", "tf32", "fp16"])
+    ap.add_argument("--precision", default=os.environ.get("BV2_PRECISION", "tf32"), choices=["fp32", "tf32", "fp16g", "fp16"])
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--batched-steps", type=int, default=5, help="extra config-3 (B=32) measurement; 0 disables")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl", "none"],
@@ -367,7 +367,7 @@ def main():
         line = {
             "metric": "audio-sec/s (real-time factor) at 44.1kHz", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"tf32": "tf32", "fp16": "f16xf16+f32acc", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "vs_baseline": None, "dtype": {"tf32": "tf32", "fp16": "f16xf16+f32acc", "fp16g": "f16xf16+f32acc", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": "config2: B=1, T=256 ZH phonemes per GPU, full SynthesizerTrn.infer path (transformer flow)",
                        "global_batch": world * B, "frames_per_utterance": fpu, "audio_seconds_per_step": audio / args.steps,
                        "parallelism": (f"dp{world} (utterance sharding; waveforms to rank 0: " +

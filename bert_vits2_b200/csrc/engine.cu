@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "kernels_simt.cuh"
 #include "tc_conv.cuh"
+#include "tc_attn.cuh"
 
 namespace bv2 {
 
@@ -118,6 +119,8 @@ struct bv2_engine {
         for (int i = 0; i < 4; i++) { BV2_CUDA(cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking)); BV2_CUDA(cudaEventCreateWithFlags(&ev_rb[i], cudaEventDisableTiming)); }
         BV2_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     }
+    int flow_tc = 0;       // 0 SIMT fp32, 1 TF32 tcgen05, 2 FP16 tcgen05 + fused attention (finalize)
+    AttnMnConv attn_mn;    // MN-major descriptor convention of the attention's V operand
     bool profiling = false;
     struct StageEv { cudaEvent_t a = nullptr, b = nullptr; bool rec = false; };
     std::map<std::string, StageEv> stage_ev;
@@ -263,7 +266,7 @@ struct bv2_engine {
     void finalize();
 
     // ---------------------------------------------------------------- launch helpers
-    int tc_out_tf32 = 0, tc_skip_xform = 0;  // one-shot modifiers for the next tensor-core conv() call
+    int tc_out_tf32 = 0, tc_skip_xform = 0, tc_in_f16 = 0, tc_out_f16 = 0;  // one-shot modifiers for the next tensor-core conv() call
     void conv(const ConvW& cw, const Act& x, const Act& y, cudaStream_t s, ConvArgs extra = ConvArgs(), int cin_off = 0,
               int cout_off = 0, bool allow_tc = false) {
         if (allow_tc && cw.tc.w) {
@@ -272,9 +275,9 @@ struct bv2_engine {
             e.res_C_total = extra.res_C_total; e.res_c_off = extra.res_c_off; e.accumulate = extra.accumulate; e.out_scale = extra.out_scale;
             e.out_mask = extra.out_mask; e.lens = extra.lens; e.bias_b = extra.bias_b; e.bias_b_stride = extra.bias_b_stride;
             e.cin_off = cin_off; e.cout_off = cout_off; e.dil = extra.dil ? extra.dil : 1;
-            e.out_tf32 = tc_out_tf32; e.skip_xform = tc_skip_xform;
+            e.out_tf32 = tc_out_tf32; e.skip_xform = tc_skip_xform; e.in_f16 = tc_in_f16; e.out_f16 = tc_out_f16;
             BV2_CHECK(x.T == y.T && x.B == y.B, "conv T/B mismatch");
-            tc_out_tf32 = 0; tc_skip_xform = 0;
+            tc_out_tf32 = 0; tc_skip_xform = 0; tc_in_f16 = 0; tc_out_f16 = 0;
             tc_conv1d(cw.tc, cw.b, x, y, e, s, num_sms);
             launches++;
             return;
@@ -309,7 +312,7 @@ struct bv2_engine {
         k_linear_g<<<grid, 256, 0, s>>>(gproj_w, gproj_b, g, out, gproj_n, cfg.gin_channels);
         BV2_CUDA(cudaGetLastError()); launches++;
     }
-    void run_encoder(const EncoderW& E, Act x, const int* lens, const float* gproj, cudaStream_t s, bool tc);
+    void run_encoder(const EncoderW& E, Act x, const int* lens, const float* gproj, cudaStream_t s, int tc);  // tc: 0 SIMT, 1 TF32, 2 FP16 + fused attention
     void run_dds(const DdsW& D, Act x, const int* lens, cudaStream_t s);
     void run_text_encoder(int B, int T, const int64_t* x, const int64_t* tone, const int64_t* lang, const float* bert,
                           const float* ja, const float* en, const int* lens, const float* gproj, Act& h, Act& stats, cudaStream_t s);
@@ -437,8 +440,11 @@ void bv2_engine::finalize() {
     flows.resize(n);
     // generator_precision: 0 = fp32 SIMT everywhere; 1 = TF32 tcgen05 (flow + Generator); 2 = FP16-operand tcgen05 Generator
     // (same 11-bit significand as TF32, fp32 accumulate, fp32 activations in HBM) + TF32 flow
-    const int tc = c.generator_precision ? 1 : 0;
-    const int gtc = c.generator_precision == 2 ? 2 : tc;
+    // 3 = FP16 operands in the flow too, with the fused attention kernel (tc_attn.cuh)
+    const int tc = c.generator_precision == 3 ? 2 : (c.generator_precision ? 1 : 0);
+    const int gtc = c.generator_precision >= 2 ? 2 : tc;
+    flow_tc = tc;
+    if (tc == 2) tc_flow_attn_init_device();
     for (int i = 0; i < n; i++) {
         CouplingW& fl = flows[i];
         std::string f = "flow.flows." + std::to_string(2 * i);
@@ -522,7 +528,7 @@ void bv2_engine::finalize() {
 
 // ------------------------------------------------------------------------------------------------
 // attentions.Encoder.forward (reference attentions.py:103-120)
-void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const float* gproj, cudaStream_t s, bool tc) {
+void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const float* gproj, cudaStream_t s, int tc) {
     const int B = x.B, T = x.T, H = x.C, Fc = cfg.filter_channels, nh = cfg.n_heads;
     const size_t mark = ws.used();
     Act qkv = ws.act(B, 3 * H, T), att = ws.act(B, H, T), y = ws.act(B, H, T), f = ws.act(B, Fc, T);
@@ -532,6 +538,26 @@ void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const fl
         if (i == cfg.cond_layer_idx) {
             k_add_bvec_mask<<<grid_tcb(T, H, B), 128, 0, s>>>(x.p, gproj + E.g_off, gproj_n, H, T, lens);
             BV2_CUDA(cudaGetLastError()); launches++;
+        }
+        if (tc == 2) {
+            // FP16 engine: the QKV projection's epilogue writes 16-bit c8 q|k|v (the operand images of the fused attention kernel),
+            // the attention kernel writes a 16-bit c8 output that conv_o consumes without a prologue
+            const size_t mk = ws.used();
+            Act qkv16; qkv16.B = B; qkv16.C = 3 * H; qkv16.T = T; qkv16.p = ws.alloc((size_t)B * 3 * H * T / 2);
+            Act att16; att16.B = B; att16.C = H; att16.T = T; att16.p = ws.alloc((size_t)B * H * T / 2);
+            tc_out_f16 = 1;
+            conv(L.qkv, x, qkv16, s, ConvArgs(), 0, 0, true);
+            tc_flow_attn(qkv16, att16, L.relk, L.relv, lens, nh, (int)cfg.window_size, s, attn_mn); launches++;
+            tc_in_f16 = 1;
+            conv(L.o, att16, y, s, ConvArgs(), 0, 0, true);
+            ws.release(mk);
+            layernorm(L.n1, x, y.p, x, s, 0, nullptr, lens, 0);
+            ConvArgs a1; a1.in_mask = 1; a1.act = 1; a1.lens = lens;
+            conv(L.f1, x, f, s, a1, 0, 0, true);
+            ConvArgs a2; a2.in_mask = 1; a2.out_mask = 1; a2.lens = lens;
+            conv(L.f2, f, y, s, a2, 0, 0, true);
+            layernorm(L.n2, x, y.p, x, s, 0, nullptr, lens, i == nl - 1 ? 1 : 0);
+            continue;
         }
         tc_out_tf32 = tc ? 1 : 0;  // q, k, v feed tensor-core GEMMs directly
         conv(L.qkv, x, qkv, s, ConvArgs(), 0, 0, tc);
@@ -607,7 +633,7 @@ void bv2_engine::run_text_encoder(int B, int T, const int64_t* x, const int64_t*
                                                   reinterpret_cast<const long long*>(lang), emb, temb, lemb, h.p, H, T, lens,
                                                   std::sqrt((float)H), cfg.n_vocab, cfg.num_tones, cfg.num_languages);
     BV2_CUDA(cudaGetLastError()); launches++;
-    run_encoder(enc_p, h, lens, gproj, s, false);  // feeds ceil(durations): FP32 FMA only
+    run_encoder(enc_p, h, lens, gproj, s, 0);  // feeds ceil(durations): FP32 FMA only
     ConvArgs a; a.out_mask = 1; a.lens = lens;
     conv(enc_proj, h, stats, s, a, 0, 0, true);
 }
@@ -687,7 +713,7 @@ void bv2_engine::run_flow(Act z, const int* lens, const float* gproj, cudaStream
         conv(fl.pre, z, h, s, a, in_off, 0, tcf);
         Act m_in = h;
         if (cfg.use_transformer_flow) {
-            run_encoder(fl.enc, h, lens, gproj, s, cfg.generator_precision != 0);
+            run_encoder(fl.enc, h, lens, gproj, s, flow_tc);
         } else {
             const int L = cfg.wn_layers;
             Act xin = ws.act(B, 2 * H, F), acts = ws.act(B, H, F), out = ws.act(B, H, F);

@@ -1,0 +1,330 @@
+// Fused windowed relative-position multi-head self-attention of the flow's transformer layers on tcgen05
+// (reference attentions.py:263-322 via attentions.py:103-120, called 16x per infer by TransformerCouplingBlock, models.py:82-145):
+//     scores[i,j] = q_i.k_j + [|j-i| <= w] q_i.Ek[j-i+w]      (q pre-scaled by 1/sqrt(dk) in the QKV projection weights)
+//     p = softmax_j(scores, keys j >= len excluded)            out_i = sum_j p_ij v_j + sum_r p_{i,i+r-w} Ev[r]
+// One CTA = 128 queries of one (batch, head).  S = Q.K^T lives in TMEM (double-buffered), the softmax warps turn it into the
+// FP16 A-operand image P in shared memory, P.V accumulates into a second TMEM accumulator: neither S nor P ever reaches
+// HBM/L2 (round 1: S/P round trips of 4*F^2*4 B per head-layer through three kernels + a V^T pack = 95 us per layer).
+//
+// Operands are the 16-bit c8 tensors the QKV projection's epilogue writes ([B][3H/8][T][8 halves]):
+//   * a [dk/8][rows][8] tile of q or k IS the K-major no-swizzle operand image (TMA copies it straight from global memory);
+//   * v needs no transposition either: [dk/8][keys][8] is the MN-major no-swizzle image of the [keys x dk] B operand
+//     (8 keys x 16 bytes = one 128-byte core matrix), selected with the b_major bit of the instruction descriptor.
+// Two passes over the key tiles instead of an online softmax: pass A computes the row maxima (Q.K^T + max only), pass B
+// recomputes Q.K^T, exponentiates against the final maximum and feeds P.V -- no accumulator rescaling, i.e. no TMEM
+// read-modify-write in the MMA dependency chain, at the price of 12 extra (cheap, overlapped) MMAs per key tile.
+//
+// 192 threads: warp 0 TMA producer (Q once, K tiles twice, V tiles once), warp 1 TMEM allocator + MMA issuer,
+// warps 2-5 softmax / epilogue (one thread per query row).
+#pragma once
+#include "tc_conv.cuh"
+
+namespace bv2 {
+
+struct AttnParams {
+    const uint4* qkv;   // 16-bit c8 [B][3H/8][T][8]: q | k | v channel blocks of H each, head h at channels h*dk
+    uint4* att;         // 16-bit c8 [B][H/8][T][8]
+    const float* rel_k; const float* rel_v;  // [2w+1][dk]
+    const int* lens;    // valid length per batch (keys >= len excluded, query rows >= len produce zeros)
+    int B, T, H, heads, window;
+    uint32_t idesc_qk, idesc_pv, v_lbo, v_sbo;
+};
+
+namespace tc {
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void unpack_h8(const uint4& u, float* f) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; e++) { const float2 t = __half22float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+}
+}  // namespace tc
+
+template <int DK, int KT>
+__global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int NG = DK / 8, NREL = 9;
+    constexpr uint32_t QB = DK * 128 * 2, KB = DK * KT * 2, PB = KT * 128 * 2;
+    constexpr float LOG2E = 1.4426950408889634f;
+    static_assert(KT == 128 && DK % 16 == 0 && DK <= 128, "tile shape");
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + QB;
+    uint8_t* sV = sK + 2 * KB;
+    uint8_t* sP = sV + 2 * KB;
+    float* sEk = reinterpret_cast<float*>(sP + 2 * PB);
+    float* sEv = sEk + NREL * DK;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sEv + NREL * DK);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_SEMPTY = 11, B_PFULL = 13, B_PEMPTY = 15, B_OFULL = 17, NBARS = 18 };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int H8 = p.H / 8;
+    const int w = p.window, nrel = 2 * w + 1;
+
+    if (threadIdx.x == 0) {
+        mbar_init(BAR(B_QFULL), 1); mbar_init(BAR(B_OFULL), 1);
+        for (int i = 0; i < 2; i++) {
+            mbar_init(BAR(B_KFULL + i), 1); mbar_init(BAR(B_KEMPTY + i), 1); mbar_init(BAR(B_VFULL + i), 1); mbar_init(BAR(B_VEMPTY + i), 1);
+            mbar_init(BAR(B_SFULL + i), 1); mbar_init(BAR(B_SEMPTY + i), 128); mbar_init(BAR(B_PFULL + i), 128); mbar_init(BAR(B_PEMPTY + i), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // V tiles are loaded with partial row counts at the end of the sequence: rows never written must hold finite values (they meet
+    // p = 0 in the P.V MMA), so both V stages start zeroed; later partial loads leave finite rows of an earlier tile behind.
+    for (int i = threadIdx.x; i < (int)(2 * KB / 16); i += blockDim.x) reinterpret_cast<uint4*>(sV)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < nrel * DK; i += blockDim.x) { sEk[i] = p.rel_k[i]; sEv[i] = p.rel_v[i]; }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    const int len = min(p.lens ? p.lens[b] : p.T, p.T);
+    const int NT = q0 < len ? (len + KT - 1) / KT : 0;  // key tiles that hold at least one valid key
+    const uint4* qbase = p.qkv + ((size_t)b * 3 * H8 + (size_t)h * NG) * p.T;
+    const uint4* kbase = qbase + (size_t)H8 * p.T;
+    const uint4* vbase = kbase + (size_t)H8 * p.T;
+
+    if (warp == 0) {
+        if (NT > 0) {
+            const int nq = min(128, p.T - q0);
+            if (lane == 0) mbar_expect_tx(BAR(B_QFULL), (uint32_t)nq * 16u * NG);
+            __syncwarp();
+            if (lane < NG) bulk_g2s(smem_u32(sQ) + (uint32_t)lane * 128u * 16u, qbase + (size_t)lane * p.T + q0, (uint32_t)nq * 16u, BAR(B_QFULL));
+            for (int s = 0; s < 2 * NT; s++) {
+                const int j = s < NT ? s : s - NT, k0 = j * KT, nk = min(KT, p.T - k0), st = s & 1;
+                if (lane == 0) {
+                    mbar_wait(BAR(B_KEMPTY + st), ((s >> 1) & 1) ^ 1);
+                    mbar_expect_tx(BAR(B_KFULL + st), (uint32_t)nk * 16u * NG);
+                }
+                __syncwarp();
+                if (lane < NG)
+                    bulk_g2s(smem_u32(sK) + (uint32_t)st * KB + (uint32_t)lane * KT * 16u, kbase + (size_t)lane * p.T + k0, (uint32_t)nk * 16u, BAR(B_KFULL + st));
+                if (s >= NT) {
+                    const int vs = j & 1;
+                    if (lane == 0) {
+                        mbar_wait(BAR(B_VEMPTY + vs), ((j >> 1) & 1) ^ 1);
+                        mbar_expect_tx(BAR(B_VFULL + vs), (uint32_t)nk * 16u * NG);
+                    }
+                    __syncwarp();
+                    if (lane < NG)
+                        bulk_g2s(smem_u32(sV) + (uint32_t)vs * KB + (uint32_t)lane * KT * 16u, vbase + (size_t)lane * p.T + k0, (uint32_t)nk * 16u, BAR(B_VFULL + vs));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && NT > 0) {
+            mbar_wait(BAR(B_QFULL), 0);
+            auto qk = [&](int s) {  // S[s&1] = Q . K_tile^T
+                const int st = s & 1;
+                mbar_wait(BAR(B_KFULL + st), (s >> 1) & 1);
+                mbar_wait(BAR(B_SEMPTY + st), ((s >> 1) & 1) ^ 1);
+                fence_after();
+                uint64_t ad = make_desc(smem_u32(sQ), 128u * 16u, 128u);
+                uint64_t bd = make_desc(smem_u32(sK) + (uint32_t)st * KB, (uint32_t)KT * 16u, 128u);
+                const uint32_t d = tmem + (uint32_t)(st * KT);
+#pragma unroll
+                for (int kk = 0; kk < DK / 16; kk++, ad += 2u * 128u, bd += 2u * KT) umma<1>(d, ad, bd, p.idesc_qk, kk ? 1u : 0u);
+                umma_commit(BAR(B_KEMPTY + st));
+                umma_commit(BAR(B_SFULL + st));
+            };
+            qk(0);
+            for (int s = 0; s < 2 * NT; s++) {
+                if (s + 1 < 2 * NT) qk(s + 1);  // the next tile's scores are computed while the softmax warps work on this one
+                if (s >= NT) {
+                    const int j = s - NT, pb = j & 1;
+                    mbar_wait(BAR(B_PFULL + pb), (j >> 1) & 1);
+                    mbar_wait(BAR(B_VFULL + pb), (j >> 1) & 1);
+                    fence_after();
+                    uint64_t ad = make_desc(smem_u32(sP) + (uint32_t)pb * PB, 128u * 16u, 128u);
+                    uint64_t bd = make_desc(smem_u32(sV) + (uint32_t)pb * KB, p.v_lbo, p.v_sbo);
+                    const uint32_t d = tmem + 2u * KT;
+#pragma unroll
+                    for (int kk = 0; kk < KT / 16; kk++, ad += 2u * 128u, bd += 16u) umma<1>(d, ad, bd, p.idesc_pv, (j | kk) ? 1u : 0u);
+                    umma_commit(BAR(B_PEMPTY + pb));
+                    umma_commit(BAR(B_VEMPTY + pb));
+                    if (j == NT - 1) umma_commit(BAR(B_OFULL));
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3, m = q * 32 + lane, i = q0 + m;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        uint4* obase = p.att + ((size_t)b * H8 + (size_t)h * NG) * p.T;
+        if (NT == 0) {  // every query of this tile is padding: zeros
+            if (i < p.T)
+                for (int g = 0; g < NG; g++) obase[(size_t)g * p.T + i] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+            // ---- relative-key logits of this row: qrel[r] = q_i . Ek[r]
+            float qrel[NREL];
+#pragma unroll
+            for (int r = 0; r < NREL; r++) qrel[r] = 0.f;
+            mbar_wait(BAR(B_QFULL), 0);
+            for (int g = 0; g < NG; g++) {
+                float qf[8];
+                unpack_h8(reinterpret_cast<const uint4*>(sQ)[g * 128 + m], qf);
+#pragma unroll
+                for (int r = 0; r < NREL; r++) {
+                    if (r < nrel) {
+                        const float* e = &sEk[r * DK + g * 8];
+#pragma unroll
+                        for (int c = 0; c < 8; c++) qrel[r] = fmaf(qf[c], e[c], qrel[r]);
+                    }
+                }
+            }
+            auto rel_of = [&](int d) { float v = 0.f;
+#pragma unroll
+                for (int r = 0; r < NREL; r++) v = (r == d) ? qrel[r] : v;
+                return v; };
+            // ---- pass A: row maximum over the valid keys
+            float M = -INFINITY;
+            for (int s = 0; s < NT; s++) {
+                const int st = s & 1, k0 = s * KT, nvalid = len - k0;
+                const bool band = (k0 <= q0 + 127 + w) && (k0 + KT - 1 >= q0 - w);
+                mbar_wait(BAR(B_SFULL + st), (s >> 1) & 1);
+                fence_after();
+                for (int c0 = 0; c0 < KT; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(trow + (uint32_t)(st * KT + c0), v);
+                    tmem_wait_ld();
+                    if (band) {
+#pragma unroll
+                        for (int e = 0; e < 32; e++) {
+                            const int d = k0 + c0 + e - i + w;
+                            float x = __uint_as_float(v[e]);
+                            if ((unsigned)d < (unsigned)nrel) x += rel_of(d);
+                            if (c0 + e < nvalid) M = fmaxf(M, x);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; e++)
+                            if (c0 + e < nvalid) M = fmaxf(M, __uint_as_float(v[e]));
+                    }
+                }
+                fence_before();
+                mbar_arrive(BAR(B_SEMPTY + st));
+            }
+            // ---- pass B: p = exp(s - M) -> FP16 operand image in shared memory; row sum; relative-value weights
+            const float M2 = M * LOG2E;
+            float L = 0.f;
+            float prel[NREL];
+#pragma unroll
+            for (int r = 0; r < NREL; r++) prel[r] = 0.f;
+            for (int j = 0; j < NT; j++) {
+                const int s = NT + j, st = s & 1, pb = j & 1, k0 = j * KT, nvalid = len - k0;
+                const bool band = (k0 <= q0 + 127 + w) && (k0 + KT - 1 >= q0 - w);
+                mbar_wait(BAR(B_SFULL + st), (s >> 1) & 1);
+                mbar_wait(BAR(B_PEMPTY + pb), ((j >> 1) & 1) ^ 1);
+                fence_after();
+                uint4* P = reinterpret_cast<uint4*>(sP + (size_t)pb * PB);
+                for (int c0 = 0; c0 < KT; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(trow + (uint32_t)(st * KT + c0), v);
+                    tmem_wait_ld();
+                    float pe[32];
+                    if (band) {
+#pragma unroll
+                        for (int e = 0; e < 32; e++) {
+                            const int d = k0 + c0 + e - i + w;
+                            float x = __uint_as_float(v[e]);
+                            const bool inb = (unsigned)d < (unsigned)nrel;
+                            if (inb) x += rel_of(d);
+                            pe[e] = (c0 + e < nvalid) ? ex2_approx(fmaf(x, LOG2E, -M2)) : 0.f;
+                            if (inb) {
+#pragma unroll
+                                for (int r = 0; r < NREL; r++) prel[r] = (r == d) ? pe[e] : prel[r];
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; e++) pe[e] = (c0 + e < nvalid) ? ex2_approx(fmaf(__uint_as_float(v[e]), LOG2E, -M2)) : 0.f;
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        uint4 o;
+                        o.x = pack_h2(pe[8 * g], pe[8 * g + 1]); o.y = pack_h2(pe[8 * g + 2], pe[8 * g + 3]);
+                        o.z = pack_h2(pe[8 * g + 4], pe[8 * g + 5]); o.w = pack_h2(pe[8 * g + 6], pe[8 * g + 7]);
+                        P[(size_t)(c0 / 8 + g) * 128 + m] = o;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 32; e++) L += pe[e];
+                }
+                fence_before();
+                fence_async_smem();
+                mbar_arrive(BAR(B_PFULL + pb));
+                mbar_arrive(BAR(B_SEMPTY + st));
+            }
+            // ---- epilogue: out = (P.V + sum_r p_rel[r] Ev[r]) / L  -> 16-bit c8 (the operand image of conv_o)
+            mbar_wait(BAR(B_OFULL), 0);
+            fence_after();
+            const float inv = (i < len && L > 0.f) ? 1.f / L : 0.f;
+            for (int c0 = 0; c0 < DK; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(trow + (uint32_t)(2 * KT + c0), v);
+                tmem_wait_ld();
+                float o[32];
+#pragma unroll
+                for (int e = 0; e < 32; e++) o[e] = __uint_as_float(v[e]);
+#pragma unroll
+                for (int r = 0; r < NREL; r++) {
+                    if (r < nrel) {
+                        const float pw = prel[r];
+                        const float* ev = &sEv[r * DK + c0];
+#pragma unroll
+                        for (int e = 0; e < 32; e++) o[e] = fmaf(pw, ev[e], o[e]);
+                    }
+                }
+                if (i < p.T) {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        uint4 u;
+                        u.x = pack_h2(o[8 * g] * inv, o[8 * g + 1] * inv); u.y = pack_h2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
+                        u.z = pack_h2(o[8 * g + 4] * inv, o[8 * g + 5] * inv); u.w = pack_h2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
+                        obase[(size_t)(c0 / 8 + g) * p.T + i] = u;
+                    }
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+// MN-major no-swizzle B operand (v): which of LBO / SBO carries the stride between 8-key blocks (128 B) and which the stride
+// between 8-channel blocks (KT*16 B).  tests/cuda/tc_probe.cu (run_mn_probe) measures the convention on hardware.
+struct AttnMnConv { int lbo_is_kblock = 1; };
+
+inline size_t tc_flow_attn_smem(int DK, int KT) { return (size_t)DK * 128 * 2 + 4 * (size_t)DK * KT * 2 + 2 * (size_t)KT * 128 * 2 + 2 * 9 * (size_t)DK * 4 + 18 * 8 + 16; }
+
+inline void tc_flow_attn_init_device() {
+    BV2_CUDA(cudaFuncSetAttribute(k_flow_attn<96, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+}
+
+// qkv16: 16-bit c8 tensor with C = 3H channels (Act.p reinterpreted); att16: 16-bit c8 tensor with C = H channels.
+inline void tc_flow_attn(const Act& qkv16, const Act& att16, const float* rel_k, const float* rel_v, const int* lens, int heads, int window,
+                         cudaStream_t st, AttnMnConv mn = AttnMnConv()) {
+    const int H = att16.C, dk = H / heads, KT = 128;
+    BV2_CHECK(qkv16.C == 3 * H && dk == 96 && H % 8 == 0 && window <= 4 && qkv16.T == att16.T && qkv16.B == att16.B, "tc_flow_attn shapes (head dim 96, window <= 4)");
+    AttnParams p{};
+    p.qkv = reinterpret_cast<const uint4*>(qkv16.p); p.att = reinterpret_cast<uint4*>(att16.p);
+    p.rel_k = rel_k; p.rel_v = rel_v; p.lens = lens;
+    p.B = qkv16.B; p.T = qkv16.T; p.H = H; p.heads = heads; p.window = window;
+    p.idesc_qk = tc::make_idesc(1, KT);
+    p.idesc_pv = tc::make_idesc(1, dk) | (1u << 16);  // b_major = MN
+    const uint32_t kblk = 128u, nblk = (uint32_t)KT * 16u;
+    p.v_lbo = mn.lbo_is_kblock ? kblk : nblk; p.v_sbo = mn.lbo_is_kblock ? nblk : kblk;
+    launch_pdl(k_flow_attn<96, 128>, dim3(cdiv(p.T, 128), heads, p.B), dim3(192), tc_flow_attn_smem(dk, KT), st, p);
+}
+
+}  // namespace bv2

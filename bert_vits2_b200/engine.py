@@ -16,7 +16,7 @@ class Bv2Error(RuntimeError):
 
 
 #: engine precision -> bv2_config.generator_precision (include/bv2.h)
-PRECISIONS = {"fp32": 0, "tf32": 1, "fp16": 2}
+PRECISIONS = {"fp32": 0, "tf32": 1, "fp16g": 2, "fp16": 3}  # fp16g: FP16 Generator + TF32 flow (A/B only)
 
 
 def _cfg_struct(cfg: ModelConfig, precision: int) -> _lib.Bv2Config:

@@ -8,7 +8,7 @@
 #include <cstdlib>
 #include <random>
 #include <vector>
-#include "../../bert_vits2_b200/csrc/tc_conv.cuh"
+#include "../../bert_vits2_b200/csrc/tc_attn.cuh"
 
 using namespace bv2;
 
@@ -371,12 +371,101 @@ static int run_mn_probe() {
     return found >= 0 ? 0 : 1;
 }
 
+
+// Fused flow attention (tc_attn.cuh) against a double-precision CPU evaluation of reference attentions.py:272-322 on the same
+// FP16-rounded q/k/v (banded relative-key logits, masked softmax, relative-value term).
+static int run_attn(int T, int B, std::vector<int> lens, int lbo_is_kblock, int iters) {
+    const int H = 192, heads = 2, dk = 96, w = 4, nrel = 9;
+    std::mt19937 rng(T * 7 + B);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    std::vector<float> qkv((size_t)B * 3 * H * T), ek((size_t)nrel * dk), ev((size_t)nrel * dk);
+    for (size_t i = 0; i < qkv.size(); i++) qkv[i] = f16_round_host(nd(rng) * ((i / ((size_t)H * T)) % 3 == 0 ? 0.35f : 1.f));  // q carries 1/sqrt(dk)-ish scale
+    for (auto& v : ek) v = nd(rng) * 0.1f;
+    for (auto& v : ev) v = nd(rng) * 0.1f;
+    std::vector<uint16_t> q16(qkv.size());
+    for (int b = 0; b < B; b++) for (int c = 0; c < 3 * H; c++) for (int t = 0; t < T; t++)
+        q16[(((size_t)b * (3 * H / 8) + c / 8) * T + t) * 8 + (c & 7)] = f16_rn_host(qkv[((size_t)b * 3 * H + c) * T + t]);
+    void *dq, *da; int* dl;
+    cudaMalloc(&dq, q16.size() * 2); cudaMemcpy(dq, q16.data(), q16.size() * 2, cudaMemcpyHostToDevice);
+    cudaMalloc(&da, (size_t)B * H * T * 2); cudaMemset(da, 0xff, (size_t)B * H * T * 2);
+    cudaMalloc(&dl, B * 4); cudaMemcpy(dl, lens.data(), B * 4, cudaMemcpyHostToDevice);
+    float* dek = up(ek); float* dev_ = up(ev);
+    Act aq; aq.B = B; aq.C = 3 * H; aq.T = T; aq.p = (float*)dq;
+    Act aa; aa.B = B; aa.C = H; aa.T = T; aa.p = (float*)da;
+    AttnMnConv mn; mn.lbo_is_kblock = lbo_is_kblock;
+    tc_flow_attn(aq, aa, dek, dev_, dl, heads, w, 0, mn);
+    cudaError_t er = cudaDeviceSynchronize();
+    if (er != cudaSuccess) { printf("CUDA error (attn): %s\n", cudaGetErrorString(er)); return 1; }
+    std::vector<uint16_t> got((size_t)B * H * T);
+    cudaMemcpy(got.data(), da, got.size() * 2, cudaMemcpyDeviceToHost);
+    auto gh = [&](int b, int c, int t) { uint16_t u = got[(((size_t)b * (H / 8) + c / 8) * T + t) * 8 + (c & 7)]; __half hh; std::memcpy(&hh, &u, 2); return (double)__half2float(hh); };
+    double maxerr = 0, maxref = 0;
+    std::vector<double> sc(T);
+    for (int b = 0; b < B; b++)
+        for (int h = 0; h < heads; h++)
+            for (int i = 0; i < T; i += (T > 400 ? 37 : 3)) {
+                const int len = lens[b];
+                auto Q = [&](int d, int t) { return (double)qkv[((size_t)b * 3 * H + h * dk + d) * T + t]; };
+                auto K = [&](int d, int t) { return (double)qkv[((size_t)b * 3 * H + H + h * dk + d) * T + t]; };
+                auto V = [&](int d, int t) { return (double)qkv[((size_t)b * 3 * H + 2 * H + h * dk + d) * T + t]; };
+                double mx = -1e300;
+                for (int j = 0; j < len; j++) {
+                    double s = 0;
+                    for (int d = 0; d < dk; d++) s += Q(d, i) * K(d, j);
+                    const int r = j - i + w;
+                    if (r >= 0 && r < nrel) for (int d = 0; d < dk; d++) s += Q(d, i) * ek[(size_t)r * dk + d];
+                    sc[j] = s; mx = std::max(mx, s);
+                }
+                double L = 0;
+                for (int j = 0; j < len; j++) { sc[j] = std::exp(sc[j] - mx); L += sc[j]; }
+                for (int d = 0; d < dk; d += 5) {
+                    double o = 0;
+                    if (i < len) {
+                        for (int j = 0; j < len; j++) o += sc[j] * V(d, j);
+                        for (int r = 0; r < nrel; r++) { const int j = i + r - w; if (j >= 0 && j < len) o += sc[j] * ev[(size_t)r * dk + d]; }
+                        o /= L;
+                    }
+                    const double g = gh(b, h * dk + d, i);
+                    maxerr = std::max(maxerr, std::fabs(g - o)); maxref = std::max(maxref, std::fabs(o));
+                }
+            }
+    float ms = 0;
+    if (iters > 0) {
+        cudaEvent_t a, c; cudaEventCreate(&a); cudaEventCreate(&c);
+        for (int i = 0; i < 3; i++) tc_flow_attn(aq, aa, dek, dev_, dl, heads, w, 0, mn);
+        cudaEventRecord(a);
+        for (int i = 0; i < iters; i++) tc_flow_attn(aq, aa, dek, dev_, dl, heads, w, 0, mn);
+        cudaEventRecord(c); cudaEventSynchronize(c); cudaEventElapsedTime(&ms, a, c); ms /= iters;
+    }
+    const bool ok = maxerr < 4e-3 * std::max(1.0, maxref) && maxerr == maxerr;
+    printf("%s ATTN T=%d B=%d len0=%d mn=%d : maxerr %.3e (ref max %.3f)", ok ? "PASS" : "FAIL", T, B, lens[0], lbo_is_kblock, maxerr, maxref);
+    if (iters > 0) printf("  | %.3f ms", ms);
+    printf("\n"); fflush(stdout);
+    cudaFree(dq); cudaFree(da); cudaFree(dl);
+    free_all();
+    return ok ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
     int fails = 0;
     bool perf = argc > 1;
     try {
         g_flag = tc_init_device();
         fails += run_mn_probe();
+        if (getenv("PROBE_ATTN")) {
+            tc_flow_attn_init_device();
+            const int mn = atoi(getenv("PROBE_ATTN"));
+            fails += run_attn(128, 1, {128}, mn, 0);
+            fails += run_attn(100, 1, {100}, mn, 0);
+            fails += run_attn(300, 2, {300, 170}, mn, 0);
+            fails += run_attn(700, 3, {1, 700, 129}, mn, 0);
+            fails += run_attn(1573, 1, {1573}, mn, perf ? 20 : 0);
+            fails += run_attn(1024, 1, {1024}, mn, perf ? 20 : 0);
+            fails += run_attn(800, 32, std::vector<int>(32, 640), mn, perf ? 10 : 0);
+            fails += g_timeouts;
+            printf("%s (%d failing, %d barrier timeouts)\n", fails ? "ATTN PROBE FAILED" : "ATTN PROBE OK", fails, g_timeouts);
+            return fails ? 1 : 0;
+        }
         for (int f16 = 0; f16 < 2; f16++) {
             // functional: K=1 first (no tap shift), then taps with shifts not multiple of 8 rows
             fails += run_case(f16, 16, 16, 1, 1, 300, 1, 1.f, false, false, 1.f, 0);

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 TOL_FP32 = 2e-4        # max-abs per stage, pre-Generator stages (values are O(1))
 TOL_WAV_FP32 = 2e-5    # waveform RMS, fp32 Generator
 TOL_WAV_TF32 = 1e-3    # waveform RMS, tf32 / fp16-operand tcgen05 Generator (north_star bar)
-PRECISIONS = ["fp32", "tf32", "fp16"]
+PRECISIONS = ["fp32", "tf32", "fp16g", "fp16"]
 
 
 @pytest.fixture(scope="module")
