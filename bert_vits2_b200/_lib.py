@@ -41,6 +41,10 @@ SYMBOLS = {
     "bv2_infer_begin": (C.c_int, [P, C.c_int, C.c_int, I64P, I64P, I64P, I64P, I64P, F32P, F32P, F32P, F32P, C.c_float,
                                   C.c_float, C.c_float, F32P, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "bv2_infer_finish": (C.c_int, [P, F32P, C.c_int64, C.c_float, C.c_int32, F32P, F32P, F32P, F32P, F32P, F32P, F32P, C.c_void_p]),
+    "bv2_infer_finish_pcm16": (C.c_int, [P, F32P, C.c_int64, C.c_float, C.c_int32, C.c_void_p, F32P, F32P, F32P, F32P, F32P, F32P, C.c_void_p]),
+    "bv2_wave_to_pcm16": (C.c_int, [P, C.c_int, C.c_int64, F32P, I64P, C.c_void_p, C.c_void_p]),
+    "bv2_attn_path": (C.c_int, [P, F32P, C.c_void_p]),
+    "bv2_reserve": (C.c_int, [P, C.c_int, C.c_int, C.c_int]),
     "bv2_text_encoder": (C.c_int, [P, C.c_int, C.c_int, I64P, I64P, I64P, I64P, I64P, F32P, F32P, F32P, F32P, F32P, F32P, C.c_void_p]),
     "bv2_duration": (C.c_int, [P, C.c_int, C.c_int, F32P, I64P, I64P, F32P, C.c_float, F32P, F32P, C.c_void_p]),
     "bv2_flow_reverse": (C.c_int, [P, C.c_int, C.c_int, F32P, I64P, I64P, F32P, C.c_void_p]),
@@ -50,6 +54,7 @@ SYMBOLS = {
     "bv2_stage_ms": (C.c_float, [P, C.c_char_p]),
     "bv2_launch_count": (C.c_int64, [P]),
     "bv2_workspace_bytes": (C.c_int64, [P]),
+    "bv2_workspace_grows": (C.c_int64, [P]),
     "bv2_peer_slab_alloc": (C.c_int, [C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "bv2_peer_slab_open": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "bv2_peer_slab_close": (C.c_int, [C.c_int, C.c_void_p]),

@@ -105,7 +105,7 @@ struct bv2_engine {
     Arena ws, persist;  // persist: state kept between infer_begin and infer_finish
     std::map<std::string, DebugBuf> dbg;
     struct {
-        bool active = false; int B = 0, T = 0, F = 0;
+        bool active = false, finished = false; int B = 0, T = 0, F = 0;
         float* stats = nullptr; int* cum = nullptr; long long* ylen = nullptr; int* ylen32 = nullptr; int* lens = nullptr;
         float* gproj = nullptr; float* w_ceil = nullptr;
     } st;
@@ -352,6 +352,21 @@ struct bv2_engine {
         BV2_CUDA(cudaStreamSynchronize(s));
         throw_if_bad_inputs(h);
     }
+    int hop = 512;
+    // wave [B][L] fp32 -> int16 (peak-normalised per utterance over n_valid samples; ylen given in units of `unit` samples)
+    void pcm16(const float* wave, int B, long long L, const long long* ylen, int unit, long long* nval_scratch, unsigned* peak, int16_t* out, cudaStream_t s) {
+        const long long* nv = ylen;
+        if (ylen && unit != 1) {
+            k_scale_i64<<<cdiv(B, 128), 128, 0, s>>>(ylen, nval_scratch, unit, B);
+            BV2_CUDA(cudaGetLastError()); launches++;
+            nv = nval_scratch;
+        }
+        BV2_CUDA(cudaMemsetAsync(peak, 0, (size_t)B * sizeof(unsigned), s));
+        dim3 g1((unsigned)std::min<long long>((L + 255) / 256, 256), B), g2((unsigned)((L + 255) / 256), B);
+        k_wave_peak<<<g1, 256, 0, s>>>(wave, L, nv, peak);
+        k_wave_to_pcm16<<<g2, 256, 0, s>>>(wave, L, nv, peak, reinterpret_cast<short*>(out));
+        BV2_CUDA(cudaGetLastError()); launches += 2;
+    }
     void check_device_error() {
         if (h_err && *reinterpret_cast<volatile int*>(h_err)) {
             *h_err = 0;
@@ -517,6 +532,7 @@ void bv2_engine::finalize() {
         }
     }
     BV2_CHECK(ch == 16, "conv_post kernel instantiated for 16 input channels");
+    hop = 1; for (int i = 0; i < c.n_ups; i++) hop *= c.upsample_rates[i];
     conv_post_w = upload(W("dec.conv_post.weight").data);  // [1][16][7]
     emb_g = upload(W("emb_g.weight").data);
     gproj_n = (int)gb.size();
@@ -846,6 +862,10 @@ static size_t ws_bytes_for(const bv2_config& c, int B, int T, int F) {
     return enc + flow + gen + (64u << 20);
 }
 
+static size_t persist_bytes_for(const bv2_config& c, int B, int T, int gproj_n) {
+    return (size_t)B * T * (2 * c.inter_channels + 8) * 4 + (size_t)B * (gproj_n + c.gin_channels + 16) * 4 + (1 << 20);
+}
+
 extern "C" {
 
 const char* bv2_version(void) { return "bv2-b200 0.1 (sm_100a)"; }
@@ -903,10 +923,10 @@ int bv2_infer_begin(bv2_engine* e, int B, int T, const int64_t* x, const int64_t
     e->dbg.clear();
     e->ws.ensure(ws_bytes_for(c, B, T, 0));
     e->ws.reset();
-    e->persist.ensure((size_t)B * T * (2 * I + 8) * 4 + (size_t)B * (e->gproj_n + c.gin_channels + 16) * 4 + (1 << 20));
+    e->persist.ensure(persist_bytes_for(c, B, T, e->gproj_n));
     e->persist.reset();
     auto& st = e->st;
-    st.active = false; st.B = B; st.T = T;
+    st.active = false; st.finished = false; st.B = B; st.T = T; st.F = 0;
     e->stage_begin("encoder_duration", s);
     st.ylen = reinterpret_cast<long long*>(e->persist.alloc(2 * (size_t)B + 4));  // [B] y_lengths, then the input-validation mask
     int* err_dev = reinterpret_cast<int*>(st.ylen + B);
@@ -946,12 +966,12 @@ int bv2_infer_begin(bv2_engine* e, int B, int T, const int64_t* x, const int64_t
     BV2_API_END(e)
 }
 
-int bv2_infer_finish(bv2_engine* e, const float* noise_z, int64_t noise_ld, float noise_scale, int32_t max_len, float* o,
-                     float* attn, float* y_mask, float* z_out, float* z_p, float* m_p, float* logs_p, void* stream) {
+static int infer_finish_impl(bv2_engine* e, const float* noise_z, int64_t noise_ld, float noise_scale, int32_t max_len, float* o, int16_t* o16,
+                             float* attn, float* y_mask, float* z_out, float* z_p, float* m_p, float* logs_p, void* stream) {
     BV2_API_BEGIN(e)
     auto& st = e->st;
     BV2_CHECK(st.active, "infer_finish without infer_begin");
-    BV2_CHECK(noise_z && o && noise_ld >= st.F, "infer_finish args");
+    BV2_CHECK(noise_z && (o || o16) && noise_ld >= st.F, "infer_finish args");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bv2_config& c = e->cfg;
     const int B = st.B, T = st.T, F = st.F, I = c.inter_channels;
@@ -989,9 +1009,63 @@ int bv2_infer_finish(bv2_engine* e, const float* noise_z, int64_t noise_ld, floa
         BV2_CUDA(cudaMemcpy2DAsync(zg.p, (size_t)Fg * 16, z.p, (size_t)F * 16, (size_t)Fg * 16, (size_t)B * I / 4, cudaMemcpyDeviceToDevice, s));
     }
     e->stage_begin("generator", s);
-    e->run_generator(zg, st.ylen32, st.gproj + e->goff_dec, e->gproj_n, o, s);
+    if (o16) {
+        // 16-bit PCM epilogue: the float waveform stays in the workspace, only int16 leaves the engine
+        // (halves the D2H / peer-store bytes); peak-normalised exactly like the reference's convert_to_16_bit_wav (webui.py:86)
+        const long long L = (long long)Fg * e->hop;
+        float* wf = e->ws.alloc((size_t)B * L);
+        unsigned* peak = reinterpret_cast<unsigned*>(e->ws.alloc(B));
+        long long* nval = reinterpret_cast<long long*>(e->ws.alloc(2 * (size_t)B));
+        e->run_generator(zg, st.ylen32, st.gproj + e->goff_dec, e->gproj_n, wf, s);
+        e->pcm16(wf, B, L, st.ylen, e->hop, nval, peak, o16, s);
+    } else {
+        e->run_generator(zg, st.ylen32, st.gproj + e->goff_dec, e->gproj_n, o, s);
+    }
     e->stage_end("generator", s);
-    st.active = false;
+    st.active = false; st.finished = true;
+    BV2_API_END(e)
+}
+
+int bv2_infer_finish(bv2_engine* e, const float* noise_z, int64_t noise_ld, float noise_scale, int32_t max_len, float* o,
+                     float* attn, float* y_mask, float* z_out, float* z_p, float* m_p, float* logs_p, void* stream) {
+    if (!o) return BV2_ERR_ARG;
+    return infer_finish_impl(e, noise_z, noise_ld, noise_scale, max_len, o, nullptr, attn, y_mask, z_out, z_p, m_p, logs_p, stream);
+}
+
+int bv2_infer_finish_pcm16(bv2_engine* e, const float* noise_z, int64_t noise_ld, float noise_scale, int32_t max_len, int16_t* o16,
+                           float* attn, float* y_mask, float* z_out, float* z_p, float* m_p, float* logs_p, void* stream) {
+    if (!o16) return BV2_ERR_ARG;
+    return infer_finish_impl(e, noise_z, noise_ld, noise_scale, max_len, nullptr, o16, attn, y_mask, z_out, z_p, m_p, logs_p, stream);
+}
+
+int bv2_attn_path(bv2_engine* e, float* attn, void* stream) {
+    BV2_API_BEGIN(e)
+    auto& st = e->st;
+    BV2_CHECK(attn && (st.active || st.finished) && st.F > 0, "attn_path needs a preceding infer_begin");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    dim3 grid(cdiv(st.T, 128), st.F, st.B);
+    k_attn_path<<<grid, 128, 0, s>>>(st.cum, st.ylen, st.lens, attn, st.T, st.F);
+    BV2_CUDA(cudaGetLastError()); e->launches++;
+    BV2_API_END(e)
+}
+
+int bv2_wave_to_pcm16(bv2_engine* e, int B, int64_t L, const float* wave, const int64_t* n_valid, int16_t* out, void* stream) {
+    BV2_API_BEGIN(e)
+    BV2_CHECK(e->finalized && B >= 1 && L >= 1 && wave && out, "wave_to_pcm16 args");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned* peak = nullptr;
+    BV2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&peak), (size_t)B * sizeof(unsigned), s));
+    e->pcm16(wave, B, L, reinterpret_cast<const long long*>(n_valid), 1, nullptr, peak, out, s);
+    BV2_CUDA(cudaFreeAsync(peak, s));
+    BV2_API_END(e)
+}
+
+int bv2_reserve(bv2_engine* e, int B, int T, int F_cap) {
+    BV2_API_BEGIN(e)
+    BV2_CHECK(e->finalized && B >= 1 && T >= 1 && F_cap >= 1, "reserve args");
+    const bv2_config& c = e->cfg;
+    e->ws.ensure(ws_bytes_for(c, B, T, F_cap));
+    e->persist.ensure(persist_bytes_for(c, B, T, e->gproj_n));
     BV2_API_END(e)
 }
 
@@ -1147,6 +1221,7 @@ float bv2_stage_ms(bv2_engine* e, const char* stage) {
 
 int64_t bv2_launch_count(const bv2_engine* e) { return e ? e->launches : 0; }
 int64_t bv2_workspace_bytes(const bv2_engine* e) { return e ? (int64_t)(e->ws.cap() + e->persist.cap()) : 0; }
+int64_t bv2_workspace_grows(const bv2_engine* e) { return e ? (int64_t)(e->ws.grows() + e->persist.grows()) : 0; }
 // ---- peer output slab (multi-GPU exchange step): plain CUDA IPC plumbing, no engine state
 static_assert(sizeof(cudaIpcMemHandle_t) == BV2_IPC_HANDLE_BYTES, "IPC handle size");
 int bv2_peer_slab_alloc(int dev, int64_t bytes, void** dptr, unsigned char* handle_out) {

@@ -1081,4 +1081,33 @@ __global__ void k_pack_vt(const float* __restrict__ qkv, float* __restrict__ vt,
     dst[0] = v.x; dst[4] = v.y; dst[8] = v.z; dst[12] = v.w;
 }
 
+__global__ void k_scale_i64(const long long* __restrict__ a, long long* __restrict__ b, int s, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = a[i] * s;
+}
+
+// 16-bit PCM conversion exactly as gradio.processing_utils.convert_to_16_bit_wav does for float input (called on every
+// infer() result by reference webui.py:86, 129, 198): data / abs(data).max() * 32767 -> astype(int16) (truncation), all in
+// float32.  Pass 1: per-utterance peak over the valid samples (positive floats order like their bit patterns).
+__global__ void k_wave_peak(const float* __restrict__ w, long long L, const long long* __restrict__ nvalid, unsigned* __restrict__ peak) {
+    const int b = blockIdx.y;
+    const long long n = nvalid ? min(nvalid[b], L) : L;
+    float m = 0.f;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(w[(size_t)b * L + t]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(peak + b, __float_as_uint(m));
+}
+__global__ void k_wave_to_pcm16(const float* __restrict__ w, long long L, const long long* __restrict__ nvalid, const unsigned* __restrict__ peak,
+                                short* __restrict__ out) {
+    const int b = blockIdx.y;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= L) return;
+    const long long n = nvalid ? min(nvalid[b], L) : L;
+    const float pk = __uint_as_float(peak[b]);
+    short v = 0;
+    if (t < n && pk > 0.f) v = (short)(int)__fmul_rn(__fdiv_rn(w[(size_t)b * L + t], pk), 32767.f);  // C cast = truncation toward zero, as astype(int16)
+    out[(size_t)b * L + t] = v;
+}
+
+
 }  // namespace bv2

@@ -84,6 +84,8 @@ class Engine:
         if rc != 0:
             msg = self.lib.bv2_last_error(self._h).decode(errors="replace")
             if rc == -1:
+                if "index out of range" in msg:
+                    raise IndexError(msg)  # the reference raises IndexError from nn.Embedding
                 raise ValueError(msg)
             raise Bv2Error(f"libbv2 error {rc}: {msg}")
 
@@ -108,6 +110,15 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.bv2_launch_count(self._h))
 
+    @property
+    def workspace_grows(self) -> int:
+        """(Re)allocations of the workspace arenas since creation (0 on the hot path once `reserve` covered the shapes)."""
+        return int(self.lib.bv2_workspace_grows(self._h))
+
+    def reserve(self, B: int, T: int, F_cap: int):
+        """Size the workspace up front for batches up to (B, T tokens, F_cap frames): no allocation / device sync afterwards."""
+        self._check(self.lib.bv2_reserve(self._h, int(B), int(T), int(F_cap)))
+
     def set_profiling(self, on: bool = True):
         self._check(self.lib.bv2_set_profiling(self._h, int(on)))
 
@@ -129,24 +140,43 @@ class Engine:
                                              float(sdp_ratio), _ptr(k[9]), self._stream(), ylen, C.byref(fmax)))
         return np.frombuffer(ylen, dtype=np.int64).copy(), int(fmax.value)
 
-    def infer_finish(self, B, T, F, noise_z, noise_scale, max_len=None, want_attn=True, out_ptr: Optional[int] = None):
+    def infer_finish(self, B, T, F, noise_z, noise_scale, max_len=None, want_attn=True, out_ptr: Optional[int] = None, pcm16: bool = False):
         """`out_ptr`: raw device address that receives the waveform batch [B,1,Fg*hop] instead of a fresh tensor -- e.g. a
         slice of a peer-mapped slab (sharding.PeerWaveSlab) so the Generator epilogue stores straight into the root GPU's
-        memory over NVLink; the returned `o` is then None."""
+        memory over NVLink; the returned `o` is then None.  `want_attn=False` skips the O(F*T) attn write (use `attn_path()`
+        later if it is needed after all).  `pcm16=True`: `o` is int16, peak-normalised exactly as the reference's callers
+        convert every infer() result (gradio convert_to_16_bit_wav, webui.py:86)."""
         I, hop = self.cfg.inter_channels, self.cfg.hop
         noise_z = self._f32(noise_z)
         assert noise_z.shape[0] == B and noise_z.shape[1] == I and noise_z.shape[2] >= F
         Fg = F if (max_len is None or max_len >= F) else int(max_len)
         dev = self.device
-        o = torch.empty(B, 1, Fg * hop, device=dev, dtype=torch.float32) if out_ptr is None else None
+        o = torch.empty(B, 1, Fg * hop, device=dev, dtype=torch.int16 if pcm16 else torch.float32) if out_ptr is None else None
         attn = torch.empty(B, 1, F, T, device=dev, dtype=torch.float32) if want_attn else None
         y_mask = torch.empty(B, 1, F, device=dev, dtype=torch.float32)
         z, z_p, m_p, logs_p = (torch.empty(B, I, F, device=dev, dtype=torch.float32) for _ in range(4))
-        self._check(self.lib.bv2_infer_finish(self._h, _ptr(noise_z), noise_z.shape[2], float(noise_scale),
-                                              -1 if max_len is None else int(max_len), _ptr(o) if out_ptr is None else C.c_void_p(int(out_ptr)),
-                                              _ptr(attn), _ptr(y_mask), _ptr(z),
-                                              _ptr(z_p), _ptr(m_p), _ptr(logs_p), self._stream()))
+        self._last = (B, T, F)
+        fn = self.lib.bv2_infer_finish_pcm16 if pcm16 else self.lib.bv2_infer_finish
+        self._check(fn(self._h, _ptr(noise_z), noise_z.shape[2], float(noise_scale),
+                -1 if max_len is None else int(max_len), _ptr(o) if out_ptr is None else C.c_void_p(int(out_ptr)),
+                _ptr(attn), _ptr(y_mask), _ptr(z), _ptr(z_p), _ptr(m_p), _ptr(logs_p), self._stream()))
         return o, attn, y_mask, (z, z_p, m_p, logs_p)
+
+    def attn_path(self) -> torch.Tensor:
+        """attn [B,1,F,T] of the last infer_begin/infer_finish, materialised on demand (valid until the next infer_begin)."""
+        B, T, F = self._last
+        attn = torch.empty(B, 1, F, T, device=self.device, dtype=torch.float32)
+        self._check(self.lib.bv2_attn_path(self._h, _ptr(attn), self._stream()))
+        return attn
+
+    def wave_to_pcm16(self, wave: torch.Tensor, n_valid: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """wave [B,1,L] or [B,L] fp32 -> int16 of the same shape, as gradio's convert_to_16_bit_wav does per utterance."""
+        w = self._f32(wave)
+        B, L = w.shape[0], w.shape[-1]
+        nv = None if n_valid is None else self._i64(n_valid)
+        out = torch.empty(w.shape, device=self.device, dtype=torch.int16)
+        self._check(self.lib.bv2_wave_to_pcm16(self._h, B, L, _ptr(w), _ptr(nv), _ptr(out), self._stream()))
+        return out
 
     # ---- per-stage entry points (parity tests, microbenchmarks) -----------------------------------------
     def text_encoder(self, x, x_lengths, sid, tone, language, bert, ja_bert, en_bert):

@@ -25,6 +25,51 @@ from .engine import Bv2Error, Engine
 from .spec import ModelConfig, param_specs
 
 
+class LazyAttn:
+    """Stand-in for the `attn` tensor infer() returns (reference models.py:1074): the dense [B,1,F,T] one-hot path is only
+    written when somebody reads it (the reference's own callers never do: infer.py:302-318 uses `o` alone).  Any attribute
+    access, indexing or torch function materialises it once through bv2_attn_path; `.materialize()` returns the tensor."""
+
+    def __init__(self, engine, shape, token):
+        self._engine, self._shape, self._token, self._t = engine, tuple(shape), token, None
+
+    def materialize(self) -> torch.Tensor:
+        if self._t is None:
+            if getattr(self._engine, "_attn_token", None) is not self._token:
+                raise RuntimeError("attn of an earlier infer() call: materialise it before the next call on the same module")
+            self._t = self._engine.attn_path()
+        return self._t
+
+    @property
+    def shape(self):
+        return torch.Size(self._shape)
+
+    def size(self, *a):
+        return self.shape if not a else self.shape[a[0]]
+
+    def dim(self):
+        return len(self._shape)
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+    def __len__(self):
+        return self._shape[0]
+
+    def __repr__(self):
+        return f"LazyAttn(shape={self._shape}, materialized={self._t is not None})"
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        conv = lambda a: a.materialize() if isinstance(a, LazyAttn) else a  # noqa: E731
+        return func(*[conv(a) for a in args], **{k: conv(v) for k, v in (kwargs or {}).items()})
+
+
 class _Node(nn.Module):
     """Anonymous container used to reproduce the reference's dotted state_dict key tree."""
 
@@ -95,10 +140,11 @@ class SynthesizerTrn(nn.Module):
     # ----------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def infer(self, x, x_lengths, sid, tone, language, bert, ja_bert, en_bert, noise_scale=0.667, length_scale=1,
-              noise_scale_w=0.8, max_len=None, sdp_ratio=0, y=None, *, noise_w=None, noise_z=None, w_ceil_override=None):
+              noise_scale_w=0.8, max_len=None, sdp_ratio=0, y=None, *, noise_w=None, noise_z=None, w_ceil_override=None, pcm16=False):
         """reference models.py:1026-1074.  Keyword-only extras (not in the reference): explicit noise tensors
         `noise_w` [B,2,T] / `noise_z` [B,inter,>=F] replacing the two in-model RNG draws (models.py:249, 1071), and
-        `w_ceil_override` [B,T] to teacher-force durations in parity harnesses."""
+        `w_ceil_override` [B,T] to teacher-force durations in parity harnesses, `pcm16=True` to get `o` as int16 converted like
+        the reference's callers do (gradio convert_to_16_bit_wav, webui.py:86).  `attn` comes back as a LazyAttn (see above)."""
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise Bv2Error("SynthesizerTrn.infer: module is on CPU; bert_vits2_b200 has no CPU path — call .to('cuda')")
@@ -112,9 +158,10 @@ class SynthesizerTrn(nn.Module):
                                        length_scale, sdp_ratio, w_ceil_override)
         if noise_z is None:  # torch.randn_like(m_p), m_p: [B, inter, F] (models.py:1071)
             noise_z = torch.randn(B, self.inter_channels, F, device=dev, dtype=torch.float32)
-        o, attn, y_mask, aux = eng.infer_finish(B, T, F, noise_z, noise_scale, max_len)
+        o, _, y_mask, aux = eng.infer_finish(B, T, F, noise_z, noise_scale, max_len, want_attn=False, pcm16=pcm16)
+        eng._attn_token = token = object()
         self.last_y_lengths = y_lengths
-        return o, attn, y_mask, aux
+        return o, LazyAttn(eng, (B, 1, F, T), token), y_mask, aux
 
     def forward(self, *a, **kw):
         raise NotImplementedError("training forward (reference models.py:937-1024) is out of scope; use .infer()")

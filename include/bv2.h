@@ -86,6 +86,26 @@ int bv2_infer_finish(bv2_engine* e, const float* noise_z, int64_t noise_ld, floa
                      float* o, float* attn, float* y_mask, float* z, float* z_p, float* m_p, float* logs_p,
                      void* stream);
 
+/* Same as bv2_infer_finish, but the waveform leaves the engine as 16-bit PCM o16 [B,1,Fg*hop] (int16), converted exactly as the
+ * reference's callers do with gradio.processing_utils.convert_to_16_bit_wav on every infer() result (reference webui.py:86,
+ * 129, 198; hiyoriUI.py:343): per utterance, over its valid samples, data / abs(data).max() * 32767 -> astype(int16) in
+ * float32 (samples past the valid length and all-zero utterances give 0).  Halves the D2H / peer-store bytes. */
+int bv2_infer_finish_pcm16(bv2_engine* e, const float* noise_z, int64_t noise_ld, float noise_scale, int32_t max_len,
+                           int16_t* o16, float* attn, float* y_mask, float* z, float* z_p, float* m_p, float* logs_p,
+                           void* stream);
+/* The same conversion for a waveform batch the caller already holds: wave [B,L] fp32 (device), n_valid [B] int64 (device,
+ * may be NULL = L) -> out [B,L] int16 (device). */
+int bv2_wave_to_pcm16(bv2_engine* e, int B, int64_t L, const float* wave, const int64_t* n_valid, int16_t* out, void* stream);
+
+/* attn [B,1,F,T] (reference commons.generate_path, commons.py:126-140; returned by infer() at models.py:1074) materialised
+ * on demand from the durations of the last bv2_infer_begin: callers that never read it (infer.py:302-318 does not) skip the
+ * O(F*T) write by passing attn = NULL to bv2_infer_finish.  Valid until the next bv2_infer_begin on this engine. */
+int bv2_attn_path(bv2_engine* e, float* attn, void* stream);
+
+/* Size the workspace for batches up to (B, T tokens, F_cap frames) up front: afterwards no call within those bounds
+ * allocates or synchronises the device (the workspace otherwise grows geometrically on first use of a larger shape). */
+int bv2_reserve(bv2_engine* e, int B, int T, int F_cap);
+
 /* ---- per-stage entry points (parity tests + microbenchmarks; same kernels as the whole path) ---------------
  * text encoder: outputs x [B,H,T], m_p/logs_p [B,inter,T] (reference models.py:377-400)                       */
 int bv2_text_encoder(bv2_engine* e, int B, int T, const int64_t* x, const int64_t* x_lengths, const int64_t* sid,
@@ -114,6 +134,7 @@ float bv2_stage_ms(bv2_engine* e, const char* stage);
 /* Counters: kernels launched by the engine since creation / bytes of workspace in use. */
 int64_t bv2_launch_count(const bv2_engine* e);
 int64_t bv2_workspace_bytes(const bv2_engine* e);
+int64_t bv2_workspace_grows(const bv2_engine* e); /* (re)allocations of the workspace arenas since creation */
 
 /* Peer output slab -- the path's one exchange step on a multi-GPU node (the reference has no equivalent:
  * its inference is single-device, webui.py:31, 397-399).  The root rank owns a device slab and exports its CUDA IPC

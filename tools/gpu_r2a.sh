@@ -7,7 +7,7 @@ PROBE_ATTN=1 timeout 120 tests/cuda/tc_probe perf > gpurun_out/r2a_attn1.log 2>&
 PROBE_ATTN=0 timeout 120 tests/cuda/tc_probe > gpurun_out/r2a_attn0.log 2>&1; echo "attn(mn=0) exit $?"; grep -E "ATTN|error|TIMEOUT" gpurun_out/r2a_attn0.log | head -12
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2a_tests.log 2>&1; tail -5 gpurun_out/r2a_tests.log
 for prec in tf32 fp16g fp16; do
-  timeout 200 python bench.py --precision $prec --steps 10 --cpu-baseline-steps 0 --batched-steps 0 2> gpurun_out/r2a_bench_${prec}_err.log | tail -1 > gpurun_out/r2a_bench_${prec}.json
+  timeout 200 python bench.py --precision $prec --steps 10 --cpu-baseline-steps 0 --extras 0 2> gpurun_out/r2a_bench_${prec}_err.log | tail -1 > gpurun_out/r2a_bench_${prec}.json
   python - <<PY
 import json
 try:
