@@ -49,13 +49,14 @@ def import_reference():
     return models, utils, commons, hps
 
 
-def build_reference_net(use_transformer_flow=True):
+def build_reference_net(use_transformer_flow=True, **model_overrides):
     """SynthesizerTrn exactly as infer.get_net_g builds it (infer.py:95-101), on CPU, eval()."""
     models, utils, commons, hps = import_reference()
     from text.symbols import symbols
     kw = dict(hps.model)
     if not use_transformer_flow:
         kw["use_transformer_flow"] = False
+    kw.update(model_overrides)
     net = models.SynthesizerTrn(
         len(symbols),
         hps.data.filter_length // 2 + 1,

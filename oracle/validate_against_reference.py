@@ -30,6 +30,11 @@ FRESH_CASES = [
     (True, [1], [0], dict(sdp_ratio=0.0, noise_scale=0.6, noise_scale_w=0.9, length_scale=1.0), (11, 12, 13)),
     # train_ms.evaluate-style call: the decoder input is cut to max_len frames (models.py:1073)
     (False, [15, 11], [0, 1], dict(sdp_ratio=0.5, noise_scale=0.6, noise_scale_w=0.9, length_scale=1.0, max_len=20), (14, 15, 16)),
+    # spline tails: noise_scale_w = 8 pushes the SDP latent beyond the +-5 tail bound (identity branch, transforms.py:61-74) and onto
+    # the outermost bins; sdp_ratio = 0 keeps exp(logw_sdp) out of the durations (the logw_sdp stage itself is compared)
+    (True, [24, 9], [0, 2], dict(sdp_ratio=0.0, noise_scale=0.6, noise_scale_w=8.0, length_scale=1.0), (17, 18, 19)),
+    # WN flow with n_flow_layer != 4: ResidualCouplingBlock receives n_flow_layer as n_layers, n_flows stays 4 (models.py:918-919)
+    (False, [14], [1], dict(sdp_ratio=0.5, noise_scale=0.6, noise_scale_w=0.9, length_scale=1.0), (20, 21, 22), dict(n_flow_layer=3)),
 ]
 
 
@@ -44,9 +49,11 @@ def validate(cases=FRESH_CASES, f_cap=512):
     """Returns [(case index, {stage: max abs error}, durations_equal)]."""
     mg = _golden_tools()
     out = []
-    for ci, (tflow, lengths, langs, kw, (ws, is_, ns)) in enumerate(cases):
-        net, hps = ref_import.build_reference_net(tflow)
-        cfg = ModelConfig.from_hps_model(hps.model, use_transformer_flow=tflow)
+    for ci, case in enumerate(cases):
+        tflow, lengths, langs, kw, (ws, is_, ns) = case[:5]
+        model_kw = case[5] if len(case) > 5 else {}
+        net, hps = ref_import.build_reference_net(tflow, **model_kw)
+        cfg = ModelConfig.from_hps_model(dict(hps.model, **model_kw), use_transformer_flow=tflow)
         sd = synth.synthetic_state_dict(cfg, ws)
         missing, unexpected = net.load_state_dict(sd, strict=False)
         assert not unexpected and all(k.startswith("enc_q.") for k in missing)

@@ -389,3 +389,20 @@ def infer(sd: Dict[str, torch.Tensor], cfg, x, x_lengths, sid, tone, language, b
                     logs_p_tok=logs_p, x_mask=x_mask, logw_sdp=logw_sdp, logw_dp=logw_dp, logw=logw, w_ceil=w_ceil,
                     y_lengths=y_lengths)
     return o, attn, y_mask, (z, z_p, m_e, l_e)
+
+
+# --------------------------------------------------------------------------------------------------
+# 16-bit PCM conversion applied by the reference's callers to every infer() result (reference webui.py:86,
+# 129, 198; hiyoriUI.py:343): gradio.processing_utils.convert_to_16_bit_wav.  gradio is a third-party
+# dependency that is absent from /root/reference and from this image (requirements.txt pins gradio==3.50.2);
+# its published float branch is restated here:   data = data / np.abs(data).max(); data = data * 32767;
+# data = data.astype(np.int16)   -- float32 arithmetic throughout, astype truncates toward zero.
+# --------------------------------------------------------------------------------------------------
+def convert_to_16_bit_wav(data):
+    import numpy as np
+    data = np.asarray(data)
+    assert data.dtype == np.float32
+    data = data / np.abs(data).max()
+    data = data * 32767
+    return data.astype(np.int16)
+

@@ -302,3 +302,281 @@ def test_long_utterance_T512_and_batch8(engines):
         e = rms(o.cpu(), st["o"])
         print(f"B={B} T={T} F={F}: duration flips {flips}, waveform RMS err {e:.3e}, z max err {float((z.cpu() - st['z']).abs().max()):.2e}")
         assert torch.isfinite(o).all() and e < TOL_WAV_TF32
+
+
+# ================================================================================================
+# round 2: parity gaps named by VERDICT r1 (spline tails, named configs at size, caller-side API vs the oracle, fp16
+# checkpoints, WN flow at size, 16-bit PCM epilogue, lazy attn, input validation, tensor-core flow stage)
+# ================================================================================================
+TOL_Z_TC = 5e-3  # flow output max-abs, tensor-core engines (11-bit-significand operands through 16 transformer layers)
+
+
+def _infer_checked(eng, inp, nw, nz, kw, st, max_flips=2):
+    """Engine infer with the duration-flip protocol: report flips, teacher-force the oracle's w_ceil if any."""
+    B, T = inp["x"].shape
+    ylen, F = eng.infer_begin(inp["x"], inp["x_lengths"], inp["sid"], inp["tone"], inp["language"], inp["bert"], inp["ja_bert"],
+                              inp["en_bert"], nw, kw["noise_scale_w"], kw["length_scale"], kw["sdp_ratio"])
+    w_ceil = eng.debug_read("w_ceil", (B, 1, T))
+    flips = int((w_ceil != st["w_ceil"]).sum())
+    if flips:
+        ylen, F = eng.infer_begin(inp["x"], inp["x_lengths"], inp["sid"], inp["tone"], inp["language"], inp["bert"], inp["ja_bert"],
+                                  inp["en_bert"], nw, kw["noise_scale_w"], kw["length_scale"], kw["sdp_ratio"],
+                                  w_ceil_override=st["w_ceil"][:, 0])
+    assert flips <= max_flips and ylen.tolist() == st["y_lengths"].tolist(), (flips, ylen.tolist())
+    return ylen, F, flips
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_spline_tails_through_bv2_duration(engines, precision):
+    """noise_w scaled so that the SDP latent crosses the +-5 tail bound: identity branch (reference transforms.py:61-74), the
+    outermost bins and the boundary itself (inside = (x >= -5) & (x <= 5)).  The oracle is pinned against the live reference
+    on exactly this regime (oracle/validate_against_reference.py case 4)."""
+    from oracle import vits2_oracle as O
+    import torch.nn.functional as Fn
+    cfg, sd = model_for(True, 0)
+    eng = engines(True, precision)
+    inp = synth.synthetic_inputs(cfg, [40, 23], [0, 1], seed=51)
+    nw, _ = synth.synthetic_noise(cfg, 2, 40, 64, seed=52)
+    nw = nw.clone()
+    nw[0, :, :8] = torch.tensor([[-9.0, -5.0, -4.999, 0.0, 4.999, 5.0, 6.0, 9.0]] * 2)  # scaled by 1.0 below: exact tail-bound values
+    g = Fn.embedding(inp["sid"], sd["emb_g.weight"]).unsqueeze(-1)
+    h, _, _, x_mask = O.text_encoder(sd, cfg, inp["x"], inp["x_lengths"], inp["tone"], inp["language"], inp["bert"], inp["ja_bert"], inp["en_bert"], g)
+    for nsw in (1.0, 8.0):
+        ref = O.sdp_reverse(sd, cfg, h, x_mask, g, nw, nsw)
+        a, _ = eng.duration(h, inp["x_lengths"], inp["sid"], nw, nsw)
+        outside = int(((nw * nsw).abs() > 5).sum())
+        err = float((a.cpu() - ref).abs().max())
+        print(f"[{precision}] noise_scale_w={nsw}: {outside} latent values beyond the tail bound, logw_sdp max-abs err {err:.2e} (|ref| max {float(ref.abs().max()):.1f})")
+        assert outside > 0 and err < TOL_FP32 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp16"])
+@pytest.mark.parametrize("name", ["tflow_b1", "tflow_b3"])
+def test_flow_stage_tensor_core_engines(engines, name, precision):
+    meta, gold = load_golden(name)
+    cfg, sd, inp, nw, nz, kw = case_inputs(meta)
+    eng = engines(True, precision)
+    z = eng.flow_reverse(gold["z_p"], gold["y_lengths"], inp["sid"])
+    err = float((z.cpu() - gold["z"]).abs().max())
+    print(f"[{name}/{precision}] flow z max-abs err {err:.2e}")
+    assert err < TOL_Z_TC, err
+
+
+def test_config3_full_size_vs_oracle(engines):
+    """BASELINE.json config 3 at size: B=32 mixed ZH/JA/EN 128-phoneme utterances (length_scale 0.625 as in bench.py)."""
+    from oracle import vits2_oracle as O
+    cfg, sd = model_for(True, 0)
+    eng = engines(True, "fp16")
+    inp = synth.synthetic_inputs(cfg, [128] * 32, [i % 3 for i in range(32)], seed=3)
+    nw, nz = synth.synthetic_noise(cfg, 32, 128, 2048, seed=3)
+    kw = dict(sdp_ratio=0.5, noise_scale=0.6, noise_scale_w=0.9, length_scale=0.625)
+    st = O.infer(sd, cfg, **inp, noise_w=nw, noise_z=nz, return_stages=True, **kw)
+    ylen, F, flips = _infer_checked(eng, inp, nw, nz, kw, st, max_flips=6)
+    o, attn, y_mask, (z, *_) = eng.infer_finish(32, 128, F, nz, kw["noise_scale"])
+    e = rms(o.cpu(), st["o"])
+    print(f"config3 B=32 T=128 F={F}: flips {flips}, waveform RMS err {e:.3e}, z max err {float((z.cpu() - st['z']).abs().max()):.2e}")
+    assert torch.equal(attn.cpu().sum(2), st["w_ceil"]) and e < TOL_WAV_TF32
+
+
+def test_config4_shaped_ragged_batch_vs_oracle(engines):
+    """BASELINE.json config 4 shape (one rank's share, subsampled for the CPU oracle): ragged T in [64, 512] in one padded batch."""
+    from oracle import vits2_oracle as O
+    cfg, sd = model_for(True, 0)
+    eng = engines(True, "fp16")
+    lengths = [64, 173, 512, 256, 384, 450]
+    inp = synth.synthetic_inputs(cfg, lengths, [i % 3 for i in range(len(lengths))], seed=41)
+    nw, nz = synth.synthetic_noise(cfg, len(lengths), 512, 4096, seed=41)
+    kw = dict(sdp_ratio=0.5, noise_scale=0.6, noise_scale_w=0.9, length_scale=0.5)
+    st = O.infer(sd, cfg, **inp, noise_w=nw, noise_z=nz, return_stages=True, **kw)
+    ylen, F, flips = _infer_checked(eng, inp, nw, nz, kw, st, max_flips=4)
+    o, attn, y_mask, (z, *_) = eng.infer_finish(len(lengths), 512, F, nz, kw["noise_scale"])
+    e = rms(o.cpu(), st["o"])
+    print(f"config4-shaped B={len(lengths)} T<=512 F={F}: flips {flips}, waveform RMS err {e:.3e}")
+    assert torch.equal(y_mask.cpu(), st["y_mask"]) and e < TOL_WAV_TF32
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp16"])
+def test_config5_generator_1024_frames(engines, precision):
+    """BASELINE.json config 5: Generator-only, z[1,192,1024] -> wav[1,1,524288] through bv2_generator."""
+    from oracle import vits2_oracle as O
+    cfg, sd = model_for(True, 0)
+    eng = engines(True, precision)
+    z, g = synth.synthetic_generator_inputs(cfg, 1, 1024)
+    ref = O.generator(sd, cfg, z, g)
+    o = eng.generator(z, g).cpu()
+    e = rms(o, ref)
+    print(f"config5/{precision}: waveform RMS err {e:.3e} (signal RMS {float(ref.pow(2).mean().sqrt()):.3f})")
+    assert o.shape == ref.shape == (1, 1, 1024 * 512) and e < (TOL_WAV_FP32 if precision == "fp32" else TOL_WAV_TF32)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_wn_flow_T256_vs_oracle(engines, precision):
+    """use_transformer_flow=False (ResidualCouplingBlock / WN, reference models.py:403-445, modules.py:185-210) at config-2 size."""
+    from oracle import vits2_oracle as O
+    cfg, sd = model_for(False, 0)
+    eng = engines(False, precision)
+    inp = synth.synthetic_inputs(cfg, [256], [0], seed=2)
+    nw, nz = synth.synthetic_noise(cfg, 1, 256, 8192, seed=2)
+    kw = dict(sdp_ratio=0.5, noise_scale=0.6, noise_scale_w=0.9, length_scale=0.3)
+    st = O.infer(sd, cfg, **inp, noise_w=nw, noise_z=nz, return_stages=True, **kw)
+    ylen, F, flips = _infer_checked(eng, inp, nw, nz, kw, st)
+    o, attn, y_mask, (z, *_) = eng.infer_finish(1, 256, F, nz, kw["noise_scale"])
+    e, ez = rms(o.cpu(), st["o"]), float((z.cpu() - st["z"]).abs().max())
+    print(f"WN flow T=256 F={F} [{precision}]: flips {flips}, z max err {ez:.2e}, waveform RMS err {e:.3e}")
+    assert ez < (TOL_FP32 if precision == "fp32" else TOL_Z_TC) and e < (5e-5 if precision == "fp32" else TOL_WAV_TF32)
+
+
+def _dropin(precision="fp32", tflow=True):
+    from bert_vits2_b200.models import SynthesizerTrn
+    cfg, sd = model_for(tflow, 0)
+    net = SynthesizerTrn(112, 1025, 32, 192, 192, 768, 2, 6, 3, 0.1, "1", [3, 7, 11], [[1, 3, 5]] * 3, [8, 8, 2, 2, 2], 512,
+                         [16, 16, 8, 2, 2], n_speakers=850, gin_channels=512, init_seed=None, precision=precision, use_transformer_flow=tflow)
+    net.load_state_dict(sd, strict=False)
+    return cfg, sd, net.to("cuda:0").eval()
+
+
+def test_infer_batch_vs_oracle():
+    """the batched caller-side API against the ORACLE on the same padded buckets and the same RNG draws
+    (torch.randn on the device in the reference's order: [B,2,T] first, then [B,192,F], per bucket)."""
+    from bert_vits2_b200.infer_api import infer_batch
+    from bert_vits2_b200.sharding import deal_buckets
+    from oracle import vits2_oracle as O
+    cfg, sd, net = _dropin("fp32")
+    lens = [9, 14, 11, 14, 30]
+    items, inps = [], []
+    for k, t in enumerate(lens):
+        inp = synth.synthetic_inputs(cfg, [t], [k % 3], seed=20 + k)
+        inps.append(inp)
+        items.append((inp["bert"][0], inp["ja_bert"][0], inp["en_bert"][0], inp["x"][0], inp["tone"][0], inp["language"][0]))
+    kw = dict(sdp_ratio=0.3, noise_scale=0.6, noise_scale_w=0.8, length_scale=1.0)
+    torch.manual_seed(77)
+    outs = infer_batch(net, items, sid=0, batch_size=2, **kw)
+    # replay: same buckets, same device RNG stream
+    torch.manual_seed(77)
+    plan = deal_buckets(lens, world_size=1, batch_size=2)[0]
+    for bucket in plan:
+        ls = [lens[i] for i in bucket]
+        B, T = len(ls), max(ls)
+        pad = {k: torch.zeros(B, T, dtype=torch.int64) for k in ("x", "tone", "language")}
+        feats = {k: torch.zeros(B, 1024, T) for k in ("bert", "ja_bert", "en_bert")}
+        for b, i in enumerate(bucket):
+            t = lens[i]
+            for k in pad:
+                pad[k][b, :t] = inps[i][k][0]
+            for k in feats:
+                feats[k][b, :, :t] = inps[i][k][0]
+        nw = torch.randn(B, 2, T, device="cuda:0").cpu()
+        g = torch.nn.functional.embedding(torch.zeros(B, dtype=torch.int64), sd["emb_g.weight"]).unsqueeze(-1)
+        # frames are needed to draw noise_z with the reference's shape: run the oracle's front end first
+        h, m_p, logs_p, x_mask = O.text_encoder(sd, cfg, pad["x"], torch.tensor(ls), pad["tone"], pad["language"], feats["bert"], feats["ja_bert"], feats["en_bert"], g)
+        logw = O.sdp_reverse(sd, cfg, h, x_mask, g, nw, kw["noise_scale_w"]) * kw["sdp_ratio"] + O.duration_predictor(sd, cfg, h, x_mask, g) * (1 - kw["sdp_ratio"])
+        F = int(torch.ceil(torch.exp(logw) * x_mask * kw["length_scale"]).sum((1, 2)).clamp_min(1).max())
+        nz = torch.randn(B, 192, F, device="cuda:0").cpu()
+        ref, _, ym, _ = O.infer(sd, cfg, pad["x"], torch.tensor(ls), torch.zeros(B, dtype=torch.int64), pad["tone"], pad["language"], feats["bert"],
+                                feats["ja_bert"], feats["en_bert"], noise_w=nw, noise_z=nz, **kw)
+        for b, i in enumerate(bucket):
+            n = int(ym[b].sum()) * 512
+            assert outs[i].shape == (n,), (outs[i].shape, n)
+            e = float(np.sqrt(np.mean((outs[i].astype(np.float64) - ref[b, 0, :n].double().numpy()) ** 2)))
+            assert e < 5e-5, (i, e)
+
+
+def test_max_len_vs_oracle():
+    """train_ms.evaluate-style call (max_len cuts the decoder input, reference models.py:1073) against the oracle."""
+    from oracle import vits2_oracle as O
+    cfg, sd, net = _dropin("fp32")
+    inp = synth.synthetic_inputs(cfg, [12], [2], seed=3)
+    dev = {k: v.to("cuda:0") for k, v in inp.items()}
+    nw, nz = synth.synthetic_noise(cfg, 1, 12, 512, seed=5)
+    kw = dict(sdp_ratio=0.2, noise_scale=0.6, noise_scale_w=0.9, length_scale=1.0)
+    o_cut, _, y_mask, _ = net.infer(**dev, **kw, max_len=10, noise_w=nw.cuda(), noise_z=nz.cuda())
+    ref, _, ym, _ = O.infer(sd, cfg, **inp, noise_w=nw, noise_z=nz, max_len=10, **kw)
+    assert int(ym.sum()) > 10 and o_cut.shape == ref.shape == (1, 1, 10 * 512)
+    assert rms(o_cut.cpu(), ref) < 5e-5
+
+
+def test_fp16_checkpoint_load():
+    """compress_model.py:49-52 style fp16 checkpoints: bv2_set_weight dtype 1 converts on load; equals the oracle run on the
+    same half-rounded weights."""
+    from bert_vits2_b200.engine import Engine
+    from oracle import vits2_oracle as O
+    cfg, sd = model_for(True, 0)
+    sd16 = {k: v.half() for k, v in sd.items()}
+    eng = Engine(cfg, sd16, device="cuda:0", precision="fp32")
+    sdr = {k: v.float() for k, v in sd16.items()}
+    inp = synth.synthetic_inputs(cfg, [21], [0], seed=61)
+    nw, nz = synth.synthetic_noise(cfg, 1, 21, 1024, seed=62)
+    kw = dict(sdp_ratio=0.5, noise_scale=0.6, noise_scale_w=0.9, length_scale=1.0)
+    st = O.infer(sdr, cfg, **inp, noise_w=nw, noise_z=nz, return_stages=True, **kw)
+    ylen, F, flips = _infer_checked(eng, inp, nw, nz, kw, st)
+    o, *_ = eng.infer_finish(1, 21, F, nz, kw["noise_scale"])
+    assert rms(o.cpu(), st["o"]) < 5e-5
+
+
+def test_pcm16_epilogue_bit_exact(engines):
+    """16-bit PCM exactly as the reference's callers convert every infer() result (gradio
+    convert_to_16_bit_wav, webui.py:86).  (1) the device conversion of the ORACLE's float waveform is bit-identical to the
+    restated reference conversion; (2) infer_finish(pcm16=True) is bit-identical to converting the float output of the same call."""
+    from oracle import vits2_oracle as O
+    cfg, sd = model_for(True, 0)
+    eng = engines(True, "fp16")
+    inp = synth.synthetic_inputs(cfg, [17, 9], [0, 1], seed=71)
+    nw, nz = synth.synthetic_noise(cfg, 2, 17, 1024, seed=72)
+    kw = dict(sdp_ratio=0.5, noise_scale=0.6, noise_scale_w=0.9, length_scale=1.0)
+    ref, _, ym, _ = O.infer(sd, cfg, **inp, noise_w=nw, noise_z=nz, **kw)
+    nvalid = (ym.sum((1, 2)).long() * 512)
+    got = eng.wave_to_pcm16(ref, nvalid).cpu().numpy()
+    for b in range(2):
+        n = int(nvalid[b])
+        want = O.convert_to_16_bit_wav(ref[b, 0, :n].numpy())
+        assert np.array_equal(got[b, 0, :n], want) and not got[b, 0, n:].any()
+    ylen, F = eng.infer_begin(inp["x"], inp["x_lengths"], inp["sid"], inp["tone"], inp["language"], inp["bert"], inp["ja_bert"], inp["en_bert"], nw, 0.9, 1.0, 0.5)
+    o_f, *_ = eng.infer_finish(2, 17, F, nz, 0.6)
+    eng.infer_begin(inp["x"], inp["x_lengths"], inp["sid"], inp["tone"], inp["language"], inp["bert"], inp["ja_bert"], inp["en_bert"], nw, 0.9, 1.0, 0.5)
+    o_i, *_ = eng.infer_finish(2, 17, F, nz, 0.6, pcm16=True)
+    assert o_i.dtype == torch.int16 and o_i.shape == o_f.shape
+    for b in range(2):
+        n = int(ylen[b]) * 512
+        assert np.array_equal(o_i[b, 0, :n].cpu().numpy(), O.convert_to_16_bit_wav(o_f[b, 0, :n].cpu().numpy()))
+
+
+def test_lazy_attn_and_no_hidden_allocation():
+    """attn is materialised on demand (reference callers never read it) and equals the eager path; a steady workload does not
+    touch the allocator after reserve()."""
+    cfg, sd, net = _dropin("fp32")
+    inp = synth.synthetic_inputs(cfg, [13, 8], [0, 2], seed=81)
+    dev = {k: v.to("cuda:0") for k, v in inp.items()}
+    eng = net._engine(torch.device("cuda:0"))
+    eng.reserve(2, 13, 512)
+    g0 = eng.workspace_grows
+    nw, nz = synth.synthetic_noise(cfg, 2, 13, 512, seed=82)
+    for _ in range(3):
+        o, attn, y_mask, _ = net.infer(**dev, sdp_ratio=0.5, noise_w=nw.cuda(), noise_z=nz.cuda())
+    assert eng.workspace_grows == g0
+    assert type(attn).__name__ == "LazyAttn" and attn.shape == (2, 1, int(y_mask.shape[-1]), 13)
+    dense = attn.materialize()
+    ylen, F = eng.infer_begin(dev["x"], dev["x_lengths"], dev["sid"], dev["tone"], dev["language"], dev["bert"], dev["ja_bert"], dev["en_bert"],
+                              nw, 0.8, 1.0, 0.5)
+    _, eager, *_ = eng.infer_finish(2, 13, F, nz, 0.667, want_attn=True)
+    assert torch.equal(dense, eager) and torch.equal(attn.sum(3).squeeze(1), y_mask.squeeze(1))
+
+
+def test_out_of_range_ids_raise_index_error(engines):
+    """The reference raises IndexError from nn.Embedding; the engine validates on the device (no out-of-bounds read, context alive)."""
+    cfg, sd = model_for(True, 0)
+    eng = engines(True, "fp32")
+    inp = synth.synthetic_inputs(cfg, [10], [0], seed=91)
+    nw, nz = synth.synthetic_noise(cfg, 1, 10, 256, seed=92)
+    args = lambda d: (d["x"], d["x_lengths"], d["sid"], d["tone"], d["language"], d["bert"], d["ja_bert"], d["en_bert"], nw, 0.9, 1.0, 0.5)  # noqa: E731
+    for key, val in (("sid", cfg.n_speakers), ("x", cfg.n_vocab + 5), ("tone", -1), ("language", 7)):
+        bad = {k: v.clone() for k, v in inp.items()}
+        bad[key].view(-1)[0] = val
+        with pytest.raises(IndexError):
+            eng.infer_begin(*args(bad))
+    bad = {k: v.clone() for k, v in inp.items()}
+    bad["x_lengths"][0] = 11
+    with pytest.raises(IndexError):
+        eng.infer_begin(*args(bad))
+    ylen, F = eng.infer_begin(*args(inp))  # still healthy
+    o, *_ = eng.infer_finish(1, 10, F, nz, 0.6)
+    assert torch.isfinite(o).all()

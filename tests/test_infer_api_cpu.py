@@ -57,3 +57,42 @@ def test_infer_batch_order_bucketing_and_trimming():
         assert isinstance(o, np.ndarray) and o.dtype == np.float32 and o.shape == (2 * t * 4,)
         expect = (it[3].float() + 0.5 * (it[0][0] > 0).float()).repeat_interleave(8).numpy()
         assert np.array_equal(o, expect)
+
+
+def test_dropin_loads_through_the_reference_load_checkpoint(tmp_path):
+    """Build container only: the drop-in class goes through the UNMODIFIED reference utils.load_checkpoint (utils.py:65-120,
+    what infer.get_net_g calls at infer.py:102) and hps.model kwargs, and ends up with exactly the checkpoint's tensors
+    (enc_q.* keys present in the file are ignored, as compress_model.py drops them)."""
+    import pytest
+    import torch
+    from oracle import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present (GPU box)")
+    from bert_vits2_b200 import synth
+    from bert_vits2_b200.models import SynthesizerTrn
+    from bert_vits2_b200.spec import ModelConfig
+    models, utils, commons, hps = ref_import.import_reference()
+    from text.symbols import symbols
+    cfg = ModelConfig.from_hps_model(hps.model)
+    sd = synth.synthetic_state_dict(cfg, 3)
+    ck = dict(sd)
+    ck["enc_q.pre.weight"] = torch.zeros(192, 1025, 1)  # training-only module still present in un-compressed checkpoints
+    path = str(tmp_path / "G_0.pth")
+    torch.save({"model": ck, "iteration": 7, "optimizer": None, "learning_rate": 2e-4}, path)
+    net = SynthesizerTrn(len(symbols), hps.data.filter_length // 2 + 1, hps.train.segment_size // hps.data.hop_length,
+                         n_speakers=hps.data.n_speakers, **hps.model)  # exactly infer.get_net_g's construction (infer.py:95-101)
+    net, _, lr, it = utils.load_checkpoint(path, net, None, skip_optimizer=True)
+    assert it == 7 and lr == 2e-4
+    got = net.state_dict()
+    assert set(got) == set(sd)
+    for k, v in sd.items():
+        assert torch.equal(got[k], v), k
+
+
+def test_oracle_pcm16_restatement():
+    """The restated gradio conversion (oracle.convert_to_16_bit_wav): peak maps to +-32767, truncation toward zero."""
+    import numpy as np
+    from oracle import vits2_oracle as O
+    x = np.array([0.0, 0.25, -0.5, 0.1234567, -0.49999], dtype=np.float32)
+    y = O.convert_to_16_bit_wav(x)
+    assert y.dtype == np.int16 and y[2] == -32767 and y[0] == 0 and y[1] == 16383 and y[4] == int(np.float32(-0.49999) / np.float32(0.5) * np.float32(32767))
