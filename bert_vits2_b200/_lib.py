@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libbv2.so")
 SOURCES = [os.path.join(HERE, "csrc", "engine.cu")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "kernels_simt.cuh", "tc_conv.cuh")] + [
+HEADERS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith(".cuh")) + [
     os.path.join(ROOT, "include", "bv2.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
 
@@ -81,6 +81,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if not force and not needs_build():
             return LIB_PATH
         cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
+        if os.environ.get("BV2_BUILD_TUNING"):  # development builds: BV2_* environment knobs of the probes become active (tc_conv.cuh tune_env)
+            cmd.insert(1, "-DBV2_TUNING")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

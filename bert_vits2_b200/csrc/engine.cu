@@ -16,6 +16,7 @@
 #include "kernels_simt.cuh"
 #include "tc_conv.cuh"
 #include "tc_attn.cuh"
+#include "kernels_tok.cuh"
 
 namespace bv2 {
 
@@ -407,7 +408,8 @@ void bv2_engine::finalize() {
     // stages therefore stay on FP32 FMA (SIMT) in every engine (x3 = 0: no tensor-core weight image is packed for them).
     const int x3 = 0;
     BV2_CUDA(cudaSetDevice(device));
-    if (!h_err) h_err = tc_init_device();  // > 48 KB dynamic shared memory opt-in (a per-device function attribute) + device error flag
+    if (!h_err) h_err = tc_init_device();
+    tok_init_device();  // > 48 KB dynamic shared memory opt-in (a per-device function attribute) + device error flag
     // ---- enc_p (reference models.py:333-375)
     emb = upload(W("enc_p.emb.weight").data);
     temb = upload(W("enc_p.tone_emb.weight").data);
@@ -615,6 +617,24 @@ void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const fl
 void bv2_engine::run_dds(const DdsW& D, Act x, const int* lens, cudaStream_t s) {
     const int B = x.B, T = x.T, C = x.C;
     const size_t mark = ws.used();
+    const int nl0 = (int)D.c1.size();
+    if (C == 192 && nl0 >= 2 && tune_env("BV2_DDS_FUSED", 1)) {
+        // one launch per layer (kernels_tok.cuh); the layer reads a +-dilation halo, so it ping-pongs between buffers and the last
+        // layer lands in x again
+        Act tmp[2] = {ws.act(B, C, T), ws.act(B, C, T)};
+        int dil = 1;
+        for (int i = 0; i < nl0; i++) {
+            DdsArgs a;
+            a.x = i == 0 ? x.p : tmp[(i - 1) & 1].p; a.y = i == nl0 - 1 ? x.p : tmp[i & 1].p;
+            a.dw_w = D.sep_w[i]; a.dw_b = D.sep_b[i]; a.w1 = D.c1[i].w; a.b1 = D.c1[i].b;
+            a.g1 = D.n1[i].g; a.be1 = D.n1[i].b; a.g2 = D.n2[i].g; a.be2 = D.n2[i].b;
+            a.lens = lens; a.T = T; a.B = B; a.dil = dil; a.last = i == nl0 - 1;
+            launch_dds_layer(a, C, s); launches++;
+            dil *= cfg.sdp_kernel;
+        }
+        ws.release(mark);
+        return;
+    }
     Act y = ws.act(B, C, T), y2 = ws.act(B, C, T);
     const int nl = (int)D.c1.size();
     int dil = 1;

@@ -5,7 +5,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv | t
 timeout 420 tests/cuda/tc_probe perf > gpurun_out/r2a_probe.log 2>&1; echo "probe exit $?"; grep -c PASS gpurun_out/r2a_probe.log; grep -E "FAIL|error|TIMEOUT|PROBE|MN-major" gpurun_out/r2a_probe.log | head -40
 PROBE_ATTN=1 timeout 120 tests/cuda/tc_probe perf > gpurun_out/r2a_attn1.log 2>&1; echo "attn(mn=1) exit $?"; grep -E "ATTN|MN-major|error|TIMEOUT" gpurun_out/r2a_attn1.log | head -20
 PROBE_ATTN=0 timeout 120 tests/cuda/tc_probe > gpurun_out/r2a_attn0.log 2>&1; echo "attn(mn=0) exit $?"; grep -E "ATTN|error|TIMEOUT" gpurun_out/r2a_attn0.log | head -12
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2a_tests.log 2>&1; tail -5 gpurun_out/r2a_tests.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2a_tests.log 2>&1; tail -25 gpurun_out/r2a_tests.log | cut -c1-220
+BV2_DDS_FUSED=0 timeout 300 python -m pytest tests -m gpu -q -k "duration_stage or text_encoder" > gpurun_out/r2a_tests_nodds.log 2>&1; tail -3 gpurun_out/r2a_tests_nodds.log
 for prec in tf32 fp16g fp16; do
   timeout 200 python bench.py --precision $prec --steps 10 --cpu-baseline-steps 0 --extras 0 2> gpurun_out/r2a_bench_${prec}_err.log | tail -1 > gpurun_out/r2a_bench_${prec}.json
   python - <<PY
