@@ -294,6 +294,21 @@ struct bv2_engine {
         launch_conv1d(a, s);
         launches++;
     }
+    // token-rate FP32 conv through the cluster split-K kernel (kernels_tok.cuh); false -> caller uses the generic path
+    bool tok_conv(const ConvW& cw, const Act& x, const Act& y, cudaStream_t s, const ConvArgs& e, const LnW* ln = nullptr, const float* ln_res = nullptr,
+                  int mask_pre = 0, int cout_off = 0) {
+        if (!tune_env("BV2_TOK_GEMM", 1)) return false;
+        TokGemmArgs a{};
+        a.x = x.p; a.Cin_total = x.C; a.cin_off = 0; a.Cin = cw.Cin;
+        a.w = cw.w; a.Cout_w = cw.Cout_w; a.bias = cw.b; a.bias_b = e.bias_b; a.bias_b_stride = e.bias_b_stride;
+        a.y = y.p; a.Cout_total = y.C; a.cout_off = cout_off;
+        a.res = ln_res; a.res_C_total = 192; a.gamma = ln ? ln->g : nullptr; a.beta = ln ? ln->b : nullptr;
+        a.lens = e.lens; a.T = x.T; a.B = x.B; a.relu = e.act == 1; a.in_mask = e.in_mask; a.out_mask = e.out_mask; a.mask_pre = mask_pre;
+        if (e.res || e.accumulate || e.in_slope != 1.f || e.out_scale != 1.f || (e.dil != 0 && e.dil != 1) || cw.Cin % 16) return false;
+        if (!launch_tok_gemm(a, cw.K, cw.Cout, s)) return false;
+        launches++;
+        return true;
+    }
     void layernorm(const LnW& w, const Act& x, const float* add, const Act& y, cudaStream_t s, int gelu, const float* post_res,
                    const int* lens, int out_mask) {
         LnArgs a; a.x = x.p; a.add = add; a.gamma = w.g; a.beta = w.b; a.y = y.p; a.post_res = post_res; a.C = x.C; a.T = x.T;
@@ -577,6 +592,27 @@ void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const fl
             layernorm(L.n2, x, y.p, x, s, 0, nullptr, lens, i == nl - 1 ? 1 : 0);
             continue;
         }
+        if (tc == 0 && H == 192) {
+            // FP32 token-rate layer: 5 launches (qkv | attention | conv_o + residual + LayerNorm | FFN conv_1 + relu | FFN conv_2 + mask +
+            // residual + LayerNorm) instead of 7, the dense convs on the cluster split-K kernel
+            if (!tok_conv(L.qkv, x, qkv, s, ConvArgs())) conv(L.qkv, x, qkv, s, ConvArgs());
+            dim3 grid(cdiv(T, 16), nh, B);
+            k_attention_rel<96><<<grid, 128, 0, s>>>(qkv.p, L.relk, L.relv, att.p, H, T, lens, cfg.window_size);
+            BV2_CUDA(cudaGetLastError()); launches++;
+            if (!tok_conv(L.o, att, x, s, ConvArgs(), &L.n1, x.p)) {
+                conv(L.o, att, y, s, ConvArgs());
+                layernorm(L.n1, x, y.p, x, s, 0, nullptr, lens, 0);
+            }
+            ConvArgs a1; a1.in_mask = 1; a1.act = 1; a1.lens = lens;
+            if (!tok_conv(L.f1, x, f, s, a1)) conv(L.f1, x, f, s, a1);
+            ConvArgs a2; a2.in_mask = 1; a2.lens = lens; a2.out_mask = i == nl - 1 ? 1 : 0;
+            if (!tok_conv(L.f2, f, x, s, a2, &L.n2, x.p, 1)) {
+                ConvArgs a2b; a2b.in_mask = 1; a2b.out_mask = 1; a2b.lens = lens;
+                conv(L.f2, f, y, s, a2b);
+                layernorm(L.n2, x, y.p, x, s, 0, nullptr, lens, i == nl - 1 ? 1 : 0);
+            }
+            continue;
+        }
         tc_out_tf32 = tc ? 1 : 0;  // q, k, v feed tensor-core GEMMs directly
         conv(L.qkv, x, qkv, s, ConvArgs(), 0, 0, tc);
         tc_out_tf32 = 0;
@@ -664,14 +700,14 @@ void bv2_engine::run_text_encoder(int B, int T, const int64_t* x, const int64_t*
         BV2_CUDA(cudaGetLastError()); launches++;
     }
     Act proj = ws.act(B, H, T);
-    conv(bert_proj, bc, proj, s, ConvArgs(), 0, 0, true);
+    if (!tok_conv(bert_proj, bc, proj, s, ConvArgs())) conv(bert_proj, bc, proj, s, ConvArgs(), 0, 0, true);
     k_embed_sum<<<grid_tcb(T, H, B), 128, 0, s>>>(proj.p, reinterpret_cast<const long long*>(x), reinterpret_cast<const long long*>(tone),
                                                   reinterpret_cast<const long long*>(lang), emb, temb, lemb, h.p, H, T, lens,
                                                   std::sqrt((float)H), cfg.n_vocab, cfg.num_tones, cfg.num_languages);
     BV2_CUDA(cudaGetLastError()); launches++;
     run_encoder(enc_p, h, lens, gproj, s, 0);  // feeds ceil(durations): FP32 FMA only
     ConvArgs a; a.out_mask = 1; a.lens = lens;
-    conv(enc_proj, h, stats, s, a, 0, 0, true);
+    if (!tok_conv(enc_proj, h, stats, s, a)) conv(enc_proj, h, stats, s, a, 0, 0, true);
 }
 
 // StochasticDurationPredictor(reverse) + DurationPredictor (reference models.py:197-204,245-256, 285-299)
@@ -691,10 +727,10 @@ void bv2_engine::run_durations(Act h, const int* lens, const float* gproj, const
     // ---- SDP conditioning
     Act c = ws.act(B, Cf, T), cond = ws.act(B, Cf, T);
     ConvArgs a0; a0.bias_b = gproj + goff_sdp; a0.bias_b_stride = gproj_n;
-    conv(sdp_pre, h, c, s, a0, 0, 0, true);
+    if (!tok_conv(sdp_pre, h, c, s, a0)) conv(sdp_pre, h, c, s, a0, 0, 0, true);
     run_dds(sdp_dds, c, lens, s);
     ConvArgs a1; a1.out_mask = 1; a1.lens = lens;
-    conv(sdp_proj, c, cond, s, a1, 0, 0, true);
+    if (!tok_conv(sdp_proj, c, cond, s, a1)) conv(sdp_proj, c, cond, s, a1, 0, 0, true);
     debug("sdp_cond", cond);
     {
         size_t n = (size_t)B * 2 * T;

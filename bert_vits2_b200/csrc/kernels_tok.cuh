@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(256, 1) k_dds_layer(DdsArgs a) {
         bulk_g2s(smem_u32(sW), a.w1, (uint32_t)(C * C * 4), smem_u32(bar));  // weights: independent of the upstream kernel
     }
     pdl_wait();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int len = a.lens ? a.lens[b] : a.T;
     const float4* x4 = reinterpret_cast<const float4*>(a.x) + (size_t)b * NCG * a.T;
     // ---- phase 1: depthwise conv + LayerNorm 1 + GELU; warp w owns time steps 2w, 2w+1; lane owns c4 groups lane and 32+lane (<16)
@@ -154,12 +155,239 @@ __global__ void __launch_bounds__(256, 1) k_dds_layer(DdsArgs a) {
 }
 
 inline size_t dds_layer_smem(int C) { return (size_t)C * C * 4 + (size_t)C * 16 * 4 + 16; }
-inline void tok_init_device() {
-    BV2_CUDA(cudaFuncSetAttribute(k_dds_layer<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dds_layer_smem(192)));
-}
 inline void launch_dds_layer(const DdsArgs& a, int C, cudaStream_t st) {
     BV2_CHECK(C == 192, "fused DDS layer is instantiated for 192 channels");
     launch_pdl(k_dds_layer<192>, dim3(cdiv(a.T, 16), a.B), dim3(256), dds_layer_smem(C), st, a);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Token-rate FP32 GEMM-style Conv1d (K = 1 or 3 taps, dilation 1) with cluster split-K and fused epilogues: replaces
+// k_conv1d_c4 + k_layernorm_c4 pairs of the text encoder / duration predictors (reference attentions.py:103-120 conv_o + norm,
+// FFN conv_1 / conv_2 + norm attentions.py:438-464; models.py:285-299).
+//   one CTA      = 16 time steps x one 192-channel column block x one slice of the input channels (4 warps; warp w owns time
+//                  steps 4w..4w+3, lane owns output channels 4*lane..+3 and 128+2*lane,+1: 24 accumulators, every weight load
+//                  feeds 4 time steps)
+//   weights      streamed through a 3-stage shared-memory ring by bulk TMA copies (16 input channels x K taps x 192 columns per
+//                stage), the input tile staged once ([time][ci], zero padding / x_mask applied while staging)
+//   split-K      at T = 256 tokens a 768->192 conv has only 16 such tiles; the reduction is therefore cut across a thread-block
+//                CLUSTER of `ksplit` CTAs (one per input-channel slice, so each SM streams 1/ksplit of the weights) and the partial
+//                tiles are summed through distributed shared memory in fixed rank order (deterministic: ceil(durations) must not
+//                depend on scheduling); each rank finishes 16/ksplit rows, so bias / relu / residual + LayerNorm / mask run in the
+//                same kernel on rows that hold all 192 channels.
+// ------------------------------------------------------------------------------------------------
+struct TokGemmArgs {
+    const float* x; int Cin_total, cin_off, Cin;   // c4 input [B][Cin_total/4][T][4], channels [cin_off, cin_off + Cin)
+    const float* w; int Cout_w;                    // packed [Cin][K][Cout_w] (co fastest)
+    const float* bias; const float* bias_b; int bias_b_stride;  // [Cout]; optional per-batch bias row
+    float* y; int Cout_total, cout_off;            // c4 output; column block n covers channels cout_off + 192 n ..
+    const float* res; int res_C_total;             // LayerNorm mode: y = LN(res + conv) (res: c4, 192 channels at offset 0)
+    const float* gamma; const float* beta;         // null: no LayerNorm
+    const int* lens;
+    int T, B, relu, in_mask, out_mask, mask_pre, ksplit;  // mask_pre: (conv + bias) * x_mask BEFORE the residual add (FFN: norm(x + ffn(x) * mask))
+};
+
+template <int K>
+__global__ void __launch_bounds__(128, 1) k_tok_gemm(TokGemmArgs a) {
+    using namespace tc;
+    constexpr int TT = 16, NB = 192, CK = 16, NST = 3, TTP = TT + K - 1, PAD = (K - 1) / 2;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int S = a.ksplit;
+    const int cin_cta = a.Cin / S;                      // input channels of this CTA (multiple of 16)
+    float* sW = reinterpret_cast<float*>(smem);         // [NST][CK][K][NB]
+    float* sX = sW + NST * CK * K * NB;                 // [TTP][cin_cta]
+    float* sP = sX + TTP * cin_cta;                     // [TT][NB] partial tile (split-K only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TT * NB);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = blockIdx.x;                        // cluster rank == K slice
+    const int mtiles = (a.T + TT - 1) / TT;
+    const int mt = blockIdx.y % mtiles, nb = blockIdx.y / mtiles, b = blockIdx.z;
+    const int t0 = mt * TT, ci0 = rank * cin_cta;
+    const int nch = cin_cta / CK;
+    const uint32_t bar0 = smem_u32(bars);
+    const uint32_t stage_bytes = (uint32_t)(CK * K * NB * 4);
+    const float* wbase = a.w + ((size_t)ci0 * K) * a.Cout_w + (size_t)nb * NB;
+    auto issue = [&](int c) {  // warp 0: one bulk copy per (ci, tap) row of 192 columns (768 B), or one per stage when rows are contiguous
+        const int st = c % NST;
+        if (lane == 0) mbar_expect_tx(bar0 + 8u * st, stage_bytes);
+        __syncwarp();
+        const float* src = wbase + (size_t)c * CK * K * a.Cout_w;
+        if (a.Cout_w == NB) {
+            if (lane == 0) bulk_g2s(smem_u32(sW + (size_t)st * CK * K * NB), src, stage_bytes, bar0 + 8u * st);
+        } else {
+            for (int r = lane; r < CK * K; r += 32) bulk_g2s(smem_u32(sW + ((size_t)st * CK * K + r) * NB), src + (size_t)r * a.Cout_w, NB * 4, bar0 + 8u * st);
+        }
+    };
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NST; i++) mbar_init(bar0 + 8u * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0)
+        for (int c = 0; c < NST && c < nch; c++) issue(c);  // weights do not depend on the upstream kernel
+    pdl_wait();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int len = a.lens ? a.lens[b] : a.T;
+    // ---- stage the input tile [TTP][cin_cta] (zero padding, x * x_mask)
+    {
+        const float4* x4 = reinterpret_cast<const float4*>(a.x) + ((size_t)b * (a.Cin_total / 4) + (a.cin_off + ci0) / 4) * a.T;
+        const int ncg = cin_cta / 4;
+        for (int i = threadIdx.x; i < ncg * TTP; i += 128) {
+            const int p = i / ncg, cg = i - p * ncg, t = t0 - PAD + p;  // cg fastest: conflict-free 16-byte shared stores
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t >= 0 && t < a.T && (!a.in_mask || t < len)) v = x4[(size_t)cg * a.T + t];
+            *reinterpret_cast<float4*>(&sX[p * cin_cta + cg * 4]) = v;
+        }
+    }
+    __syncthreads();
+    float acc[4][6];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int e = 0; e < 6; e++) acc[k][e] = 0.f;
+    for (int c = 0; c < nch; c++) {
+        const int st = c % NST;
+        mbar_wait(bar0 + 8u * st, (c / NST) & 1);
+        const float* W = sW + (size_t)st * CK * K * NB;
+#pragma unroll
+        for (int c4 = 0; c4 < CK; c4 += 4) {
+            // activations of 4 input channels at the K + 3 time positions this warp needs (warp-uniform 16-byte loads)
+            float xv[K + 3][4];
+#pragma unroll
+            for (int p = 0; p < K + 3; p++) {
+                const float4 v = *reinterpret_cast<const float4*>(&sX[(4 * warp + p) * cin_cta + c * CK + c4]);
+                xv[p][0] = v.x; xv[p][1] = v.y; xv[p][2] = v.z; xv[p][3] = v.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+#pragma unroll
+                for (int j = 0; j < K; j++) {  // fixed (ci ascending, tap ascending) summation order
+                    const float* wr = W + ((c4 + e) * K + j) * NB;
+                    const float4 wA = *reinterpret_cast<const float4*>(wr + 4 * lane);
+                    const float2 wB = *reinterpret_cast<const float2*>(wr + 128 + 2 * lane);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float x = xv[k + j][e];
+                        acc[k][0] = fmaf(x, wA.x, acc[k][0]); acc[k][1] = fmaf(x, wA.y, acc[k][1]); acc[k][2] = fmaf(x, wA.z, acc[k][2]);
+                        acc[k][3] = fmaf(x, wA.w, acc[k][3]); acc[k][4] = fmaf(x, wB.x, acc[k][4]); acc[k][5] = fmaf(x, wB.y, acc[k][5]);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // every warp is done with stage st
+        if (warp == 0 && c + NST < nch) issue(c + NST);
+    }
+    // ---- epilogue of one finished row (all 192 channels of this column block live in one warp: 6 per lane)
+    const int co = a.cout_off + nb * NB;
+    const int cA = co + 4 * lane, cB = co + 128 + 2 * lane;
+    auto finish_row = [&](int t, float* v) {
+        float4 bA = a.bias ? *reinterpret_cast<const float4*>(a.bias + cA - a.cout_off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 bB = a.bias ? *reinterpret_cast<const float2*>(a.bias + cB - a.cout_off) : make_float2(0.f, 0.f);
+        if (a.bias_b) {
+            const float4 b2 = *reinterpret_cast<const float4*>(a.bias_b + (size_t)b * a.bias_b_stride + cA - a.cout_off);
+            const float2 b3 = *reinterpret_cast<const float2*>(a.bias_b + (size_t)b * a.bias_b_stride + cB - a.cout_off);
+            bA.x += b2.x; bA.y += b2.y; bA.z += b2.z; bA.w += b2.w; bB.x += b3.x; bB.y += b3.y;
+        }
+        v[0] += bA.x; v[1] += bA.y; v[2] += bA.z; v[3] += bA.w; v[4] += bB.x; v[5] += bB.y;
+        if (a.relu) {
+#pragma unroll
+            for (int e = 0; e < 6; e++) v[e] = fmaxf(v[e], 0.f);
+        }
+        if (a.mask_pre && t >= len) {
+#pragma unroll
+            for (int e = 0; e < 6; e++) v[e] = 0.f;
+        }
+        float4* y4 = reinterpret_cast<float4*>(a.y) + (size_t)b * (a.Cout_total / 4) * a.T;
+        if (a.gamma) {  // y = LN(res + v): statistics are warp-uniform, so every lane takes part even when t >= T
+            float rr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (t < a.T) {
+                const float4* r4 = reinterpret_cast<const float4*>(a.res) + (size_t)b * (a.res_C_total / 4) * a.T;
+                const float4 rA = r4[(size_t)lane * a.T + t];
+                const float2 rB = *(reinterpret_cast<const float2*>(r4 + (size_t)(32 + (lane >> 1)) * a.T + t) + (lane & 1));
+                rr[0] = rA.x; rr[1] = rA.y; rr[2] = rA.z; rr[3] = rA.w; rr[4] = rB.x; rr[5] = rB.y;
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int e = 0; e < 6; e++) { v[e] += rr[e]; }
+            s = ((v[0] + v[1]) + (v[2] + v[3])) + (v[4] + v[5]);
+            s = warp_sum(s);
+            const float mean = s / (float)NB;
+            float q = 0.f;
+#pragma unroll
+            for (int e = 0; e < 6; e++) { const float d = v[e] - mean; q += d * d; }
+            q = warp_sum(q);
+            const float rstd = rsqrtf(q / (float)NB + 1e-5f);
+            const float4 gA = *reinterpret_cast<const float4*>(a.gamma + 4 * lane), eA = *reinterpret_cast<const float4*>(a.beta + 4 * lane);
+            const float2 gB = *reinterpret_cast<const float2*>(a.gamma + 128 + 2 * lane), eB = *reinterpret_cast<const float2*>(a.beta + 128 + 2 * lane);
+            v[0] = (v[0] - mean) * rstd * gA.x + eA.x; v[1] = (v[1] - mean) * rstd * gA.y + eA.y; v[2] = (v[2] - mean) * rstd * gA.z + eA.z;
+            v[3] = (v[3] - mean) * rstd * gA.w + eA.w; v[4] = (v[4] - mean) * rstd * gB.x + eB.x; v[5] = (v[5] - mean) * rstd * gB.y + eB.y;
+        }
+        if (t >= a.T) return;
+        const float m = (a.out_mask && t >= len) ? 0.f : 1.f;
+        y4[(size_t)(cA / 4) * a.T + t] = make_float4(v[0] * m, v[1] * m, v[2] * m, v[3] * m);
+        *(reinterpret_cast<float2*>(y4 + (size_t)(cB / 4) * a.T + t) + ((cB >> 1) & 1)) = make_float2(v[4] * m, v[5] * m);
+    };
+    if (S == 1) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) finish_row(t0 + 4 * warp + k, acc[k]);
+        return;
+    }
+    // ---- split-K: partial tiles -> own shared memory -> cluster barrier -> each rank sums and finishes TT/S rows over DSMEM
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float* pr = sP + (4 * warp + k) * NB;
+        *reinterpret_cast<float4*>(pr + 4 * lane) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+        *reinterpret_cast<float2*>(pr + 128 + 2 * lane) = make_float2(acc[k][4], acc[k][5]);
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const int rows = TT / S;
+    for (int r = rank * rows + warp; r < (rank + 1) * rows; r += 4) {
+        float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const uint32_t local = smem_u32(sP + r * NB);
+        for (int q = 0; q < S; q++) {  // fixed rank order
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(q));
+            float4 pA; float2 pB;
+            asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pA.x), "=f"(pA.y), "=f"(pA.z), "=f"(pA.w) : "r"(remote + 16u * lane));
+            asm volatile("ld.shared::cluster.v2.f32 {%0,%1}, [%2];" : "=f"(pB.x), "=f"(pB.y) : "r"(remote + 512u + 8u * lane));
+            v[0] += pA.x; v[1] += pA.y; v[2] += pA.z; v[3] += pA.w; v[4] += pB.x; v[5] += pB.y;
+        }
+        finish_row(t0 + r, v);
+    }
+    // no CTA may exit while a peer still reads its shared memory
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+inline size_t tok_gemm_smem(int K, int cin_cta) { return (size_t)3 * 16 * K * 192 * 4 + (size_t)(16 + K - 1) * cin_cta * 4 + 16 * 192 * 4 + 64; }
+
+// Launch helper: picks the split so that ~128 CTAs exist; requires Cout (of this launch) % 192 == 0, Cin % (16 * split) == 0.
+inline bool launch_tok_gemm(TokGemmArgs a, int K, int Cout, cudaStream_t st, int force_split = 0) {
+    if (!(K == 1 || K == 3) || Cout % 192 || a.Cin % 16 || a.T < 1) return false;
+    if (a.gamma && (Cout != 192 || a.cout_off != 0 || !a.res)) return false;
+    if ((a.in_mask || a.out_mask || a.mask_pre) && !a.lens) return false;
+    const int nbk = Cout / 192, mtiles = cdiv(a.T, 16);
+    int S = 1;
+    const long long base = (long long)nbk * mtiles * a.B;
+    while (S < 8 && base * S < 120 && a.Cin % (16 * S * 2) == 0) S *= 2;
+    if (force_split) S = force_split;
+    if (a.Cin % (16 * S)) return false;
+    a.ksplit = S;
+    const size_t smem = tok_gemm_smem(K, a.Cin / S);
+    if (smem > 227 * 1024) return false;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(S, nbk * mtiles, a.B); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension; attr[1].val.clusterDim.x = S; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    if (K == 1) BV2_CUDA(cudaLaunchKernelEx(&cfg, k_tok_gemm<1>, a)); else BV2_CUDA(cudaLaunchKernelEx(&cfg, k_tok_gemm<3>, a));
+    return true;
+}
+
+inline void tok_init_device() {
+    BV2_CUDA(cudaFuncSetAttribute(k_dds_layer<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dds_layer_smem(192)));
+    BV2_CUDA(cudaFuncSetAttribute(k_tok_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BV2_CUDA(cudaFuncSetAttribute(k_tok_gemm<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 }
 
 }  // namespace bv2

@@ -6,7 +6,7 @@ timeout 420 tests/cuda/tc_probe perf > gpurun_out/r2a_probe.log 2>&1; echo "prob
 PROBE_ATTN=1 timeout 120 tests/cuda/tc_probe perf > gpurun_out/r2a_attn1.log 2>&1; echo "attn(mn=1) exit $?"; grep -E "ATTN|MN-major|error|TIMEOUT" gpurun_out/r2a_attn1.log | head -20
 PROBE_ATTN=0 timeout 120 tests/cuda/tc_probe > gpurun_out/r2a_attn0.log 2>&1; echo "attn(mn=0) exit $?"; grep -E "ATTN|error|TIMEOUT" gpurun_out/r2a_attn0.log | head -12
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/r2a_tests.log 2>&1; tail -25 gpurun_out/r2a_tests.log | cut -c1-220
-BV2_DDS_FUSED=0 timeout 300 python -m pytest tests -m gpu -q -k "duration_stage or text_encoder" > gpurun_out/r2a_tests_nodds.log 2>&1; tail -3 gpurun_out/r2a_tests_nodds.log
+for knob in "BV2_DDS_FUSED=0" "BV2_TOK_GEMM=0" "BV2_DDS_FUSED=0 BV2_TOK_GEMM=0"; do echo "== $knob"; env $knob timeout 300 python -m pytest tests -m gpu -q -k "duration_stage or text_encoder" 2>&1 | tail -3 | cut -c1-200; done
 for prec in tf32 fp16g fp16; do
   timeout 200 python bench.py --precision $prec --steps 10 --cpu-baseline-steps 0 --extras 0 2> gpurun_out/r2a_bench_${prec}_err.log | tail -1 > gpurun_out/r2a_bench_${prec}.json
   python - <<PY
