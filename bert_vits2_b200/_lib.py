@@ -38,6 +38,8 @@ SYMBOLS = {
     "bv2_create": (C.c_int, [C.POINTER(P), C.POINTER(Bv2Config), C.c_int]),
     "bv2_set_weight": (C.c_int, [P, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_int]),
     "bv2_finalize": (C.c_int, [P]),
+    "bv2_save_packed": (C.c_int, [P, C.c_char_p]),
+    "bv2_load_packed": (C.c_int, [P, C.c_char_p]),
     "bv2_infer_begin": (C.c_int, [P, C.c_int, C.c_int, I64P, I64P, I64P, I64P, I64P, F32P, F32P, F32P, F32P, C.c_float,
                                   C.c_float, C.c_float, F32P, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "bv2_infer_finish": (C.c_int, [P, F32P, C.c_int64, C.c_float, C.c_int32, F32P, F32P, F32P, F32P, F32P, F32P, F32P, C.c_void_p]),

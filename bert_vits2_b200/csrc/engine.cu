@@ -1,6 +1,7 @@
 // libbv2: engine (weights, workspace, stage orchestration) and the C ABI declared in include/bv2.h.
 // Orchestrates the path of reference models.SynthesizerTrn.infer (models.py:1026-1074).
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <cuda_fp16.h>
@@ -139,6 +140,7 @@ struct bv2_engine {
 
     ~bv2_engine() {
         for (void* p : dev_allocs) cudaFree(p);
+        if (warena) cudaFree(warena);
         if (h_ylen) cudaFreeHost(h_ylen);
         if (h_err) cudaFreeHost(h_err);
         for (int i = 0; i < 4; i++) { if (side[i]) cudaStreamDestroy(side[i]); if (ev_rb[i]) cudaEventDestroy(ev_rb[i]); }
@@ -152,12 +154,22 @@ struct bv2_engine {
         if (it == host.end()) throw Error(BV2_ERR_STATE, "missing weight: " + k);
         return it->second;
     }
+    // ---- weight arena.  Every device-resident weight image (SIMT packs, tcgen05 stage images, embeddings, LayerNorm vectors)
+    // lives in ONE allocation filled by ONE cudaMemcpy.  build_weights() runs twice: a measuring pass (sizes only, packing
+    // loops skipped) and the real pass that writes into a host mirror at the same offsets.  bv2_save_packed() dumps that
+    // arena; bv2_load_packed() re-runs the structure pass with the packing loops skipped and copies the file in.
+    uint8_t* warena = nullptr; size_t warena_bytes = 0, woff = 0;
+    std::vector<uint8_t> wmirror;
+    bool wmeasure = false, wfill = true;
+    bool packing() const { return wfill && !wmeasure; }  // false: skip the expensive fold / repack loops (only sizes matter)
     float* upload(const std::vector<float>& v) {
-        void* p = nullptr;
-        BV2_CUDA(cudaMalloc(&p, std::max<size_t>(v.size(), 4) * sizeof(float)));
-        BV2_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
-        dev_allocs.push_back(p);
-        return static_cast<float*>(p);
+        const size_t bytes = (std::max<size_t>(v.size(), 4) * sizeof(float) + 255) & ~(size_t)255;
+        const size_t o = woff;
+        woff += bytes;
+        if (wmeasure) return reinterpret_cast<float*>(o + 256);  // never dereferenced; discarded with the measuring pass
+        BV2_CHECK(woff <= warena_bytes, "weight arena overflow");
+        if (wfill) std::memcpy(wmirror.data() + o, v.data(), v.size() * sizeof(float));
+        return reinterpret_cast<float*>(warena + o);
     }
     // torch.nn.utils.weight_norm fold, dim=0: w = g * v / ||v|| over dims (1,2)  
     std::vector<float> fold_wn(const std::string& name, std::vector<int64_t>* shape) const {
@@ -166,6 +178,8 @@ struct bv2_engine {
         int64_t d0 = v.shape[0], inner = v.numel() / d0;
         BV2_CHECK(g.numel() == d0, "weight_g shape " + name);
         std::vector<float> w(v.data.size());
+        *shape = v.shape;
+        if (!packing()) return w;
         for (int64_t i = 0; i < d0; i++) {
             double n = 0;
             for (int64_t j = 0; j < inner; j++) { double x = v.data[i * inner + j]; n += x * x; }
@@ -180,14 +194,15 @@ struct bv2_engine {
     ConvW make_conv(const std::vector<float>& w, int Cout, int Cin, int K, const std::vector<float>* bias, int tc_mode = 0, int tc_nt = 0, int tc_kc = 0) {
         ConvW c; c.Cin = Cin; c.Cout = (Cout + 3) / 4 * 4; c.Cout_w = c.Cout; c.K = K;
         std::vector<float> p((size_t)Cin * K * c.Cout_w, 0.f);
-        for (int co = 0; co < Cout; co++)
-            for (int ci = 0; ci < Cin; ci++)
-                for (int j = 0; j < K; j++) p[((size_t)ci * K + j) * c.Cout_w + co] = w[((size_t)co * Cin + ci) * K + j];
+        if (packing())
+            for (int co = 0; co < Cout; co++)
+                for (int ci = 0; ci < Cin; ci++)
+                    for (int j = 0; j < K; j++) p[((size_t)ci * K + j) * c.Cout_w + co] = w[((size_t)co * Cin + ci) * K + j];
         c.w = upload(p);
         std::vector<float> b(c.Cout, 0.f);
         if (bias) for (int co = 0; co < Cout; co++) b[co] = (*bias)[co];
         c.b = upload(b);
-        if (tc_mode && Cout % 16 == 0) c.tc = tc_pack_weights(*this_uploader(), w, Cout, Cin, K, tc_nt, tc_mode == 2 ? 1 : 0, tc_kc);  // tc_mode: 1 = TF32, 2 = FP16 operands
+        if (tc_mode && Cout % 16 == 0) c.tc = tc_pack_weights(*this_uploader(), w, Cout, Cin, K, tc_nt, tc_mode == 2 ? 1 : 0, tc_kc, packing());  // tc_mode: 1 = TF32, 2 = FP16 operands
         return c;
     }
     // uploader functor handed to tc_conv.cuh
@@ -264,7 +279,13 @@ struct bv2_engine {
         return off;
     }
 
-    void finalize();
+    void finalize(const uint8_t* packed = nullptr, size_t packed_bytes = 0);
+    void build_weights();
+    void reset_weights() {
+        enc_p = EncoderW(); sdp_dds = DdsW(); sdp_flows.clear(); flows.clear(); ups.clear(); resblocks.clear();
+        bert_proj = enc_proj = sdp_pre = sdp_proj = dp_c1 = dp_c2 = dp_proj = conv_pre = ConvW();
+    }
+    std::vector<std::pair<std::string, std::vector<int64_t>>> shape_table;  // kept for bv2_save_packed
 
     // ---------------------------------------------------------------- launch helpers
     int tc_out_tf32 = 0, tc_skip_xform = 0, tc_in_f16 = 0, tc_out_f16 = 0;  // one-shot modifiers for the next tensor-core conv() call
@@ -408,7 +429,7 @@ int* bv2_engine::lens_to_device(const int64_t* xl, int B, Arena& ar, cudaStream_
     return lens;
 }
 
-void bv2_engine::finalize() {
+void bv2_engine::finalize(const uint8_t* packed, size_t packed_bytes) {
     const bv2_config& c = cfg;
     const int H = c.hidden_channels, I = c.inter_channels;
     BV2_CHECK(H % 4 == 0 && I % 8 == 0 && c.filter_channels % 4 == 0 && c.gin_channels % 4 == 0, "channel multiples of 4");
@@ -416,15 +437,46 @@ void bv2_engine::finalize() {
     BV2_CHECK(c.window_size <= 4, "window_size <= 4 (relative-position tables of the attention kernels hold 9 slots)");
     BV2_CHECK(c.n_flows >= 1 && c.n_flows <= 16, "n_flows");
     BV2_CHECK(c.sdp_num_bins == 10 && c.sdp_kernel == 3, "sdp spline bins/kernel");
+    BV2_CUDA(cudaSetDevice(device));
+    if (!h_err) h_err = tc_init_device();  // > 48 KB dynamic shared memory opt-in (a per-device function attribute) + device error flag
+    tok_init_device();
+    shape_table.clear();
+    for (const auto& kv : host) shape_table.emplace_back(kv.first, kv.second.shape);
+    std::sort(shape_table.begin(), shape_table.end());
+    // pass 1: sizes
+    wmeasure = true; woff = 0;
+    build_weights();
+    const size_t total = woff;
+    reset_weights();
+    BV2_CUDA(cudaMalloc(reinterpret_cast<void**>(&warena), total));
+    warena_bytes = total;
+    wmeasure = false; woff = 0;
+    if (packed) {
+        BV2_CHECK(packed_bytes == total, "packed weight file does not match this configuration (arena size)");
+        wfill = false;
+        build_weights();
+        BV2_CUDA(cudaMemcpy(warena, packed, total, cudaMemcpyHostToDevice));
+    } else {
+        wmirror.assign(total, 0);
+        wfill = true;
+        build_weights();
+        BV2_CUDA(cudaMemcpy(warena, wmirror.data(), total, cudaMemcpyHostToDevice));
+        std::vector<uint8_t>().swap(wmirror);
+    }
+    if (!h_ylen) BV2_CUDA(cudaMallocHost(&h_ylen, 4100 * sizeof(long long)));
+    host.clear();
+    finalized = true;
+}
+
+void bv2_engine::build_weights() {
+    const bv2_config& c = cfg;
+    const int H = c.hidden_channels, I = c.inter_channels;
     std::vector<float> gw, gb;
     // Precision policy: stages that feed ceil(durations) never run on the tensor-core path.  Error-compensated 3xTF32
     // was measured in round 1: the tcgen05 FP32 accumulator truncates, so the error grows linearly with the reduction length
     // (~6.6e-8 per accumulated product: 1.5e-4 at Cin*K = 2304) and misses the fp32-class accuracy ceil() needs.  These
     // stages therefore stay on FP32 FMA (SIMT) in every engine (x3 = 0: no tensor-core weight image is packed for them).
     const int x3 = 0;
-    BV2_CUDA(cudaSetDevice(device));
-    if (!h_err) h_err = tc_init_device();
-    tok_init_device();  // > 48 KB dynamic shared memory opt-in (a per-device function attribute) + device error flag
     // ---- enc_p (reference models.py:333-375)
     emb = upload(W("enc_p.emb.weight").data);
     temb = upload(W("enc_p.tone_emb.weight").data);
@@ -528,11 +580,12 @@ void bv2_engine::finalize() {
         UpW u; u.Cin = (int)shp[0]; u.Cout = (int)shp[1]; u.K = (int)shp[2]; u.u = c.upsample_rates[i];
         BV2_CHECK(u.K % u.u == 0 && u.K <= 16 && u.Cin == ch && u.Cout == ch / 2 && (u.K - u.u) % 2 == 0, "upsample config");
         std::vector<float> p((size_t)u.Cin * u.K * u.Cout);
+        if (packing())
         for (int ci = 0; ci < u.Cin; ci++)
             for (int co = 0; co < u.Cout; co++)
                 for (int j = 0; j < u.K; j++) p[((size_t)ci * u.K + j) * u.Cout + co] = w[((size_t)ci * u.Cout + co) * u.K + j];
         u.w = upload(p); u.b = upload(W("dec.ups." + std::to_string(i) + ".bias").data);
-        if (gtc) u.tc = tc_pack_upsample(*this_uploader(), w, u.Cin, u.Cout, u.K, u.u, 32, gtc == 2);
+        if (gtc) u.tc = tc_pack_upsample(*this_uploader(), w, u.Cin, u.Cout, u.K, u.u, 32, gtc == 2, packing());
         ups.push_back(u);
         ch /= 2;
         for (int j = 0; j < c.n_resblock_kernels; j++) {
@@ -554,9 +607,6 @@ void bv2_engine::finalize() {
     emb_g = upload(W("emb_g.weight").data);
     gproj_n = (int)gb.size();
     gproj_w = upload(gw); gproj_b = upload(gb);
-    BV2_CUDA(cudaMallocHost(&h_ylen, 4100 * sizeof(long long)));
-    host.clear();
-    finalized = true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -962,6 +1012,74 @@ int bv2_finalize(bv2_engine* e) {
     BV2_API_BEGIN(e)
     BV2_CHECK(!e->finalized, "already finalized");
     e->finalize();
+    BV2_API_END(e)
+}
+
+// ---- packed engine weight file (the reference's counterpart is compress_model.py:44-53, which only drops enc_q and
+// casts to fp16): header | reference state_dict key/shape table | arena image (weight-norm folded, Flip folded, SIMT + tcgen05 packs).
+namespace {
+struct PackHeader {
+    char magic[8];
+    uint32_t version, cfg_bytes;
+    uint64_t arena_bytes;
+    uint32_t n_keys, reserved;
+    float ea_m[2], ea_logs[2];
+};
+const char kPackMagic[8] = {'B', 'V', '2', 'P', 'A', 'C', 'K', '2'};
+}  // namespace
+
+int bv2_save_packed(bv2_engine* e, const char* path) {
+    BV2_API_BEGIN(e)
+    BV2_CHECK(e->finalized && path, "save_packed needs a finalized engine");
+    std::vector<uint8_t> img(e->warena_bytes);
+    BV2_CUDA(cudaDeviceSynchronize());
+    BV2_CUDA(cudaMemcpy(img.data(), e->warena, e->warena_bytes, cudaMemcpyDeviceToHost));
+    FILE* f = std::fopen(path, "wb");
+    if (!f) throw Error(BV2_ERR_ARG, std::string("cannot open ") + path);
+    PackHeader h{};
+    std::memcpy(h.magic, kPackMagic, 8);
+    h.version = 2; h.cfg_bytes = (uint32_t)sizeof(bv2_config); h.arena_bytes = e->warena_bytes; h.n_keys = (uint32_t)e->shape_table.size();
+    for (int i = 0; i < 2; i++) { h.ea_m[i] = e->ea_m[i]; h.ea_logs[i] = e->ea_logs[i]; }
+    bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(&e->cfg, sizeof(bv2_config), 1, f) == 1;
+    for (const auto& kv : e->shape_table) {
+        const uint32_t kl = (uint32_t)kv.first.size(), nd = (uint32_t)kv.second.size();
+        ok = ok && std::fwrite(&kl, 4, 1, f) == 1 && std::fwrite(kv.first.data(), 1, kl, f) == kl && std::fwrite(&nd, 4, 1, f) == 1;
+        if (nd) ok = ok && std::fwrite(kv.second.data(), sizeof(int64_t), nd, f) == nd;
+    }
+    ok = ok && std::fwrite(img.data(), 1, img.size(), f) == img.size();
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) throw Error(BV2_ERR_INTERNAL, std::string("short write to ") + path);
+    BV2_API_END(e)
+}
+
+int bv2_load_packed(bv2_engine* e, const char* path) {
+    BV2_API_BEGIN(e)
+    BV2_CHECK(!e->finalized && path, "load_packed replaces set_weight + finalize on a fresh engine");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) throw Error(BV2_ERR_ARG, std::string("cannot open ") + path);
+    struct Closer { FILE* f; ~Closer() { std::fclose(f); } } closer{f};
+    PackHeader h{};
+    bv2_config fc{};
+    if (std::fread(&h, sizeof(h), 1, f) != 1 || std::memcmp(h.magic, kPackMagic, 8) != 0 || h.version != 2 || h.cfg_bytes != sizeof(bv2_config) ||
+        std::fread(&fc, sizeof(fc), 1, f) != 1)
+        throw Error(BV2_ERR_ARG, "not a bv2 packed weight file (magic / version / config size)");
+    if (std::memcmp(&fc, &e->cfg, sizeof(fc)) != 0) throw Error(BV2_ERR_ARG, "packed weight file was written for a different configuration / precision");
+    e->host.clear();
+    for (uint32_t i = 0; i < h.n_keys; i++) {
+        uint32_t kl = 0, nd = 0;
+        if (std::fread(&kl, 4, 1, f) != 1 || kl > 512) throw Error(BV2_ERR_ARG, "corrupt key table");
+        std::string key(kl, '\0');
+        if (std::fread(&key[0], 1, kl, f) != kl || std::fread(&nd, 4, 1, f) != 1 || nd > 4) throw Error(BV2_ERR_ARG, "corrupt key table");
+        HostTensor t;
+        t.shape.resize(nd);
+        if (nd && std::fread(t.shape.data(), sizeof(int64_t), nd, f) != nd) throw Error(BV2_ERR_ARG, "corrupt key table");
+        t.data.assign((size_t)t.numel(), 0.f);  // structure only: the packing loops are skipped, the images come from the file
+        e->host[key] = std::move(t);
+    }
+    std::vector<uint8_t> img(h.arena_bytes);
+    if (std::fread(img.data(), 1, img.size(), f) != img.size()) throw Error(BV2_ERR_ARG, "truncated packed weight file");
+    e->finalize(img.data(), img.size());
+    for (int i = 0; i < 2; i++) { e->ea_m[i] = h.ea_m[i]; e->ea_logs[i] = h.ea_logs[i]; }
     BV2_API_END(e)
 }
 

@@ -92,8 +92,10 @@ inline int tune_env(const char* name, int dflt) {
 // w: [Cout][Cin][K] fp32 (weight-norm already folded)
 // nt = N tile (0: largest divisor of Cout that is a multiple of 16 and <= 256)
 // kc = K chunk (channels per pipeline stage)
+// fill = false: only the sizes / layout fields are computed and an all-zero image of the right size is handed to `up` (the engine's
+// measuring pass and bv2_load_packed, where the image comes from a file)
 inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>& up, const std::vector<float>& w, int Cout, int Cin, int K, int nt = 0,
-                               int f16 = 0, int kc = 0) {
+                               int f16 = 0, int kc = 0, bool fill = true) {
     TcConvW t; t.Cin = Cin; t.Cout = Cout; t.K = K; t.f16 = f16;
     if (!nt) { nt = std::min(Cout, 256); while (Cout % nt || nt % 16) nt -= 16; }
     kc = tune_env("BV2_TC_KC", kc);
@@ -109,7 +111,7 @@ inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>&
     const size_t total = (size_t)Cin * K * Cout;
     std::vector<float> p(f16 ? (total + 1) / 2 : total);
     uint16_t* ph = reinterpret_cast<uint16_t*>(p.data());
-    for (int tile = 0; tile < Cout / nt; tile++)
+    for (int tile = 0; fill && tile < Cout / nt; tile++)
         for (int c = 0; c < t.nchunks; c++)
             for (int j = 0; j < K; j++)
                 for (int g = 0; g < ncg; g++)
@@ -130,7 +132,7 @@ inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>&
 // -> an ordinary conv over input-rate time with Kp taps (union of the per-phase offsets), N = u*Cout columns ordered
 // (r, co), structural zeros where a phase does not use a tap.  wT: [Cin][Cout][K] (weight-norm folded).
 inline TcConvW tc_pack_upsample(std::function<float*(const std::vector<float>&)>& up, const std::vector<float>& wT, int Cin, int Cout, int K, int u,
-                                int kc = 0, int f16 = 0) {
+                                int kc = 0, int f16 = 0, bool fill = true) {
     const int p = (K - u) / 2, taps = K / u;
     int omin = 1 << 30, omax = -(1 << 30);
     for (int r = 0; r < u; r++)
@@ -138,7 +140,7 @@ inline TcConvW tc_pack_upsample(std::function<float*(const std::vector<float>&)>
     int half = std::max(-omin, omax);
     const int Kp = 2 * half + 1;  // symmetric so that pad = (Kp-1)/2
     std::vector<float> w((size_t)u * Cout * Cin * Kp, 0.f);  // [N = u*Cout][Cin][Kp]
-    for (int r = 0; r < u; r++)
+    for (int r = 0; fill && r < u; r++)
         for (int m = 0; m < taps; m++) {
             const int o = (r + p) / u - m, j = (r + p) % u + m * u, tap = o + half;
             for (int co = 0; co < Cout; co++)
@@ -146,7 +148,7 @@ inline TcConvW tc_pack_upsample(std::function<float*(const std::vector<float>&)>
                     w[(((size_t)(r * Cout + co)) * Cin + ci) * Kp + tap] = wT[((size_t)ci * Cout + co) * K + j];
         }
     int nt = std::min(u * Cout, 256);
-    TcConvW t = tc_pack_weights(up, w, u * Cout, Cin, Kp, nt, f16, kc);
+    TcConvW t = tc_pack_weights(up, w, u * Cout, Cin, Kp, nt, f16, kc, fill);
     t.ups_u = u; t.ups_cout = Cout;
     return t;
 }

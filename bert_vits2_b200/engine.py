@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -54,7 +55,8 @@ class Engine:
     operands) or 'fp16' (tcgen05 with FP16 operands -- same 11-bit significand as TF32, twice the tensor rate, half the
     operand traffic; fp32 accumulate and fp32 activations in HBM).  Everything that feeds ceil(durations) is FP32 FMA in all three."""
 
-    def __init__(self, cfg: ModelConfig, state_dict: Dict[str, torch.Tensor], device="cuda:0", precision: str = "tf32"):
+    def __init__(self, cfg: ModelConfig, state_dict: Optional[Dict[str, torch.Tensor]], device="cuda:0", precision: str = "tf32",
+                 packed_path: Optional[str] = None):
         self.lib = _lib.load()
         self.cfg = cfg
         self.device = torch.device(device)
@@ -68,6 +70,9 @@ class Engine:
         rc = self.lib.bv2_create(C.byref(self._h), C.byref(cs), idx)
         if rc != 0:
             raise Bv2Error(f"bv2_create failed ({rc}): needs an sm_100 CUDA device, there is no fallback")
+        if packed_path is not None:  # pre-folded, pre-packed weight file written by save_packed(): load = one cudaMemcpy
+            self._check(self.lib.bv2_load_packed(self._h, os.fsencode(packed_path)))
+            return
         for k, v in state_dict.items():
             if not is_infer_key(k):
                 continue
@@ -79,6 +84,10 @@ class Engine:
             shape = (C.c_int64 * max(1, t.dim()))(*t.shape)
             self._check(self.lib.bv2_set_weight(self._h, k.encode(), C.c_void_p(t.data_ptr()), shape, t.dim(), dt))
         self._check(self.lib.bv2_finalize(self._h))
+
+    def save_packed(self, path: str):
+        """Dump the finalized weight arena (folded + packed for this config and precision); reload with Engine(cfg, None, packed_path=path)."""
+        self._check(self.lib.bv2_save_packed(self._h, os.fsencode(path)))
 
     def _check(self, rc):
         if rc != 0:

@@ -69,6 +69,14 @@ int bv2_set_weight(bv2_engine* e, const char* key, const void* host_ptr, const i
  * packs and uploads.  replaces: net_g.eval() + the per-call weight-norm re-evaluation of the reference. */
 int bv2_finalize(bv2_engine* e);
 
+/* Packed engine weight file (the reference's only checkpoint tool is compress_model.py:44-53, which drops enc_q and
+ * casts to fp16).  bv2_save_packed dumps the finalized engine's weight arena: weight-norm and Flip already folded, SIMT and
+ * tcgen05 operand images already packed for this configuration + precision.  bv2_load_packed replaces the
+ * bv2_set_weight... + bv2_finalize sequence on a fresh engine created with the SAME bv2_config: it rebuilds the (cheap) layout
+ * bookkeeping and fills device memory with ONE cudaMemcpy of the file image.  Mismatching configurations are rejected. */
+int bv2_save_packed(bv2_engine* e, const char* path);
+int bv2_load_packed(bv2_engine* e, const char* path);
+
 /* ---- whole path: SynthesizerTrn.infer (reference models.py:1026-1074), split at the data-dependent length.
  * begin: emb_g -> enc_p -> sdp/dp -> durations.  Inputs as the reference passes them (int64 ids, fp32 feats).
  *   noise_w [B,2,T] replaces torch.randn at models.py:249.  w_ceil_override (optional, [B,T] fp32) teacher-forces

@@ -1,5 +1,7 @@
 """GPU parity: the CUDA engine (through the C ABI / drop-in class) against the CPU oracle and against the
 committed reference-generated goldens.  Run on the B200 box: pytest -m gpu."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -580,3 +582,32 @@ def test_out_of_range_ids_raise_index_error(engines):
     ylen, F = eng.infer_begin(*args(inp))  # still healthy
     o, *_ = eng.infer_finish(1, 10, F, nz, 0.6)
     assert torch.isfinite(o).all()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_packed_weight_file_roundtrip(tmp_path, precision):
+    """pre-folded, pre-packed engine weight file.  An engine loaded from the file (one cudaMemcpy) produces
+    bit-identical output to the engine that wrote it; a file written for another precision is rejected."""
+    import time
+    from bert_vits2_b200.engine import Bv2Error, Engine
+    cfg, sd = model_for(True, 0)
+    t0 = time.perf_counter()
+    eng = Engine(cfg, sd, device="cuda:0", precision=precision)
+    t_build = time.perf_counter() - t0
+    path = str(tmp_path / f"bv2_{precision}.pack")
+    eng.save_packed(path)
+    t0 = time.perf_counter()
+    eng2 = Engine(cfg, None, device="cuda:0", precision=precision, packed_path=path)
+    t_load = time.perf_counter() - t0
+    inp = synth.synthetic_inputs(cfg, [19, 7], [0, 1], seed=101)
+    nw, nz = synth.synthetic_noise(cfg, 2, 19, 1024, seed=102)
+    outs = []
+    for e in (eng, eng2):
+        ylen, F = e.infer_begin(inp["x"], inp["x_lengths"], inp["sid"], inp["tone"], inp["language"], inp["bert"], inp["ja_bert"], inp["en_bert"], nw, 0.9, 1.0, 0.5)
+        o, *_ = e.infer_finish(2, 19, F, nz, 0.6)
+        outs.append((ylen.tolist(), o.cpu()))
+    print(f"[{precision}] engine from state_dict {t_build:.2f} s, from packed file {t_load:.2f} s ({os.path.getsize(path) / 1e6:.0f} MB)")
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
+    other = "fp32" if precision != "fp32" else "tf32"
+    with pytest.raises((Bv2Error, ValueError)):
+        Engine(cfg, None, device="cuda:0", precision=other, packed_path=path)
