@@ -245,7 +245,7 @@ struct bv2_engine {
                 for (int i2 = 0; i2 < H; i2++) b[p * H + i2] = bt.data[i2] * s;
             }
             L.qkv = make_conv(w, 3 * H, H, 1, &b, tc_mode, 96, 64);
-            L.o = conv_from(a + ".conv_o", false, tc_mode, 48, 64);
+            L.o = conv_from(a + ".conv_o", false, tc_mode, tc_mode == 2 ? H : 48, 64);  // FP16 flow: one N tile = all channels (LayerNorm fused into the tail)
             L.relk = upload(W(a + ".emb_rel_k").data);
             L.relv = upload(W(a + ".emb_rel_v").data);
             L.n1 = ln_from(name + ".norm_layers_1." + std::to_string(i));
@@ -289,6 +289,7 @@ struct bv2_engine {
 
     // ---------------------------------------------------------------- launch helpers
     int tc_out_tf32 = 0, tc_skip_xform = 0, tc_in_f16 = 0, tc_out_f16 = 0;  // one-shot modifiers for the next tensor-core conv() call
+    const LnW* tc_ln = nullptr;                                               // one-shot: LayerNorm fused into the tail
     void conv(const ConvW& cw, const Act& x, const Act& y, cudaStream_t s, ConvArgs extra = ConvArgs(), int cin_off = 0,
               int cout_off = 0, bool allow_tc = false) {
         if (allow_tc && cw.tc.w) {
@@ -299,7 +300,8 @@ struct bv2_engine {
             e.cin_off = cin_off; e.cout_off = cout_off; e.dil = extra.dil ? extra.dil : 1;
             e.out_tf32 = tc_out_tf32; e.skip_xform = tc_skip_xform; e.in_f16 = tc_in_f16; e.out_f16 = tc_out_f16;
             BV2_CHECK(x.T == y.T && x.B == y.B, "conv T/B mismatch");
-            tc_out_tf32 = 0; tc_skip_xform = 0; tc_in_f16 = 0; tc_out_f16 = 0;
+            if (tc_ln) { e.ln_gamma = tc_ln->g; e.ln_beta = tc_ln->b; }
+            tc_out_tf32 = 0; tc_skip_xform = 0; tc_in_f16 = 0; tc_out_f16 = 0; tc_ln = nullptr;
             tc_conv1d(cw.tc, cw.b, x, y, e, s, num_sms);
             launches++;
             return;
@@ -631,10 +633,12 @@ void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const fl
             tc_out_f16 = 1;
             conv(L.qkv, x, qkv16, s, ConvArgs(), 0, 0, true);
             tc_flow_attn(qkv16, att16, L.relk, L.relv, lens, nh, (int)cfg.window_size, s, attn_mn); launches++;
-            tc_in_f16 = 1;
-            conv(L.o, att16, y, s, ConvArgs(), 0, 0, true);
+            {   // x = norm_1(x + conv_o(att)): the residual is pre-loaded into the accumulator, LayerNorm runs in the tail
+                ConvArgs ao; ao.res = x.p; ao.res_mode = 1; ao.res_C_total = H;
+                tc_in_f16 = 1; tc_ln = &L.n1;
+                conv(L.o, att16, x, s, ao, 0, 0, true);
+            }
             ws.release(mk);
-            layernorm(L.n1, x, y.p, x, s, 0, nullptr, lens, 0);
             ConvArgs a1; a1.in_mask = 1; a1.act = 1; a1.lens = lens;
             conv(L.f1, x, f, s, a1, 0, 0, true);
             ConvArgs a2; a2.in_mask = 1; a2.out_mask = 1; a2.lens = lens;

@@ -57,6 +57,8 @@ struct TcEpi {
     int skip_xform = 0;  // TF32: input already TF32-exact, no activation / mask / padding needed (K == 1)
     int in_f16 = 0;      // FP16: x is a 16-bit c8 tensor [B][C/8][T][8] (the operand image itself: no prologue; K == 1)
     int out_f16 = 0;     // store y as a 16-bit c8 tensor
+    const float* ln_gamma = nullptr; const float* ln_beta = nullptr;  // LayerNorm over the Cout channels of each time step fused into the
+                                                                      // tail (one N tile = all channels; combine with res for norm(x + conv))
 };
 
 inline float tf32_rn_host(float x) {
@@ -162,6 +164,7 @@ struct TcParams {
     float in_slope, out_scale;
     int accumulate, relu, res_mode, in_mask, out_mask, ups_u, ups_cout;
     int out_tf32, skip_xform, in_f16, out_f16;
+    const float* ln_gamma; const float* ln_beta;
     // batched-GEMM extensions (TF32 attention GEMMs of the fp32/tf32 engines): grid z = b * zsplit + h
     int zsplit;                 // 0/1: z == batch
     int x_batch_z, y_batch_z;   // 1: tensor's batch index is z (else b)
@@ -386,6 +389,47 @@ __device__ __forceinline__ void acc_tail_tile(const TcParams& p, uint32_t trow, 
                     ybp[(size_t)((coff + co) / 4) * tstride + tt] = o;
                 }
             }
+        }
+    }
+}
+
+// Tail with a fused LayerNorm over the nt = Cout channels of each row (reference attentions.py:21-24 after the residual add of
+// attentions.py:114,118): the accumulator already holds bias + residual + conv (accumulator-init fusion), so the row statistics
+// are three cheap passes over TMEM (16 TB/s) instead of a separate kernel with an HBM round trip.
+__device__ __forceinline__ void acc_tail_ln(const TcParams& p, uint32_t trow, int b, int t, int nt, int len) {
+    const bool ok = t < p.T;
+    float4* ybp = reinterpret_cast<float4*>(p.y) + (size_t)b * (p.Cout_total / 4) * p.T;
+    float s = 0.f;
+    for (int c0 = 0; c0 < nt; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + (uint32_t)c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; e++) s += __uint_as_float(v[e]);
+    }
+    const float mean = s / (float)nt;
+    float q = 0.f;
+    for (int c0 = 0; c0 < nt; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(trow + (uint32_t)c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 32; e++) { const float d = __uint_as_float(v[e]) - mean; q = fmaf(d, d, q); }
+    }
+    const float rstd = rsqrtf(q / (float)nt + 1e-5f);
+    const float m = (p.out_mask && t >= len) ? 0.f : 1.f;
+    for (int c0 = 0; c0 < nt; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(trow + (uint32_t)c0, v);
+        tmem_wait_ld();
+        if (!ok) continue;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c0 + 4 * g)), be = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c0 + 4 * g));
+            float4 o;
+            o.x = ((__uint_as_float(v[4 * g]) - mean) * rstd * ga.x + be.x) * m; o.y = ((__uint_as_float(v[4 * g + 1]) - mean) * rstd * ga.y + be.y) * m;
+            o.z = ((__uint_as_float(v[4 * g + 2]) - mean) * rstd * ga.z + be.z) * m; o.w = ((__uint_as_float(v[4 * g + 3]) - mean) * rstd * ga.w + be.w) * m;
+            ybp[(size_t)((p.cout_off + c0) / 4 + g) * p.T + t] = o;
         }
     }
 }
@@ -616,8 +660,12 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
         // ===== tail
         mbar_wait(BAR(B_ACC), 0);
         fence_after();
-        for (int mt = 0; mt < MT; mt++)
-            acc_tail_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, len, yb, cout_off);
+        if (GEN && p.ln_gamma) {
+            acc_tail_ln(p, tmem + ((uint32_t)(q * 32) << 16), b, t0 + q * 32 + lane, nt, len);
+        } else {
+            for (int mt = 0; mt < MT; mt++)
+                acc_tail_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, len, yb, cout_off);
+        }
     }
     fence_before();
     __syncthreads();
@@ -1237,13 +1285,15 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     p.in_slope = e.in_slope; p.out_scale = e.out_scale; p.accumulate = e.accumulate; p.relu = e.relu; p.res_mode = e.res ? (e.res_mode ? e.res_mode : 1) : 0;
     p.in_mask = e.in_mask; p.out_mask = e.out_mask; p.ups_u = w.ups_u; p.ups_cout = w.ups_cout;
     p.out_tf32 = e.out_tf32; p.skip_xform = e.skip_xform; p.in_f16 = e.in_f16; p.out_f16 = e.out_f16;
+    p.ln_gamma = e.ln_gamma; p.ln_beta = e.ln_beta;
+    if (e.ln_gamma) BV2_CHECK(e.ln_beta && ntiles == 1 && nt % 32 == 0 && !w.ups_u && !e.out_f16 && !e.out_tf32 && !e.relu && e.out_scale == 1.f && e.res_mode != 2 && e.cout_off % 4 == 0, "LayerNorm tail needs one N tile holding every channel");
     if (e.skip_xform) BV2_CHECK(!F16 && w.K == 1 && e.in_slope == 1.f && !e.in_mask, "skip_xform needs a TF32 plain 1x1 conv input");
     if (e.in_f16) BV2_CHECK(F16 && w.K == 1 && e.in_slope == 1.f && !e.in_mask && e.cin_off % 8 == 0 && x.C % 8 == 0, "in_f16 needs an FP16 plain 1x1 conv");
     if (e.out_f16) BV2_CHECK(F16 && !w.ups_u && e.cout_off % 8 == 0 && y.C % 8 == 0 && !e.res && !e.accumulate, "out_f16 epilogue");
     if (p.in_mask || p.out_mask) BV2_CHECK(e.lens != nullptr, "mask needs lens");
     BV2_CHECK(!(p.relu && (p.res_mode || p.accumulate)), "relu cannot be combined with residual/accumulate (accumulator-init fusion)");
     p.idesc = tc::make_idesc(F16, nt);
-    const bool generic = w.ups_u || e.bias_b || e.relu || e.out_f16;
+    const bool generic = w.ups_u || e.bias_b || e.relu || e.out_f16 || e.ln_gamma;
     const uint32_t esz = F16 ? 2u : 4u;
     p.w_stage_bytes = (uint32_t)(p.KC * nt) * esz;
     auto set_rows = [&](int MT) {
@@ -1256,7 +1306,7 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
 
     // ---- narrow layer with many tiles: persistent CTAs, resident weights, double-buffered TMEM
     const size_t w_all = (size_t)p.K * p.KC * nt * esz;
-    if (tune_env("BV2_TC_PERSIST", 1) && !e.skip_xform && !e.in_f16 && !e.out_f16 && p.nchunks == 1 && ntiles == 1 && w_all <= 64 * 1024 && nctas >= 2 * num_sms) {
+    if (tune_env("BV2_TC_PERSIST", 1) && !e.skip_xform && !e.in_f16 && !e.out_f16 && !e.ln_gamma && p.nchunks == 1 && ntiles == 1 && w_all <= 64 * 1024 && nctas >= 2 * num_sms) {
         p.nas = 3;
         const size_t wb = (w_all + 127) & ~(size_t)127;
         const size_t smem_p = wb + (size_t)p.nas * p.a_stage_bytes + (size_t)(3 * p.nas + 5) * 8 + 16;
@@ -1272,7 +1322,7 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
         return;
     }
     // ---- wide layer with at least one tile per SM: persistent CTAs, continuously streamed weights, double-buffered TMEM
-    if (tune_env("BV2_TC_PSTREAM", 1) && !e.skip_xform && !e.in_f16 && nctas >= num_sms && nt >= 64 && 2 * nt <= 512) {
+    if (tune_env("BV2_TC_PSTREAM", 1) && !e.skip_xform && !e.in_f16 && !e.ln_gamma && nctas >= num_sms && nt >= 64 && 2 * nt <= 512) {
         // MT = 2 (256-row tiles) when both accumulator pairs fit TMEM and there are enough 256-row tiles to fill the SMs
         int MT = (4 * nt <= 512 && (long long)cdiv(p.T, 256) * ntiles * p.B >= num_sms) ? 2 : 1;
         MT = tune_env("BV2_PSTREAM_MT", MT);
