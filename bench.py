@@ -319,6 +319,7 @@ def main():
                 raise RuntimeError("waveform batch exceeds the peer slab slot")
             o, attn, y_mask, aux = eng.infer_finish(B, T, F, d_nz, INFER_KW["noise_scale"], out_ptr=slab.wave_ptr(slot), want_attn=False)
             slab.publish(slot, B, F * HOP, ylen * HOP)
+            slab.release(slot)  # back-pressure protocol (the root consumes nothing in this loop: see step_e2e for the consuming variant)
         else:
             o, attn, y_mask, aux = eng.infer_finish(B, T, F, d_nz, INFER_KW["noise_scale"], want_attn=False)
             if exchange == "nccl":
@@ -333,6 +334,10 @@ def main():
             slot = step_no[0] % 2; step_no[0] += 1
             slab.wait(slot)
             slab.publish(slot, B, o.shape[-1], net.last_y_lengths * HOP, wave=o)
+            if rank == 0:  # the root really consumes every rank's waveform each step: one device copy out of the slab per rank
+                waves, counts = slab.collect(slot)
+                keep = [w.clone() for w in waves]  # noqa: F841
+            slab.release(slot)
         elif exchange == "nccl":
             gather_waveforms(o, torch.as_tensor(net.last_y_lengths, device=o.device) * HOP, dst=0)
         wav = o[:, 0].cpu()  # D2H of the step's result, as infer.py:315-318 does

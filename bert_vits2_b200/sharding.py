@@ -80,7 +80,10 @@ class PeerWaveSlab:
     pointer of `infer_finish`, so the waveform never exists in the producer's memory and no NCCL payload moves.
     `publish` adds the per-batch meta record (one small peer copy) and a 1-element all-reduce as the completion signal: when
     it completes on `dst`, every rank's stores of that slot are done.  `slots` >= 2 lets step i+1 be produced while
-    the root consumes step i.  With world_size 1 (or torch.distributed not initialised) everything stays local.
+    the root consumes step i.  Back-pressure: `release(slot)` (collective, every rank calls it once per publish of that slot, the
+    root AFTER it has copied what `collect` returned) posts a 1-element broadcast from the root; `wait(slot)` orders the next
+    producer after both the completion flag and that release, so a peer can never overwrite a slot the root is still reading.
+    With world_size 1 (or torch.distributed not initialised) everything stays local.
     """
 
     def __init__(self, device, b_cap: int, l_cap: int, dst: int = 0, slots: int = 2):
@@ -126,6 +129,8 @@ class PeerWaveSlab:
         self.base = int(p.value)
         self._flag = [torch.zeros(1, device=self.device) for _ in range(slots)]
         self._work = [None] * slots
+        self._rel = [torch.zeros(1, device=self.device) for _ in range(slots)]
+        self._rel_work = [None] * slots
         self._keep = [None] * slots
         self._meta_host = [torch.zeros(self.meta_len, dtype=torch.int64).pin_memory() for _ in range(slots)]
         self._meta_dev = [torch.zeros(self.meta_len, dtype=torch.int64, device=self.device) for _ in range(slots)]
@@ -176,15 +181,30 @@ class PeerWaveSlab:
             self._work[slot] = dist.all_reduce(self._flag[slot], async_op=True)
 
     def wait(self, slot: int):
-        """Order the current stream after every rank's stores into `slot` (no host block)."""
+        """Order the current stream after every rank's stores into `slot` and after the root's release of it (no host block)."""
         w = self._work[slot]
         if w is not None:
             w.wait()
             self._work[slot] = None
+        r = self._rel_work[slot]
+        if r is not None:
+            r.wait()
+            self._rel_work[slot] = None
+
+    def release(self, slot: int):
+        """Collective: the root declares `slot` consumed (call it after copying out what collect() returned -- the broadcast is
+        enqueued behind that work on the root's stream); producers only post the matching receive.  Views returned by collect()
+        for this slot are invalid afterwards."""
+        if self.world > 1:
+            self._rel_work[slot] = dist.broadcast(self._rel[slot], src=self.dst, async_op=True)
 
     def collect(self, slot: int) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
-        """Root only: per-rank waveform views [B_r,1,L_r] into the slab + sample counts (valid until the slot is reused)."""
-        self.wait(slot)
+        """Root only: per-rank waveform views [B_r,1,L_r] into the slab + sample counts, valid until release(slot): copy them out,
+        then call release(slot) on every rank."""
+        w = self._work[slot]
+        if w is not None:
+            w.wait()
+            self._work[slot] = None
         if not self.owner:
             return [], []
         torch.cuda.current_stream(self.device).synchronize()

@@ -611,3 +611,23 @@ def test_packed_weight_file_roundtrip(tmp_path, precision):
     other = "fp32" if precision != "fp32" else "tf32"
     with pytest.raises((Bv2Error, ValueError)):
         Engine(cfg, None, device="cuda:0", precision=other, packed_path=path)
+
+
+def test_two_engines_two_devices_one_process():
+    """the > 48 KB dynamic shared memory opt-in is a per-device function attribute -- one process driving one engine per
+    GPU must work on every device (set per engine in finalize, not once per process)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process (gpurun --gpus 2)")
+    from bert_vits2_b200.engine import Engine
+    cfg, sd = model_for(True, 0)
+    inp = synth.synthetic_inputs(cfg, [33], [0], seed=111)
+    nw, nz = synth.synthetic_noise(cfg, 1, 33, 1024, seed=112)
+    outs = []
+    for d in ("cuda:0", "cuda:1"):
+        eng = Engine(cfg, sd, device=d, precision="fp16")
+        with torch.cuda.device(d):
+            ylen, F = eng.infer_begin(inp["x"], inp["x_lengths"], inp["sid"], inp["tone"], inp["language"], inp["bert"], inp["ja_bert"], inp["en_bert"], nw, 0.9, 1.0, 0.5)
+            o, *_ = eng.infer_finish(1, 33, F, nz, 0.6)
+            torch.cuda.synchronize(d)
+        outs.append(o.cpu())
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
