@@ -747,14 +747,27 @@ void bv2_engine::run_text_encoder(int B, int T, const int64_t* x, const int64_t*
                                   const float* ja, const float* en, const int* lens, const float* gproj, Act& h, Act& stats,
                                   cudaStream_t s) {
     const int H = cfg.hidden_channels, D = cfg.bert_dim;
-    Act bc = ws.act(B, 3 * D, T);
-    const float* srcs[3] = {bert, ja, en};
-    for (int p = 0; p < 3; p++) {
-        k_plain_to_c4<<<grid_tcb(T, D, B), 128, 0, s>>>(srcs[p], D, (long long)D * T, T, bc.p, 3 * D, p * D, T, nullptr, 1.f);
-        BV2_CUDA(cudaGetLastError()); launches++;
-    }
     Act proj = ws.act(B, H, T);
-    if (!tok_conv(bert_proj, bc, proj, s, ConvArgs())) conv(bert_proj, bc, proj, s, ConvArgs(), 0, 0, true);
+    bool done = false;
+    if (tune_env("BV2_TOK_GEMM", 1) && H == 192) {
+        // BERT ingest: the three [B,1024,T] feature tensors are read in the layout get_text hands them over,
+        // one K = 3072 contraction on the cluster split-K kernel (no staging transposes, no intermediate tensor)
+        TokGemmArgs a{};
+        a.plain[0] = bert; a.plain[1] = ja; a.plain[2] = en; a.plain_C = D;
+        a.Cin_total = 3 * D; a.Cin = 3 * D; a.w = bert_proj.w; a.Cout_w = bert_proj.Cout_w; a.bias = bert_proj.b;
+        a.y = proj.p; a.Cout_total = H; a.T = T; a.B = B;
+        done = launch_tok_gemm(a, 1, H, s);
+        if (done) launches++;
+    }
+    if (!done) {
+        Act bc = ws.act(B, 3 * D, T);
+        const float* srcs[3] = {bert, ja, en};
+        for (int p = 0; p < 3; p++) {
+            k_plain_to_c4<<<grid_tcb(T, D, B), 128, 0, s>>>(srcs[p], D, (long long)D * T, T, bc.p, 3 * D, p * D, T, nullptr, 1.f);
+            BV2_CUDA(cudaGetLastError()); launches++;
+        }
+        conv(bert_proj, bc, proj, s, ConvArgs(), 0, 0, true);
+    }
     k_embed_sum<<<grid_tcb(T, H, B), 128, 0, s>>>(proj.p, reinterpret_cast<const long long*>(x), reinterpret_cast<const long long*>(tone),
                                                   reinterpret_cast<const long long*>(lang), emb, temb, lemb, h.p, H, T, lens,
                                                   std::sqrt((float)H), cfg.n_vocab, cfg.num_tones, cfg.num_languages);

@@ -184,6 +184,9 @@ struct TokGemmArgs {
     const float* res; int res_C_total;             // LayerNorm mode: y = LN(res + conv) (res: c4, 192 channels at offset 0)
     const float* gamma; const float* beta;         // null: no LayerNorm
     const int* lens;
+    // plain-layout input (BERT ingest, reference models.py:386-388): input channel ci comes from plain[ci / plain_C] laid out [B][plain_C][T]
+    // (the three 1024-channel feature tensors of get_text are consumed as the caller passes them: no c4 staging copies)
+    const float* plain[3]; int plain_C;
     int T, B, relu, in_mask, out_mask, mask_pre, ksplit;  // mask_pre: (conv + bias) * x_mask BEFORE the residual add (FFN: norm(x + ffn(x) * mask))
 };
 
@@ -229,7 +232,13 @@ __global__ void __launch_bounds__(128, 1) k_tok_gemm(TokGemmArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int len = a.lens ? a.lens[b] : a.T;
     // ---- stage the input tile [TTP][cin_cta] (zero padding, x * x_mask)
-    {
+    if (a.plain_C) {
+        for (int i = threadIdx.x; i < cin_cta * TTP; i += 128) {
+            const int ci = i / TTP, p = i - ci * TTP, t = t0 - PAD + p, cg_ = ci0 + ci;  // time fastest: each row segment is contiguous in HBM
+            const float* src = a.plain[cg_ / a.plain_C] + ((size_t)b * a.plain_C + cg_ % a.plain_C) * a.T;
+            sX[p * cin_cta + ci] = (t >= 0 && t < a.T && (!a.in_mask || t < len)) ? src[t] : 0.f;
+        }
+    } else {
         const float4* x4 = reinterpret_cast<const float4*>(a.x) + ((size_t)b * (a.Cin_total / 4) + (a.cin_off + ci0) / 4) * a.T;
         const int ncg = cin_cta / 4;
         for (int i = threadIdx.x; i < ncg * TTP; i += 128) {
