@@ -66,7 +66,11 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // kernel launched this way executes `griddepcontrol.wait` (pdl_wait()) before touching data produced upstream.
 template <typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    static const int pdl_env = getenv("BV2_PDL") ? atoi(getenv("BV2_PDL")) : 1;
+#ifdef BV2_TUNING
+    static const int pdl_env = getenv("BV2_PDL") ? atoi(getenv("BV2_PDL")) : 1;  // development builds only
+#else
+    const int pdl_env = 1;
+#endif
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
