@@ -290,6 +290,7 @@ struct bv2_engine {
     // ---------------------------------------------------------------- launch helpers
     int tc_out_tf32 = 0, tc_skip_xform = 0, tc_in_f16 = 0, tc_out_f16 = 0;  // one-shot modifiers for the next tensor-core conv() call
     const LnW* tc_ln = nullptr;                                               // one-shot: LayerNorm fused into the tail
+    int tc_gate = 0;                                                          // one-shot: WN gate fused into the tail
     void conv(const ConvW& cw, const Act& x, const Act& y, cudaStream_t s, ConvArgs extra = ConvArgs(), int cin_off = 0,
               int cout_off = 0, bool allow_tc = false) {
         if (allow_tc && cw.tc.w) {
@@ -301,6 +302,7 @@ struct bv2_engine {
             e.out_tf32 = tc_out_tf32; e.skip_xform = tc_skip_xform; e.in_f16 = tc_in_f16; e.out_f16 = tc_out_f16;
             BV2_CHECK(x.T == y.T && x.B == y.B, "conv T/B mismatch");
             if (tc_ln) { e.ln_gamma = tc_ln->g; e.ln_beta = tc_ln->b; }
+            e.gate = tc_gate; tc_gate = 0;
             tc_out_tf32 = 0; tc_skip_xform = 0; tc_in_f16 = 0; tc_out_f16 = 0; tc_ln = nullptr;
             tc_conv1d(cw.tc, cw.b, x, y, e, s, num_sms);
             launches++;
@@ -556,7 +558,34 @@ void bv2_engine::build_weights() {
         } else {
             const int L = c.wn_layers;
             fl.wn_g_off = append_gproj(f + ".enc.cond_layer", gw, gb, true);
+            if (tc == 2) {
+                // FP16 engine: the gate runs in the in_layer conv's tail, which needs tanh / sigmoid pre-activations of a channel in adjacent
+                // accumulator columns -> interleave the output rows (c, H + c) of every in_layer and of its slice of cond_layer
+                for (int l = 0; l < L; l++) {
+                    const size_t G = (size_t)c.gin_channels;
+                    std::vector<float> tw(gw.begin() + ((size_t)fl.wn_g_off + 2 * (size_t)H * l) * G, gw.begin() + ((size_t)fl.wn_g_off + 2 * (size_t)H * (l + 1)) * G);
+                    std::vector<float> tb(gb.begin() + fl.wn_g_off + 2 * H * l, gb.begin() + fl.wn_g_off + 2 * H * (l + 1));
+                    for (int ch = 0; ch < H; ch++)
+                        for (int hf = 0; hf < 2; hf++) {
+                            std::copy(tw.begin() + ((size_t)hf * H + ch) * G, tw.begin() + ((size_t)hf * H + ch + 1) * G, gw.begin() + ((size_t)fl.wn_g_off + 2 * (size_t)H * l + 2 * ch + hf) * G);
+                            gb[fl.wn_g_off + 2 * H * l + 2 * ch + hf] = tb[hf * H + ch];
+                        }
+                }
+            }
             for (int l = 0; l < L; l++) {
+                if (tc == 2) {
+                    std::vector<int64_t> shp;
+                    std::vector<float> w = fold_wn(f + ".enc.in_layers." + std::to_string(l), &shp), wi(w.size());
+                    const auto& b = W(f + ".enc.in_layers." + std::to_string(l) + ".bias").data;
+                    std::vector<float> bi(b.size());
+                    const size_t row = (size_t)shp[1] * shp[2];
+                    for (int ch = 0; ch < H; ch++)
+                        for (int hf = 0; hf < 2; hf++) {
+                            if (packing()) std::copy(w.begin() + ((size_t)hf * H + ch) * row, w.begin() + ((size_t)hf * H + ch + 1) * row, wi.begin() + ((size_t)2 * ch + hf) * row);
+                            bi[2 * ch + hf] = b[hf * H + ch];
+                        }
+                    fl.wn_in.push_back(make_conv(wi, 2 * H, H, (int)shp[2], &bi, tc, 128));
+                } else
                 fl.wn_in.push_back(conv_from(f + ".enc.in_layers." + std::to_string(l), true, tc, 128));
                 std::vector<int64_t> shp;
                 std::vector<float> w = fold_wn(f + ".enc.res_skip_layers." + std::to_string(l), &shp);
@@ -857,6 +886,22 @@ void bv2_engine::run_flow(Act z, const int* lens, const float* gproj, cudaStream
             const int L = cfg.wn_layers;
             Act xin = ws.act(B, 2 * H, F), acts = ws.act(B, H, F), out = ws.act(B, H, F);
             for (int l = 0; l < L; l++) {
+                if (flow_tc == 2) {
+                    // in_layer conv with the gate (tanh * sigmoid, speaker conditioning as per-batch bias) in its tail; acts is a 16-bit c8
+                    // tensor that the two 1x1 convs below consume as their operand image
+                    ConvArgs ag; ag.bias_b = gproj + fl.wn_g_off + 2 * H * l; ag.bias_b_stride = gproj_n;
+                    tc_gate = 1;
+                    conv(fl.wn_in[l], h, acts, s, ag, 0, 0, true);
+                    if (l < L - 1) {
+                        ConvArgs ar; ar.res_mode = 1; ar.res = h.p; ar.res_C_total = H; ar.out_mask = 1; ar.lens = lens;
+                        tc_in_f16 = 1;
+                        conv(fl.wn_res[l], acts, h, s, ar, 0, 0, true);
+                    }
+                    ConvArgs as; as.accumulate = l > 0 ? 1 : 0;
+                    tc_in_f16 = 1;
+                    conv(fl.wn_skip[l], acts, out, s, as, 0, 0, true);
+                    continue;
+                }
                 conv(fl.wn_in[l], h, xin, s, ConvArgs(), 0, 0, tcf);
                 k_wn_gate<<<grid_tcb(F, H, B), 128, 0, s>>>(xin.p, gproj + fl.wn_g_off + 2 * H * l, gproj_n, acts.p, H, F);
                 BV2_CUDA(cudaGetLastError()); launches++;

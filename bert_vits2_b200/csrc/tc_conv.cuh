@@ -57,6 +57,8 @@ struct TcEpi {
     int skip_xform = 0;  // TF32: input already TF32-exact, no activation / mask / padding needed (K == 1)
     int in_f16 = 0;      // FP16: x is a 16-bit c8 tensor [B][C/8][T][8] (the operand image itself: no prologue; K == 1)
     int out_f16 = 0;     // store y as a 16-bit c8 tensor
+    int gate = 0;        // WN gate fused into the tail (reference commons.py:98-105): columns (2c, 2c+1) hold the tanh / sigmoid pre-activations of
+                         // channel c (weights interleaved at load time); y gets tanh(a) * sigmoid(b) as a 16-bit c8 tensor with Cout/2 channels
     const float* ln_gamma = nullptr; const float* ln_beta = nullptr;  // LayerNorm over the Cout channels of each time step fused into the
                                                                       // tail (one N tile = all channels; combine with res for norm(x + conv))
 };
@@ -163,7 +165,7 @@ struct TcParams {
     uint32_t a_stage_bytes, a_op_off, w_stage_bytes, tmem_cols, idesc;
     float in_slope, out_scale;
     int accumulate, relu, res_mode, in_mask, out_mask, ups_u, ups_cout;
-    int out_tf32, skip_xform, in_f16, out_f16;
+    int out_tf32, skip_xform, in_f16, out_f16, gate;
     const float* ln_gamma; const float* ln_beta;
     // batched-GEMM extensions (TF32 attention GEMMs of the fp32/tf32 engines): grid z = b * zsplit + h
     int zsplit;                 // 0/1: z == batch
@@ -359,6 +361,20 @@ __device__ __forceinline__ void acc_tail_tile(const TcParams& p, uint32_t trow, 
         if (!ok) continue;
 #pragma unroll
         for (int h = 0; h < NG / 4; h++) {
+            if (GEN && p.gate) {
+                if (col0 + 16 * h < nt) {
+                    float a[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const float ta = __uint_as_float(v[h][2 * e]), sb = __uint_as_float(v[h][2 * e + 1]);
+                        a[e] = tanhf(ta) * (1.f / (1.f + expf(-sb))) * s;
+                    }
+                    uint4 o;
+                    o.x = pack_h2(a[0], a[1]); o.y = pack_h2(a[2], a[3]); o.z = pack_h2(a[4], a[5]); o.w = pack_h2(a[6], a[7]);
+                    yhp[(size_t)((coff + (n0 + col0 + 16 * h) / 2) / 8) * tstride + t] = o;
+                }
+                continue;
+            }
             if (GEN && p.out_f16) {
                 if (col0 + 16 * h < nt) {
                     float f[16];
@@ -1285,7 +1301,8 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     p.in_slope = e.in_slope; p.out_scale = e.out_scale; p.accumulate = e.accumulate; p.relu = e.relu; p.res_mode = e.res ? (e.res_mode ? e.res_mode : 1) : 0;
     p.in_mask = e.in_mask; p.out_mask = e.out_mask; p.ups_u = w.ups_u; p.ups_cout = w.ups_cout;
     p.out_tf32 = e.out_tf32; p.skip_xform = e.skip_xform; p.in_f16 = e.in_f16; p.out_f16 = e.out_f16;
-    p.ln_gamma = e.ln_gamma; p.ln_beta = e.ln_beta;
+    p.ln_gamma = e.ln_gamma; p.ln_beta = e.ln_beta; p.gate = e.gate;
+    if (e.gate) BV2_CHECK(F16 && !w.ups_u && !e.res && !e.accumulate && !e.relu && !e.out_f16 && !e.ln_gamma && e.cout_off % 8 == 0 && y.C % 8 == 0 && 2 * y.C >= w.Cout, "gate epilogue");
     if (e.ln_gamma) BV2_CHECK(e.ln_beta && ntiles == 1 && nt % 32 == 0 && !w.ups_u && !e.out_f16 && !e.out_tf32 && !e.relu && e.out_scale == 1.f && e.res_mode != 2 && e.cout_off % 4 == 0, "LayerNorm tail needs one N tile holding every channel");
     if (e.skip_xform) BV2_CHECK(!F16 && w.K == 1 && e.in_slope == 1.f && !e.in_mask, "skip_xform needs a TF32 plain 1x1 conv input");
     if (e.in_f16) BV2_CHECK(F16 && w.K == 1 && e.in_slope == 1.f && !e.in_mask && e.cin_off % 8 == 0 && x.C % 8 == 0, "in_f16 needs an FP16 plain 1x1 conv");
@@ -1293,7 +1310,7 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     if (p.in_mask || p.out_mask) BV2_CHECK(e.lens != nullptr, "mask needs lens");
     BV2_CHECK(!(p.relu && (p.res_mode || p.accumulate)), "relu cannot be combined with residual/accumulate (accumulator-init fusion)");
     p.idesc = tc::make_idesc(F16, nt);
-    const bool generic = w.ups_u || e.bias_b || e.relu || e.out_f16 || e.ln_gamma;
+    const bool generic = w.ups_u || e.bias_b || e.relu || e.out_f16 || e.ln_gamma || e.gate;
     const uint32_t esz = F16 ? 2u : 4u;
     p.w_stage_bytes = (uint32_t)(p.KC * nt) * esz;
     auto set_rows = [&](int MT) {
@@ -1306,7 +1323,7 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
 
     // ---- narrow layer with many tiles: persistent CTAs, resident weights, double-buffered TMEM
     const size_t w_all = (size_t)p.K * p.KC * nt * esz;
-    if (tune_env("BV2_TC_PERSIST", 1) && !e.skip_xform && !e.in_f16 && !e.out_f16 && !e.ln_gamma && p.nchunks == 1 && ntiles == 1 && w_all <= 64 * 1024 && nctas >= 2 * num_sms) {
+    if (tune_env("BV2_TC_PERSIST", 1) && !e.skip_xform && !e.in_f16 && !e.out_f16 && !e.ln_gamma && !e.gate && p.nchunks == 1 && ntiles == 1 && w_all <= 64 * 1024 && nctas >= 2 * num_sms) {
         p.nas = 3;
         const size_t wb = (w_all + 127) & ~(size_t)127;
         const size_t smem_p = wb + (size_t)p.nas * p.a_stage_bytes + (size_t)(3 * p.nas + 5) * 8 + 16;
