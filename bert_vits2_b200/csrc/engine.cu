@@ -411,6 +411,7 @@ struct bv2_engine {
     void check_device_error() {
         if (h_err && *reinterpret_cast<volatile int*>(h_err)) {
             *h_err = 0;
+            tc_clear_error();
             throw Error(BV2_ERR_INTERNAL, "device-side barrier timeout in a tcgen05 kernel (results of this call are invalid)");
         }
     }

@@ -176,8 +176,11 @@ struct TcParams {
     int w_ld, w_rows, w_c_total, w_c_off, w_c_zstride;
 };
 
-// Device-side error flag (pinned, host-mapped; set by bv2_engine::finalize on each device): a barrier timeout raises it
-// and lets the kernel run to completion instead of trapping the context ("never abort across the ABI").
+// Device-side error flags: a barrier timeout raises both and lets the kernel run to completion instead of trapping the context
+// ("never abort across the ABI").  g_tc_err_dev lives in device memory (what waiting threads poll: an L2 hit, never PCIe --
+// polling the host-mapped copy from every waiting thread slowed every kernel ~100x in the first round-2 run);
+// g_tc_err_flag points to a pinned, host-mapped int the host reads without a CUDA call (set by tc_init_device()).
+__device__ int g_tc_err_dev = 0;
 __device__ int* g_tc_err_flag = nullptr;
 
 namespace tc {
@@ -219,10 +222,11 @@ __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
         if (done) return true;
-        int* f = g_tc_err_flag;
-        if (f && *reinterpret_cast<volatile int*>(f)) return false;  // another wait already timed out: drain quickly
-        if ((it & 0x3f) == 0x3f) {
+        if ((it & 0xf) == 0xf) {
+            if (*reinterpret_cast<volatile int*>(&g_tc_err_dev)) return false;  // another wait already timed out: drain quickly
             if (clock64() - t0 > 4000000000ll) {
+                *reinterpret_cast<volatile int*>(&g_tc_err_dev) = 1;
+                int* f = g_tc_err_flag;
                 if (f) *reinterpret_cast<volatile int*>(f) = 1;
                 printf("bv2 tc_conv: mbarrier wait timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z,
                        threadIdx.x, bar, parity);
@@ -1260,6 +1264,10 @@ __global__ void __launch_bounds__(320, 2) k_tc_pair_persist(TcPairPParams p) {
 // ------------------------------------------------------------------------------------------------------------
 // The > 48 KB dynamic shared memory opt-in is a per-device (per-context) function attribute: call once per device before
 // the first launch there (bv2_engine::finalize does; probes call it themselves).
+inline void tc_clear_error() {
+    const int z = 0;
+    BV2_CUDA(cudaMemcpyToSymbol(g_tc_err_dev, &z, sizeof(z)));
+}
 // Returns the host view of this device's error flag (pinned, host-mapped; raised by a barrier timeout in any tcgen05 kernel).
 inline int* tc_init_device() {
     const int mx = 227 * 1024;
@@ -1277,6 +1285,7 @@ inline int* tc_init_device() {
     int* d = nullptr;
     BV2_CUDA(cudaHostGetDevicePointer(&d, h, 0));
     BV2_CUDA(cudaMemcpyToSymbol(g_tc_err_flag, &d, sizeof(d)));
+    tc_clear_error();
     return h;
 }
 

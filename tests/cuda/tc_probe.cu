@@ -22,7 +22,7 @@ static int g_timeouts = 0;
 static void free_all() {
     for (void* p : g_allocs) cudaFree(p);
     g_allocs.clear();
-    if (g_flag && *g_flag) { printf("  ^^^ BARRIER TIMEOUT raised by this case\n"); *g_flag = 0; g_timeouts++; }
+    if (g_flag && *g_flag) { printf("  ^^^ BARRIER TIMEOUT raised by this case\n"); *g_flag = 0; tc_clear_error(); g_timeouts++; }
 }
 static float rnd_op(float v, int f16) { return f16 ? f16_round_host(v) : tf32_rn_host(v); }
 
