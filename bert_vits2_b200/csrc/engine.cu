@@ -17,6 +17,7 @@
 #include "kernels_simt.cuh"
 #include "tc_conv.cuh"
 #include "tc_attn.cuh"
+#include "tc_gen.cuh"
 #include "kernels_tok.cuh"
 
 namespace bv2 {
@@ -122,6 +123,7 @@ struct bv2_engine {
         BV2_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
     }
     int flow_tc = 0;       // 0 SIMT fp32, 1 TF32 tcgen05, 2 FP16 tcgen05 + fused attention (finalize)
+    int use_g2 = 0;        // FP16 Generator on 16-bit activation tensors (tc_gen.cuh)
     AttnMnConv attn_mn;    // MN-major descriptor convention of the attention's V operand
     bool profiling = false;
     struct StageEv { cudaEvent_t a = nullptr, b = nullptr; bool rec = false; };
@@ -362,6 +364,7 @@ struct bv2_engine {
     void run_dp(Act h, const int* lens, const float* gproj, Act& dp_out, Act xg, Act d1, Act d2, cudaStream_t s);
     void run_flow(Act z, const int* lens, const float* gproj, cudaStream_t s);
     void run_generator(Act z, const int* lens_or_null, const float* gdec, int g_stride, float* o, cudaStream_t s);
+    void run_generator_g2(Act z, const int* lens_or_null, const float* gdec, int g_stride, float* o, cudaStream_t s);
     int* lens_to_device(const int64_t* x_lengths_dev, int B, Arena& ar, cudaStream_t s);
     // ids inside their tables, 1 <= lengths <= T (the reference raises IndexError / a shape error): device-side check into *err_dev
     void launch_validate(int B, int T, const int64_t* x, const int64_t* tone, const int64_t* lang, const int64_t* sid, const int64_t* lens,
@@ -534,6 +537,8 @@ void bv2_engine::build_weights() {
     const int gtc = c.generator_precision >= 2 ? 2 : tc;
     flow_tc = tc;
     if (tc == 2) tc_flow_attn_init_device();
+    use_g2 = (gtc == 2 && tune_env("BV2_G2", 1)) ? 1 : 0;
+    if (use_g2) g2_init_device();
     for (int i = 0; i < n; i++) {
         CouplingW& fl = flows[i];
         std::string f = "flow.flows." + std::to_string(2 * i);
@@ -603,7 +608,7 @@ void bv2_engine::build_weights() {
         }
     }
     // ---- dec (reference models.py:490-564)
-    conv_pre = conv_from("dec.conv_pre", false, gtc, 128);
+    conv_pre = conv_from("dec.conv_pre", false, gtc, 128, use_g2 ? g2_kc(I) : 0);
     goff_dec = append_gproj("dec.cond", gw, gb);
     int ch = c.upsample_initial_channel;
     for (int i = 0; i < c.n_ups; i++) {
@@ -617,7 +622,8 @@ void bv2_engine::build_weights() {
             for (int co = 0; co < u.Cout; co++)
                 for (int j = 0; j < u.K; j++) p[((size_t)ci * u.K + j) * u.Cout + co] = w[((size_t)ci * u.Cout + co) * u.K + j];
         u.w = upload(p); u.b = upload(W("dec.ups." + std::to_string(i) + ".bias").data);
-        if (gtc) u.tc = tc_pack_upsample(*this_uploader(), w, u.Cin, u.Cout, u.K, u.u, 32, gtc == 2, packing());
+        if (use_g2) u.tc = tc_pack_upsample(*this_uploader(), w, u.Cin, u.Cout, u.K, u.u, g2_kc(u.Cin), 1, packing(), 128);
+        else if (gtc) u.tc = tc_pack_upsample(*this_uploader(), w, u.Cin, u.Cout, u.K, u.u, 32, gtc == 2, packing());
         ups.push_back(u);
         ch /= 2;
         for (int j = 0; j < c.n_resblock_kernels; j++) {
@@ -625,8 +631,8 @@ void bv2_engine::build_weights() {
             std::string r = "dec.resblocks." + std::to_string(i * c.n_resblock_kernels + j);
             for (int d = 0; d < c.n_dilations; d++) {
                 rb.dil.push_back(c.resblock_dilation_sizes[j][d]);
-                const int kc = 32;  // persistent kernels hide latency with deep rings: fewer, larger chunks
-                const int nt0 = ch >= 256 ? tune_env("BV2_S0_NT", 0) : 0;  // tuning knob (stage 0 N tile)
+                const int kc = use_g2 ? g2_kc(ch) : 32;  // persistent kernels hide latency with deep rings: fewer, larger chunks
+                const int nt0 = use_g2 ? g2_nt(ch) : (ch >= 256 ? tune_env("BV2_S0_NT", 0) : 0);  // tuning knob (stage 0 N tile)
                 rb.c1.push_back(conv_from(r + ".convs1." + std::to_string(d), true, gtc, nt0, kc));
                 rb.c2.push_back(conv_from(r + ".convs2." + std::to_string(d), true, gtc, nt0, kc));
             }
@@ -930,6 +936,7 @@ void bv2_engine::run_flow(Act z, const int* lens, const float* gproj, cudaStream
 
 // Generator.forward (reference models.py:538-557) + ResBlock1.forward (modules.py:296-309)
 void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_stride, float* o, cudaStream_t s) {
+    if (use_g2) { run_generator_g2(z, lens, gdec, g_stride, o, s); return; }
     const int B = z.B, F = z.T;
     int ch = cfg.upsample_initial_channel, L = F;
     Act x = ws.act(B, ch, L);
@@ -1005,6 +1012,79 @@ void bv2_engine::run_generator(Act z, const int* lens, const float* gdec, int g_
     dim3 grid(cdiv(L, 256), B);
     k_conv_post_tanh<16, 7><<<grid, 256, 0, s>>>(x.p, conv_post_w, o, L, 0.01f);
     BV2_CUDA(cudaGetLastError()); launches++;
+}
+
+// Generator on 16-bit activation tensors (tc_gen.cuh): every tensor between conv_pre and conv_post is an H8 operand image
+// (f16(lrelu_0.1(x)), zero halos); 96 launches of ONE kernel (k_g2_conv) + conv_post.
+void bv2_engine::run_generator_g2(Act z, const int* lens, const float* gdec, int g_stride, float* o, cudaStream_t s) {
+    const int B = z.B, F = z.T, I = z.C;
+    auto h8 = [&](int C, int T) {
+        H8 t; t.B = B; t.C = C; t.T = T; t.Tp = G2_PADL + T + G2_PADR;
+        t.p = reinterpret_cast<uint4*>(ws.alloc(H8::bytes(B, C, T) / 4)) + G2_PADL;
+        return t;
+    };
+    auto zero_halos = [&](std::initializer_list<const H8*> ts) {
+        G2HaloList l{}; l.n = 0;
+        for (const H8* t : ts) { l.p[l.n] = t->p; l.cg_rows[l.n] = t->B * (t->C / 8); l.T[l.n] = t->T; l.Tp[l.n] = t->Tp; l.n++; }
+        int mx = 0; for (int i = 0; i < l.n; i++) mx = std::max(mx, l.cg_rows[i]);
+        k_g2_zero_halo<<<dim3(std::max(1, std::min(cdiv(mx * (G2_PADL + G2_PADR), 128), 64)), l.n), 128, 0, s>>>(l);
+        BV2_CUDA(cudaGetLastError()); launches++;
+    };
+    int ch = cfg.upsample_initial_channel, L = F;
+    H8 zh = h8(I, F), x = h8(ch, L);
+    zero_halos({&zh, &x});
+    k_c4_to_h8<<<dim3(cdiv(F, 128), I / 8, B), 128, 0, s>>>(reinterpret_cast<const float4*>(z.p), zh.p, I, F, zh.Tp, lens);
+    BV2_CUDA(cudaGetLastError()); launches++;
+    {
+        G2Epi e; e.bias_b = gdec; e.bias_b_stride = g_stride;
+        g2_conv(conv_pre.tc, conv_pre.b, zh, x, e, s, num_sms); launches++;
+    }
+    const int nk = cfg.n_resblock_kernels, nd = cfg.n_dilations;
+    BV2_CHECK(nk <= 4, "at most 4 resblock kernels");
+    ensure_side_streams();
+    for (int i = 0; i < cfg.n_ups; i++) {
+        const UpW& u = ups[i];
+        const int Lo = L * u.u;
+        H8 S = h8(u.Cout, Lo);
+        const size_t mark_after_S = ws.used();
+        H8 xu = h8(u.Cout, Lo);
+        H8 xt[4], ra[4], rb[4];
+        for (int j = 0; j < nk; j++) { xt[j] = h8(u.Cout, Lo); ra[j] = h8(u.Cout, Lo); rb[j] = h8(u.Cout, Lo); }
+        {
+            G2HaloList l{}; l.n = 0;
+            auto add = [&](const H8& t) { l.p[l.n] = t.p; l.cg_rows[l.n] = t.B * (t.C / 8); l.T[l.n] = t.T; l.Tp[l.n] = t.Tp; l.n++; };
+            add(S); add(xu);
+            for (int j = 0; j < nk; j++) { add(xt[j]); add(ra[j]); add(rb[j]); }
+            k_g2_zero_halo<<<dim3(std::max(1, std::min(cdiv(l.cg_rows[0] * (G2_PADL + G2_PADR), 128), 64)), l.n), 128, 0, s>>>(l);
+            BV2_CUDA(cudaGetLastError()); launches++;
+        }
+        g2_conv(u.tc, u.b, x, xu, G2Epi(), s, num_sms); launches++;
+        BV2_CUDA(cudaEventRecord(ev_fork, s));
+        for (int j = 0; j < nk; j++) {
+            cudaStream_t sj = j == 0 ? s : side[j];
+            if (j) BV2_CUDA(cudaStreamWaitEvent(sj, ev_fork, 0));
+            const ResBlockW& R = resblocks[i * nk + j];
+            H8 cur = xu;
+            for (int d = 0; d < nd; d++) {
+                const bool last = d == nd - 1;
+                H8 nxt = last ? S : (cur.p == ra[j].p ? rb[j] : ra[j]);
+                G2Epi e1; e1.dil = R.dil[d];
+                g2_conv(R.c1[d].tc, R.c1[d].b, cur, xt[j], e1, sj, num_sms); launches++;
+                if (last && j > 0) BV2_CUDA(cudaStreamWaitEvent(sj, ev_rb[j - 1], 0));  // S += ... after resblock j-1 wrote S
+                G2Epi e2; e2.res = &cur;
+                if (last) { e2.accumulate = j > 0; e2.out_scale = (j == nk - 1) ? 1.f / nk : 1.f; }
+                g2_conv(R.c2[d].tc, R.c2[d].b, xt[j], nxt, e2, sj, num_sms); launches++;
+                cur = nxt;
+            }
+            BV2_CUDA(cudaEventRecord(ev_rb[j], sj));
+        }
+        if (nk > 1) BV2_CUDA(cudaStreamWaitEvent(s, ev_rb[nk - 1], 0));
+        x = S; L = Lo; ch = u.Cout;
+        ws.release(mark_after_S);
+    }
+    BV2_CHECK(ch == 16, "conv_post kernel instantiated for 16 input channels");
+    launch_pdl(k_conv_post_tanh_h8<16, 7>, dim3(cdiv(L, 256), B), dim3(256), 0, s, (const uint4*)x.p, x.Tp, (const float*)conv_post_w, o, L);
+    launches++;
 }
 
 // ================================================================================================

@@ -136,7 +136,7 @@ inline TcConvW tc_pack_weights(std::function<float*(const std::vector<float>&)>&
 // -> an ordinary conv over input-rate time with Kp taps (union of the per-phase offsets), N = u*Cout columns ordered
 // (r, co), structural zeros where a phase does not use a tap.  wT: [Cin][Cout][K] (weight-norm folded).
 inline TcConvW tc_pack_upsample(std::function<float*(const std::vector<float>&)>& up, const std::vector<float>& wT, int Cin, int Cout, int K, int u,
-                                int kc = 0, int f16 = 0, bool fill = true) {
+                                int kc = 0, int f16 = 0, bool fill = true, int nt_max = 256) {
     const int p = (K - u) / 2, taps = K / u;
     int omin = 1 << 30, omax = -(1 << 30);
     for (int r = 0; r < u; r++)
@@ -151,7 +151,7 @@ inline TcConvW tc_pack_upsample(std::function<float*(const std::vector<float>&)>
                 for (int ci = 0; ci < Cin; ci++)
                     w[(((size_t)(r * Cout + co)) * Cin + ci) * Kp + tap] = wT[((size_t)ci * Cout + co) * K + j];
         }
-    int nt = std::min(u * Cout, 256);
+    int nt = std::min(u * Cout, nt_max);
     TcConvW t = tc_pack_weights(up, w, u * Cout, Cin, Kp, nt, f16, kc, fill);
     t.ups_u = u; t.ups_cout = Cout;
     return t;

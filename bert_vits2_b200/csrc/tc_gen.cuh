@@ -1,0 +1,369 @@
+// "G2": the HiFi-GAN Generator (reference models.py:538-557, modules.py:296-309) on 16-bit activation tensors.
+//
+// Round-2 ncu of the fp32-activation conv family (tc_conv.cuh) showed the MRF convs neither HBM- nor tensor-bound: every staged
+// fp32 tile went through a generic-proxy prologue (lrelu + fp32 -> f16 in shared memory, 6 B of smem per element) before the
+// MMAs could start, which left room for only ~40 KB of weight stages in flight per SM (Little's law against the ~1.2 us L2
+// latency: ~5 TB/s of weight streaming over the whole chip, a third of what the tensor pipe consumes at N = 128).
+//
+// Here every Generator activation lives in HBM as the MMA operand image itself:
+//   H8 tensor  [B][C/8][Tp][8 halves], value = f16(lrelu_0.1(x)), Tp = G2_PADL + T + G2_PADR rows with ZERO halo rows
+//   * every consumer of a Generator activation applies lrelu(., 0.1) first (ups, convs1, convs2), so the producer's tail
+//     applies it once; the one other use, the residual `x + conv2(..)`, recovers x = a >= 0 ? a : 10 a  (lrelu is invertible);
+//     conv_post's lrelu(., 0.01) is a >= 0 ? a : 0.1 a.  CPU simulation of the f16 storage on the oracle: waveform RMS error
+//     7.7e-5 (f16 operands, fp32 activations) -> 1.0e-4 (f16 storage), bar 1e-3.
+//   * a [KC/8][R rows][16 B] window of such a tensor is the K-major no-swizzle UMMA operand tile: the TMA producer copies it
+//     straight into the ring (one cp.async.bulk per channel group), the MMA warp consumes it -- no prologue warps, 2 B of smem
+//     per element, and conv zero padding is the tensor's own zero halo (no per-tile fill, no predicates);
+//   * tap j of a dilated conv is the same staged tile with the descriptor start advanced by j*dil rows (as in tc_conv.cuh).
+//
+// One kernel, k_g2_conv: a CTA owns a super-tile of NG x MG m-tiles (128 rows each) x nt <= 128 columns, NG*MG*nt <= 512 TMEM
+// columns (the whole accumulator of the super-tile lives in TMEM), so each weight stage (chunk c, tap j) feeds MG*KC/16 MMAs:
+//   streamed weights (C >= 64): NG = 1, MG = 2..8 -- weights cross L2->SM once per MG*128 rows, ring of up to 16 stages;
+//   resident weights (C <= 32): all taps loaded once, the M-groups pipeline through the activation ring and the tail of
+//   group g overlaps the MMAs of group g+1.
+// 384 threads: warp 0 activation producer, warp 1 MMA issuer, warp 2 weight producer, warp 3 TMEM allocator,
+// warps 4-11 epilogue (TMEM -> +bias [+ residual] [+ MRF running sum] -> lrelu -> f16 -> 16-byte coalesced stores).
+#pragma once
+#include "tc_conv.cuh"
+
+namespace bv2 {
+
+constexpr int G2_PADL = 32, G2_PADR = 32;  // zero halo rows before t = 0 / after t = T-1 (max conv padding: (11-1)/2*5 = 25)
+
+// 16-bit Generator activation; p points at row t = 0 of (b = 0, channel group 0); rows [-G2_PADL, T + G2_PADR) are allocated.
+struct H8 {
+    uint4* p = nullptr;
+    int B = 0, C = 0, T = 0, Tp = 0;
+    static size_t bytes(int B, int C, int T) { return (size_t)B * (C / 8) * (size_t)(G2_PADL + T + G2_PADR) * 16; }
+};
+
+struct G2Params {
+    const uint4* x; uint4* y; const uint4* res; const void* w; const float* bias; const float* bias_b;
+    int x_cg, x_Tp, y_cg, y_Tp, res_cg, res_Tp, bias_b_stride;
+    int T, K, dil, pad, nt, KC, nchunks, NG, MG, R, nas, nws, resident;
+    uint32_t a_stage_bytes, w_stage_bytes, tmem_cols, idesc;
+    int residual, accumulate, ups_u, ups_cout;
+    float out_scale;
+};
+
+namespace tc {
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; e++) { const float2 t = __half22float2(h[e]); f[2 * e] = t.x; f[2 * e + 1] = t.y; }
+}
+__device__ __forceinline__ float unlrelu10(float a) { return a >= 0.f ? a : a * 10.f; }
+}  // namespace tc
+
+__global__ void __launch_bounds__(384, 1) k_g2_conv(G2Params p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NAS = p.nas, NWS = p.nws, NG = p.NG, MG = p.MG, NCH = p.nchunks, nt = p.nt, R = p.R;
+    const int t0 = blockIdx.x * NG * MG * 128, ntile = blockIdx.y, n0 = ntile * nt, b = blockIdx.z;
+    uint8_t* sA = smem;
+    uint8_t* sW = smem + (size_t)NAS * p.a_stage_bytes;
+    const int nwst = p.resident ? NCH * p.K : NWS;  // weight stages held in shared memory
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)nwst * p.w_stage_bytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+    // barrier map: a_full[NAS], a_empty[NAS], w_full[NWS], w_empty[NWS], acc_full[NG]
+    const int B_AFULL = 0, B_AEMPTY = NAS, B_WFULL = 2 * NAS, B_WEMPTY = 2 * NAS + NWS, B_ACC = 2 * NAS + 2 * NWS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACC + NG);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NAS; i++) { mbar_init(BAR(B_AFULL + i), 1); mbar_init(BAR(B_AEMPTY + i), 1); }
+        for (int i = 0; i < NWS; i++) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
+        for (int i = 0; i < NG; i++) mbar_init(BAR(B_ACC + i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int ncg = p.KC / 8;  // 16-byte channel groups per chunk
+
+    if (warp == 0) {
+        // ===== activation producer (reads the upstream kernel's output: PDL wait first)
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        const int steps = NG * NCH;
+        for (int s = 0; s < steps; s++) {
+            const int g = s / NCH, c = s - g * NCH, sa = s % NAS;
+            const int row0 = t0 + g * MG * 128 - p.pad;
+            const int nrows = max(0, min(R, p.T + G2_PADR - row0));  // never read past the tensor's halo; rows beyond feed discarded outputs only
+            if (lane == 0) {
+                mbar_wait(BAR(B_AEMPTY + sa), ((s / NAS) & 1) ^ 1);
+                mbar_expect_tx(BAR(B_AFULL + sa), (uint32_t)nrows * 16u * (uint32_t)ncg);
+            }
+            __syncwarp();
+            if (lane < ncg && nrows > 0) {
+                const uint4* src = p.x + ((size_t)b * p.x_cg + (size_t)c * ncg + lane) * p.x_Tp + row0;
+                bulk_g2s(smem_u32(sA + (size_t)sa * p.a_stage_bytes) + (uint32_t)lane * (uint32_t)R * 16u, src, (uint32_t)nrows * 16u, BAR(B_AFULL + sa));
+            }
+        }
+    } else if (warp == 2) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (lane == 0) {
+            // ===== weight producer (weights do not depend on the upstream kernel: no PDL wait)
+            const uint8_t* wt = reinterpret_cast<const uint8_t*>(p.w) + (size_t)ntile * NCH * p.K * p.w_stage_bytes;
+            if (p.resident) {
+                const uint32_t total = (uint32_t)(NCH * p.K) * p.w_stage_bytes;
+                mbar_expect_tx(BAR(B_WFULL), total);
+                for (uint32_t off = 0; off < total; off += 32768u)
+                    bulk_g2s(smem_u32(sW) + off, wt + off, min(32768u, total - off), BAR(B_WFULL));
+            } else {
+                int wi = 0;
+                for (int g = 0; g < NG; g++)
+                    for (int cj = 0; cj < NCH * p.K; cj++, wi++) {
+                        const int sw = wi % NWS;
+                        mbar_wait(BAR(B_WEMPTY + sw), ((wi / NWS) & 1) ^ 1);
+                        mbar_expect_tx(BAR(B_WFULL + sw), p.w_stage_bytes);
+                        bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), wt + (size_t)cj * p.w_stage_bytes, p.w_stage_bytes, BAR(B_WFULL + sw));
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (lane == 0) {
+            // ===== MMA issuer
+            const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)nt * 16u;
+            const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R), b_kstep = (uint64_t)(2u * (uint32_t)nt);
+            const int nk = p.KC / 16;
+            if (p.resident) { mbar_wait(BAR(B_WFULL), 0); fence_after(); }
+            int wi = 0, s = 0;
+            for (int g = 0; g < NG; g++) {
+                for (int c = 0; c < NCH; c++, s++) {
+                    const int sa = s % NAS;
+                    mbar_wait(BAR(B_AFULL + sa), (s / NAS) & 1);
+                    fence_after();
+                    const uint64_t a_desc0 = make_desc(smem_u32(sA + (size_t)sa * p.a_stage_bytes), a_lbo, 128u);
+                    for (int j = 0; j < p.K; j++, wi++) {
+                        uint64_t bd0;
+                        int sw = 0;
+                        if (p.resident) {
+                            bd0 = make_desc(smem_u32(sW + (size_t)(c * p.K + j) * p.w_stage_bytes), b_lbo, 128u);
+                        } else {
+                            sw = wi % NWS;
+                            mbar_wait(BAR(B_WFULL + sw), (wi / NWS) & 1);
+                            fence_after();
+                            bd0 = make_desc(smem_u32(sW + (size_t)sw * p.w_stage_bytes), b_lbo, 128u);
+                        }
+                        const uint32_t acc0 = (c | j) ? 1u : 0u;  // the very first MMA of an accumulator overwrites it
+                        for (int mt = 0; mt < MG; mt++) {
+                            uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(mt * 128 + j * p.dil), bd = bd0;
+                            const uint32_t d = tmem + (uint32_t)((g * MG + mt) * nt);
+                            umma<1>(d, ad, bd, p.idesc, acc0);
+                            for (int kk = 1; kk < nk; kk++) { ad += a_kstep; bd += b_kstep; umma<1>(d, ad, bd, p.idesc, 1u); }
+                        }
+                        if (!p.resident) umma_commit(BAR(B_WEMPTY + sw));
+                    }
+                    umma_commit(BAR(B_AEMPTY + sa));
+                }
+                umma_commit(BAR(B_ACC + g));
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: warp e = 0..7; TMEM lane quarter q = warp & 3, the two warps of a quarter take alternate m-tiles
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        const int e = warp - 4, q = warp & 3, half = e >> 2;
+        const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
+        const int u = p.ups_u;
+        for (int g = 0; g < NG; g++) {
+            mbar_wait(BAR(B_ACC + g), 0);
+            fence_after();
+            for (int mt = half; mt < MG; mt += 2) {
+                const int t = t0 + (g * MG + mt) * 128 + q * 32 + lane;
+                const bool ok = t < p.T;
+                const uint32_t tcol = trow + (uint32_t)((g * MG + mt) * nt);
+                for (int col0 = 0; col0 < nt; col0 += 32) {
+                    uint32_t v[32];
+                    const bool wide = col0 + 32 <= nt;
+                    if (wide) tmem_ld32(tcol + (uint32_t)col0, v); else tmem_ld16(tcol + (uint32_t)col0, v);
+                    tmem_wait_ld();
+                    if (!ok) continue;
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        if (h < 2 || wide) {
+                            const int n = n0 + col0 + 8 * h;  // first of 8 consecutive output columns
+                            float f[8];
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + (u ? n % p.ups_cout : n)));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + (u ? n % p.ups_cout : n) + 4));
+                            f[0] = __uint_as_float(v[8 * h]) + b0.x; f[1] = __uint_as_float(v[8 * h + 1]) + b0.y;
+                            f[2] = __uint_as_float(v[8 * h + 2]) + b0.z; f[3] = __uint_as_float(v[8 * h + 3]) + b0.w;
+                            f[4] = __uint_as_float(v[8 * h + 4]) + b1.x; f[5] = __uint_as_float(v[8 * h + 5]) + b1.y;
+                            f[6] = __uint_as_float(v[8 * h + 6]) + b1.z; f[7] = __uint_as_float(v[8 * h + 7]) + b1.w;
+                            if (p.bias_b) {
+                                const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + n));
+                                const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + n + 4));
+                                f[0] += c0.x; f[1] += c0.y; f[2] += c0.z; f[3] += c0.w; f[4] += c1.x; f[5] += c1.y; f[6] += c1.z; f[7] += c1.w;
+                            }
+                            size_t yo;
+                            if (u) { const int r = n / p.ups_cout, co = n - r * p.ups_cout; yo = ((size_t)b * p.y_cg + co / 8) * p.y_Tp + (size_t)t * u + r; }
+                            else yo = ((size_t)b * p.y_cg + n / 8) * p.y_Tp + t;
+                            if (p.residual) {
+                                float r8[8];
+                                unpack8(p.res[((size_t)b * p.res_cg + n / 8) * p.res_Tp + t], r8);
+#pragma unroll
+                                for (int k = 0; k < 8; k++) f[k] += unlrelu10(r8[k]);
+                            }
+                            if (p.accumulate) {
+                                float a8[8];
+                                unpack8(p.y[yo], a8);
+#pragma unroll
+                                for (int k = 0; k < 8; k++) f[k] += unlrelu10(a8[k]);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 8; k++) f[k] = lrelu(f[k] * p.out_scale, 0.1f);
+                            uint4 o;
+                            o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+                            p.y[yo] = o;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 3) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+// ---- halo zeroing: the zero rows around every H8 tensor are the conv padding of its consumers.  One launch per Generator stage
+// covers all tensors of the stage (the workspace is a bump arena: a stage's buffers alias whatever the previous call left there).
+struct G2HaloList { uint4* p[16]; int cg_rows[16]; int T[16]; int Tp[16]; int n; };  // cg_rows = B * C/8 channel-group runs
+__global__ void __launch_bounds__(128) k_g2_zero_halo(G2HaloList l) {
+    const int i = blockIdx.y;
+    if (i >= l.n) return;
+    const int per = G2_PADL + G2_PADR;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < l.cg_rows[i] * per; idx += gridDim.x * blockDim.x) {
+        const int run = idx / per, r = idx - run * per;
+        const int t = r < G2_PADL ? r - G2_PADL : l.T[i] + (r - G2_PADL);
+        l.p[i][(size_t)run * l.Tp[i] + t] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// fp32 c4 [B][C/4][T][4] (rows t >= lens[b] read as zero) -> raw f16 H8 (no activation): the Generator's input z * y_mask
+__global__ void __launch_bounds__(128) k_c4_to_h8(const float4* __restrict__ x, uint4* __restrict__ y, int C, int T, int Tp, const int* __restrict__ lens) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y, b = blockIdx.z;
+    if (t >= T) return;
+    const bool in = !lens || t < lens[b];
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+    if (in) { a = x[((size_t)b * (C / 4) + 2 * g) * T + t]; c = x[((size_t)b * (C / 4) + 2 * g + 1) * T + t]; }
+    uint4 o;
+    o.x = tc::pack_h2(a.x, a.y); o.y = tc::pack_h2(a.z, a.w); o.z = tc::pack_h2(c.x, c.y); o.w = tc::pack_h2(c.z, c.w);
+    y[((size_t)b * (C / 8) + g) * Tp + t] = o;
+}
+
+// conv_post (C -> 1, K taps, no bias) + tanh on an H8 input (reference models.py:553-555: F.leaky_relu default slope 0.01,
+// recovered from the stored lrelu_0.1 value as a >= 0 ? a : 0.1 a); the zero halo supplies the conv padding.
+template <int C, int K>
+__global__ void __launch_bounds__(256) k_conv_post_tanh_h8(const uint4* __restrict__ x, int Tp, const float* __restrict__ w, float* __restrict__ y, int T) {
+    __shared__ float sw[C * K];
+    for (int i = threadIdx.x; i < C * K; i += blockDim.x) sw[i] = w[i];  // [C][K]
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (t >= T) return;
+    float acc = 0.f;
+#pragma unroll
+    for (int g = 0; g < C / 8; g++) {
+        const uint4* xr = x + ((size_t)b * (C / 8) + g) * Tp + t - K / 2;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            float f[8];
+            tc::unpack8(xr[j], f);
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc = fmaf(f[k] >= 0.f ? f[k] : 0.1f * f[k], sw[(g * 8 + k) * K + j], acc);
+        }
+    }
+    y[(size_t)b * T + t] = tanhf(acc);
+}
+
+inline void g2_init_device() {
+    BV2_CUDA(cudaFuncSetAttribute(k_g2_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+}
+
+struct G2Epi {
+    const H8* res = nullptr;  // y = lrelu(conv + bias + unlrelu(res))
+    int accumulate = 0;       // ... + unlrelu(y_old)   (MRF running sum)
+    float out_scale = 1.f;
+    const float* bias_b = nullptr; int bias_b_stride = 0;  // per-batch bias (speaker conditioning of conv_pre)
+    int dil = 1;
+    int st_override = 0;      // probes: force the super-tile size (m-tiles per CTA)
+};
+
+// Static part of the plan (fixed at weight-pack time): N tile and K chunk for a conv with `cols` output columns.
+inline int g2_nt(int cols) { int nt = std::min(cols, 128); while (cols % nt || nt % 16) nt -= 16; return nt; }
+inline int g2_kc(int Cin) { return Cin >= 128 ? 32 : 16; }
+
+// x: H8 input, y: H8 output (T_out = T * max(1, ups_u)).  w packed by tc_pack_weights / tc_pack_upsample with f16 = 1, nt = g2_nt, kc = g2_kc.
+inline void g2_conv(const TcConvW& w, const float* bias, const H8& x, const H8& y, const G2Epi& e, cudaStream_t st, int num_sms) {
+    const int u = w.ups_u ? w.ups_u : 1;
+    BV2_CHECK(w.w && w.f16 && bias && x.B == y.B && y.T == x.T * u && x.C == w.Cin && (w.ups_u ? y.C == w.ups_cout : y.C == w.Cout), "g2_conv shapes");
+    BV2_CHECK(w.nt <= 128 && w.KC % 16 == 0 && w.KC <= 256 && x.C % 8 == 0 && y.C % 8 == 0, "g2_conv tiling");
+    G2Params p{};
+    p.x = x.p; p.y = y.p; p.w = w.w; p.bias = bias; p.bias_b = e.bias_b; p.bias_b_stride = e.bias_b_stride;
+    p.x_cg = x.C / 8; p.x_Tp = x.Tp; p.y_cg = y.C / 8; p.y_Tp = y.Tp;
+    if (e.res) { BV2_CHECK(!w.ups_u && e.res->C == y.C && e.res->T == y.T && e.res->B == y.B, "g2_conv residual"); p.res = e.res->p; p.res_cg = e.res->C / 8; p.res_Tp = e.res->Tp; p.residual = 1; }
+    p.accumulate = e.accumulate; p.out_scale = e.out_scale; p.ups_u = w.ups_u; p.ups_cout = w.ups_cout;
+    if (w.ups_u) BV2_CHECK(w.ups_cout % 8 == 0 && !e.accumulate, "g2_conv ups");
+    p.T = x.T; p.K = w.K; p.dil = e.dil; p.pad = (w.K - 1) / 2 * e.dil;
+    BV2_CHECK(p.pad <= G2_PADL && p.pad <= G2_PADR, "g2_conv padding exceeds the tensor halo");
+    p.nt = w.nt; p.KC = w.KC; p.nchunks = w.nchunks;
+    const int ntiles = w.Cout / w.nt, halo = (w.K - 1) * e.dil;
+    p.w_stage_bytes = (uint32_t)(w.KC * w.nt * 2);
+    p.idesc = tc::make_idesc(1, w.nt);
+    const int mtiles = cdiv(x.T, 128), mgmax = 512 / w.nt;
+    const size_t budget = 220 * 1024;
+    const size_t w_all = (size_t)w.nchunks * w.K * p.w_stage_bytes;
+    p.resident = w_all <= 48 * 1024 && ntiles == 1;
+    // ---- super-tile (m-tiles per CTA): as few CTAs as fill the SMs once; streamed weights want >= 2 m-tiles per weight pass
+    int ST = (int)std::min<long long>(mgmax, std::max<long long>(1, ((long long)mtiles * ntiles * x.B + num_sms - 1) / num_sms));
+    if (!p.resident && ST < 2 && mgmax >= 2 && mtiles >= 2 && w_all > 256 * 1024) ST = 2;
+    if (e.st_override) ST = std::min(e.st_override, mgmax);
+    ST = std::min(ST, mtiles);
+    int NG = 1, MG = ST;
+    auto a_bytes = [&](int mg) { return (size_t)(w.KC / 8) * (size_t)(mg * 128 + halo) * 16; };
+    if (p.resident) {
+        // pipeline the m-groups through the activation ring: prefer 4 groups, then 2 (whatever wastes the fewest m-tiles)
+        int best_ng = 1, best_mg = ST; long long best_cost = -1;
+        for (int ng : {4, 2, 1}) {
+            const int mg = cdiv(ST, ng);
+            if (ng * mg > mgmax || ng > ST) continue;
+            const long long ctas = (long long)cdiv(mtiles, ng * mg) * x.B;
+            const long long waves = (ctas + num_sms - 1) / num_sms;
+            const long long cost = waves * ng * mg;  // m-tile slots per SM
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_ng = ng; best_mg = mg; }
+        }
+        NG = best_ng; MG = best_mg;
+    } else {
+        while (MG > 1 && 2 * a_bytes(MG) + 4 * (size_t)p.w_stage_bytes + 1024 > budget) MG--;
+    }
+    p.NG = NG; p.MG = MG; p.R = MG * 128 + halo;
+    p.a_stage_bytes = (uint32_t)a_bytes(MG);
+    const int a_steps = NG * w.nchunks;
+    size_t wres = p.resident ? w_all : 0;
+    int nas = std::min(a_steps, p.resident ? 4 : 3);
+    while (nas > 2 && (size_t)nas * p.a_stage_bytes + wres + (p.resident ? 0 : 8 * (size_t)p.w_stage_bytes) + 1024 > budget) nas--;
+    nas = std::max(1, nas);
+    p.nas = nas;
+    if (p.resident) p.nws = 1;
+    else p.nws = (int)std::max<size_t>(2, std::min<size_t>(16, (budget - (size_t)nas * p.a_stage_bytes - 1024) / p.w_stage_bytes));
+    if (!p.resident) p.nws = std::min(p.nws, NG * w.nchunks * w.K);
+    uint32_t cols = 32; while ((int)cols < NG * MG * w.nt) cols <<= 1;
+    p.tmem_cols = cols;
+    const size_t smem = (size_t)nas * p.a_stage_bytes + (p.resident ? w_all : (size_t)p.nws * p.w_stage_bytes) + (size_t)(2 * nas + 2 * p.nws + NG + 2) * 8 + 16;
+    BV2_CHECK(smem <= 227 * 1024 && cols <= 512, "g2_conv shared memory / TMEM");
+    dim3 grid(cdiv(mtiles, NG * MG), ntiles, x.B);
+    launch_pdl(k_g2_conv, grid, dim3(384), smem, st, p);
+}
+
+}  // namespace bv2
