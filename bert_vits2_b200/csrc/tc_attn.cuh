@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && NT > 0) {
+        if (NT > 0) {  // all 32 lanes run the issue loop convergently; elect_one() guards the MMAs / commits
             mbar_wait(BAR(B_QFULL), 0);
             auto qk = [&](int s) {  // S[s&1] = Q . K_tile^T
                 const int st = s & 1;
@@ -132,9 +132,9 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                 uint64_t bd = make_desc(smem_u32(sK) + (uint32_t)st * KB, (uint32_t)KT * 16u, 128u);
                 const uint32_t d = tmem + (uint32_t)(st * KT);
 #pragma unroll
-                for (int kk = 0; kk < DK / 16; kk++, ad += 2u * 128u, bd += 2u * KT) umma<1>(d, ad, bd, p.idesc_qk, kk ? 1u : 0u);
-                umma_commit(BAR(B_KEMPTY + st));
-                umma_commit(BAR(B_SFULL + st));
+                for (int kk = 0; kk < DK / 16; kk++, ad += 2u * 128u, bd += 2u * KT) umma_e<1>(d, ad, bd, p.idesc_qk, kk ? 1u : 0u);
+                umma_commit_e(BAR(B_KEMPTY + st));
+                umma_commit_e(BAR(B_SFULL + st));
             };
             qk(0);
             for (int s = 0; s < 2 * NT; s++) {
@@ -148,10 +148,10 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                     uint64_t bd = make_desc(smem_u32(sV) + (uint32_t)pb * KB, p.v_lbo, p.v_sbo);
                     const uint32_t d = tmem + 2u * KT;
 #pragma unroll
-                    for (int kk = 0; kk < KT / 16; kk++, ad += 2u * 128u, bd += 16u) umma<1>(d, ad, bd, p.idesc_pv, (j | kk) ? 1u : 0u);
-                    umma_commit(BAR(B_PEMPTY + pb));
-                    umma_commit(BAR(B_VEMPTY + pb));
-                    if (j == NT - 1) umma_commit(BAR(B_OFULL));
+                    for (int kk = 0; kk < KT / 16; kk++, ad += 2u * 128u, bd += 16u) umma_e<1>(d, ad, bd, p.idesc_pv, (j | kk) ? 1u : 0u);
+                    umma_commit_e(BAR(B_PEMPTY + pb));
+                    umma_commit_e(BAR(B_VEMPTY + pb));
+                    if (j == NT - 1) umma_commit_e(BAR(B_OFULL));
                 }
             }
         }

@@ -254,6 +254,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// One lane of a fully converged warp.  The MMA issuer runs its loops with ALL 32 lanes (descriptors and loop state stay in uniform
+// registers) and only the tcgen05.mma / tcgen05.commit are guarded by this: issuing from inside an `if (lane == 0)` region makes
+// nvcc treat every operand as divergent and wrap each UTCHMMA in an ELECT + 5x R2UR.BROADCAST + BRA.U.ANY waterfall loop
+// (measured in round 2: ~185 cycles per MMA regardless of its size, 3x the 64-cycle MMA at N = 128).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -271,6 +280,11 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+template <int F16>
+__device__ __forceinline__ void umma_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (elect_one()) umma<F16>(tmem_d, adesc, bdesc, idesc, accumulate);
+}
+__device__ __forceinline__ void umma_commit_e(uint32_t bar) { if (elect_one()) umma_commit(bar); }
 // round-to-nearest (ties away) TF32 with two integer instructions: identical bits to cvt.rna.tf32.f32 for finite inputs,
 // but issued on the ALU pipe (round 1 ncu: the cvt saturated the XU pipe at 94-98 % in the operand prologue)
 __device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
@@ -624,7 +638,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {  // all 32 lanes run the issue loop convergently; elect_one() guards the MMAs / commits
             // ===== MMA issuer: per weight tile, MT x KC/(2G) tcgen05.mma (M=128, N=nt), always accumulating.
             // Descriptors are advanced with 64-bit adds on the (addr >> 4) field: this single thread is the issue
             // bottleneck for narrow N, so the loop body is kept to a handful of integer instructions.
@@ -647,13 +661,13 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
                     for (int mt = 0; mt < MT; mt++) {
                         uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(mt * 128 + j * p.dil), bd = b_desc0;
                         const uint32_t d = tmem + (uint32_t)(mt * nt);
-                        for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma<F16>(d, ad, bd, p.idesc, 1u);
+                        for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_e<F16>(d, ad, bd, p.idesc, 1u);
                     }
-                    umma_commit(BAR(B_WEMPTY + sw));
+                    umma_commit_e(BAR(B_WEMPTY + sw));
                 }
-                umma_commit(BAR(B_AEMPTY + sa));
+                umma_commit_e(BAR(B_AEMPTY + sa));
             }
-            umma_commit(BAR(B_ACC));
+            umma_commit_e(BAR(B_ACC));
         }
     } else {
         const int tid2 = threadIdx.x - 64;
@@ -759,7 +773,7 @@ __global__ void __launch_bounds__(320, OCC) k_tc_conv1d_persist(TcParams p, int 
         }
     } else if (warp == 1) {
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        if (lane == 0) {
+        {  // all 32 lanes run the issue loop convergently; elect_one() guards the MMAs / commits
             const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)nt * 16u;
             const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R), b_kstep = (uint64_t)(2u * (uint32_t)nt);
             const uint64_t b_tap = (uint64_t)((uint32_t)ncg * nt);  // next tap's weight tile, in 16-byte units
@@ -776,10 +790,10 @@ __global__ void __launch_bounds__(320, OCC) k_tc_conv1d_persist(TcParams p, int 
                 uint64_t bd_tap = b_desc0;
                 for (int j = 0; j < p.K; j++, bd_tap += b_tap) {
                     uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(j * p.dil), bd = bd_tap;
-                    for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma<F16>(d, ad, bd, p.idesc, 1u);
+                    for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_e<F16>(d, ad, bd, p.idesc, 1u);
                 }
-                umma_commit(BAR(B_AEMPTY + sa));
-                umma_commit(BAR(B_ACC + ab));
+                umma_commit_e(BAR(B_AEMPTY + sa));
+                umma_commit_e(BAR(B_ACC + ab));
             }
         }
     } else if (warp < 6) {
@@ -927,7 +941,7 @@ __global__ void __launch_bounds__(352, 1) k_tc_conv1d_pstream(TcParams p, int mt
         }
     } else if (warp == 1) {
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        if (lane == 0) {
+        {  // all 32 lanes run the issue loop convergently; elect_one() guards the MMAs / commits
             const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)nt * 16u;
             const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R), b_kstep = (uint64_t)(2u * (uint32_t)nt);
             const int nk = p.KC / (2 * G);
@@ -950,13 +964,13 @@ __global__ void __launch_bounds__(352, 1) k_tc_conv1d_pstream(TcParams p, int mt
                         for (int mt = 0; mt < MT; mt++) {
                             uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(mt * 128 + j * p.dil), bd = bd0;
                             const uint32_t d = d0 + (uint32_t)(mt * nt);
-                            for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma<F16>(d, ad, bd, p.idesc, 1u);
+                            for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_e<F16>(d, ad, bd, p.idesc, 1u);
                         }
-                        umma_commit(BAR(B_WEMPTY + sw));
+                        umma_commit_e(BAR(B_WEMPTY + sw));
                     }
-                    umma_commit(BAR(B_AEMPTY + sa));
+                    umma_commit_e(BAR(B_AEMPTY + sa));
                 }
-                umma_commit(BAR(B_ACC + ab));
+                umma_commit_e(BAR(B_ACC + ab));
             }
         }
     } else if (warp < 6) {
@@ -1103,7 +1117,7 @@ __global__ void __launch_bounds__(320, 2) k_tc_pair_persist(TcPairPParams p) {
         }
     } else if (warp == 1) {
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        if (lane == 0) {
+        {  // all 32 lanes run the issue loop convergently; elect_one() guards the MMAs / commits
             const uint32_t b_lbo = (uint32_t)C * 16u;
             const uint64_t b_kstep = (uint64_t)(2u * (uint32_t)C);
             const int nk = C / (2 * G);
@@ -1119,9 +1133,9 @@ __global__ void __launch_bounds__(320, 2) k_tc_pair_persist(TcPairPParams p) {
                 for (int j = 0; j < p.K; j++) {
                     uint64_t ad = xt0 + (uint64_t)(uint32_t)j;
                     uint64_t bd = make_desc(smem_u32(sW2) + (uint32_t)j * tap_bytes, b_lbo, 128u);
-                    for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma<F16>(d2, ad, bd, p.idesc, 1u);
+                    for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_e<F16>(d2, ad, bd, p.idesc, 1u);
                 }
-                umma_commit(BAR(B_D2FULL + buf));
+                umma_commit_e(BAR(B_D2FULL + buf));
             };
             for (int i = 0; i < ntl; i++) {
                 const int sa = i % NAS, buf = i & 1;
@@ -1134,10 +1148,10 @@ __global__ void __launch_bounds__(320, 2) k_tc_pair_persist(TcPairPParams p) {
                 for (int j = 0; j < p.K; j++) {
                     uint64_t ad = a0 + (uint64_t)(uint32_t)(j * p.dil);
                     uint64_t bd = make_desc(smem_u32(sW1) + (uint32_t)j * tap_bytes, b_lbo, 128u);
-                    for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma<F16>(d1, ad, bd, p.idesc, (j | kk) ? 1u : 0u);
+                    for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_e<F16>(d1, ad, bd, p.idesc, (j | kk) ? 1u : 0u);
                 }
-                umma_commit(BAR(B_AEMPTY + sa));
-                umma_commit(BAR(B_D1FULL + buf));
+                umma_commit_e(BAR(B_AEMPTY + sa));
+                umma_commit_e(BAR(B_D1FULL + buf));
                 if (i > 0) conv2(i - 1);
             }
             if (ntl > 0) conv2(ntl - 1);

@@ -44,9 +44,11 @@ struct G2Params {
     uint32_t a_stage_bytes, w_stage_bytes, tmem_cols, idesc;
     int residual, accumulate, ups_u, ups_cout;
     float out_scale;
+    long long* prof;  // probes only: per-CTA timestamps [grid][16] (globaltimer ns / clock64 sums); nullptr in the engine
 };
 
 namespace tc {
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
     const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -61,6 +63,8 @@ __global__ void __launch_bounds__(384, 1) k_g2_conv(G2Params p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NAS = p.nas, NWS = p.nws, NG = p.NG, MG = p.MG, NCH = p.nchunks, nt = p.nt, R = p.R;
     const int t0 = blockIdx.x * NG * MG * 128, ntile = blockIdx.y, n0 = ntile * nt, b = blockIdx.z;
+    long long* prof = p.prof ? p.prof + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+    if (prof && threadIdx.x == 0) prof[0] = gtime();
     uint8_t* sA = smem;
     uint8_t* sW = smem + (size_t)NAS * p.a_stage_bytes;
     const int nwst = p.resident ? NCH * p.K : NWS;  // weight stages held in shared memory
@@ -89,8 +93,10 @@ __global__ void __launch_bounds__(384, 1) k_g2_conv(G2Params p) {
 
     if (warp == 0) {
         // ===== activation producer (reads the upstream kernel's output: PDL wait first)
+        if (prof && lane == 0) prof[1] = gtime();
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        if (prof && lane == 0) prof[2] = gtime();
         const int steps = NG * NCH;
         for (int s = 0; s < steps; s++) {
             const int g = s / NCH, c = s - g * NCH, sa = s % NAS;
@@ -129,44 +135,53 @@ __global__ void __launch_bounds__(384, 1) k_g2_conv(G2Params p) {
         }
     } else if (warp == 1) {
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        if (lane == 0) {
-            // ===== MMA issuer
-            const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)nt * 16u;
-            const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R), b_kstep = (uint64_t)(2u * (uint32_t)nt);
-            const int nk = p.KC / 16;
-            if (p.resident) { mbar_wait(BAR(B_WFULL), 0); fence_after(); }
-            int wi = 0, s = 0;
-            for (int g = 0; g < NG; g++) {
-                for (int c = 0; c < NCH; c++, s++) {
-                    const int sa = s % NAS;
-                    mbar_wait(BAR(B_AFULL + sa), (s / NAS) & 1);
-                    fence_after();
-                    const uint64_t a_desc0 = make_desc(smem_u32(sA + (size_t)sa * p.a_stage_bytes), a_lbo, 128u);
-                    for (int j = 0; j < p.K; j++, wi++) {
-                        uint64_t bd0;
-                        int sw = 0;
-                        if (p.resident) {
-                            bd0 = make_desc(smem_u32(sW + (size_t)(c * p.K + j) * p.w_stage_bytes), b_lbo, 128u);
-                        } else {
-                            sw = wi % NWS;
-                            mbar_wait(BAR(B_WFULL + sw), (wi / NWS) & 1);
-                            fence_after();
-                            bd0 = make_desc(smem_u32(sW + (size_t)sw * p.w_stage_bytes), b_lbo, 128u);
-                        }
-                        const uint32_t acc0 = (c | j) ? 1u : 0u;  // the very first MMA of an accumulator overwrites it
-                        for (int mt = 0; mt < MG; mt++) {
-                            uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(mt * 128 + j * p.dil), bd = bd0;
-                            const uint32_t d = tmem + (uint32_t)((g * MG + mt) * nt);
-                            umma<1>(d, ad, bd, p.idesc, acc0);
-                            for (int kk = 1; kk < nk; kk++) { ad += a_kstep; bd += b_kstep; umma<1>(d, ad, bd, p.idesc, 1u); }
-                        }
-                        if (!p.resident) umma_commit(BAR(B_WEMPTY + sw));
+        // ===== MMA issuer: all 32 lanes run the loops convergently (uniform registers), one elected lane issues (see elect_one)
+        // Descriptors are kept as (constant high word, 32-bit low word): start address >> 4 in bits [0,14), LBO >> 4 in [16,30) of the low
+        // word; tap / m-tile / k-step offsets are plain 32-bit adds on the low word (shared memory addresses stay below 2^18), which the
+        // compiler keeps in the uniform datapath.
+        const uint32_t a_lo_c = (((uint32_t)R * 16u) >> 4) << 16, b_lo_c = (((uint32_t)nt * 16u) >> 4) << 16;
+        const uint32_t desc_hi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
+        const uint32_t a_kstep = 2u * (uint32_t)R, b_kstep = 2u * (uint32_t)nt;
+        const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+        const int nk = p.KC / 16;
+        if (p.resident) { mbar_wait(BAR(B_WFULL), 0); fence_after(); }
+        int wi = 0, s = 0;
+        long long waitA = 0, waitW = 0;
+        for (int g = 0; g < NG; g++) {
+            for (int c = 0; c < NCH; c++, s++) {
+                const int sa = s % NAS;
+                long long c0 = prof ? clock64() : 0;
+                mbar_wait(BAR(B_AFULL + sa), (s / NAS) & 1);
+                fence_after();
+                if (prof) { waitA += clock64() - c0; if (s == 0 && lane == 0) prof[3] = gtime(); }
+                const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa * p.a_stage_bytes) & 0x3ffffu) >> 4) | a_lo_c;
+                for (int j = 0; j < p.K; j++, wi++) {
+                    uint32_t b_lo0;
+                    int sw = 0;
+                    if (p.resident) {
+                        b_lo0 = ((smem_u32(sW + (size_t)(c * p.K + j) * p.w_stage_bytes) & 0x3ffffu) >> 4) | b_lo_c;
+                    } else {
+                        sw = wi % NWS;
+                        c0 = prof ? clock64() : 0;
+                        mbar_wait(BAR(B_WFULL + sw), (wi / NWS) & 1);
+                        fence_after();
+                        if (prof) waitW += clock64() - c0;
+                        b_lo0 = ((smem_u32(sW + (size_t)sw * p.w_stage_bytes) & 0x3ffffu) >> 4) | b_lo_c;
                     }
-                    umma_commit(BAR(B_AEMPTY + sa));
+                    const uint32_t acc0 = (c | j) ? 1u : 0u;  // the very first MMA of an accumulator overwrites it
+                    for (int mt = 0; mt < MG; mt++) {
+                        uint32_t a_lo = a_lo0 + (uint32_t)(mt * 128 + j * p.dil), b_lo = b_lo0;
+                        const uint32_t d = tm + (uint32_t)((g * MG + mt) * nt);
+                        for (int kk = 0; kk < nk; kk++, a_lo += a_kstep, b_lo += b_kstep)
+                            if (elect_one()) umma<1>(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, p.idesc, kk ? 1u : acc0);
+                    }
+                    if (!p.resident && elect_one()) umma_commit(BAR(B_WEMPTY + sw));
                 }
-                umma_commit(BAR(B_ACC + g));
+                if (elect_one()) umma_commit(BAR(B_AEMPTY + sa));
             }
+            if (elect_one()) umma_commit(BAR(B_ACC + g));
         }
+        if (prof && lane == 0) { prof[4] = gtime(); prof[8] = waitA; prof[9] = waitW; }
     } else if (warp >= 4) {
         // ===== epilogue: warp e = 0..7; TMEM lane quarter q = warp & 3, the two warps of a quarter take alternate m-tiles
         asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -177,6 +192,8 @@ __global__ void __launch_bounds__(384, 1) k_g2_conv(G2Params p) {
         for (int g = 0; g < NG; g++) {
             mbar_wait(BAR(B_ACC + g), 0);
             fence_after();
+            if (prof && e == 0 && lane == 0 && g == 0) prof[5] = gtime();
+            if (prof && e == 0 && lane == 0 && g == NG - 1) prof[6] = gtime();
             for (int mt = half; mt < MG; mt += 2) {
                 const int t = t0 + (g * MG + mt) * 128 + q * 32 + lane;
                 const bool ok = t < p.T;
@@ -229,6 +246,7 @@ __global__ void __launch_bounds__(384, 1) k_g2_conv(G2Params p) {
             }
         }
     }
+    if (prof && warp == 4 && lane == 0) prof[7] = gtime();
     fence_before();
     __syncthreads();
     if (warp == 3) {
@@ -298,6 +316,7 @@ struct G2Epi {
     const float* bias_b = nullptr; int bias_b_stride = 0;  // per-batch bias (speaker conditioning of conv_pre)
     int dil = 1;
     int st_override = 0;      // probes: force the super-tile size (m-tiles per CTA)
+    long long* prof = nullptr;  // probes: per-CTA timestamps
 };
 
 // Static part of the plan (fixed at weight-pack time): N tile and K chunk for a conv with `cols` output columns.
@@ -313,7 +332,7 @@ inline void g2_conv(const TcConvW& w, const float* bias, const H8& x, const H8& 
     p.x = x.p; p.y = y.p; p.w = w.w; p.bias = bias; p.bias_b = e.bias_b; p.bias_b_stride = e.bias_b_stride;
     p.x_cg = x.C / 8; p.x_Tp = x.Tp; p.y_cg = y.C / 8; p.y_Tp = y.Tp;
     if (e.res) { BV2_CHECK(!w.ups_u && e.res->C == y.C && e.res->T == y.T && e.res->B == y.B, "g2_conv residual"); p.res = e.res->p; p.res_cg = e.res->C / 8; p.res_Tp = e.res->Tp; p.residual = 1; }
-    p.accumulate = e.accumulate; p.out_scale = e.out_scale; p.ups_u = w.ups_u; p.ups_cout = w.ups_cout;
+    p.accumulate = e.accumulate; p.out_scale = e.out_scale; p.ups_u = w.ups_u; p.ups_cout = w.ups_cout; p.prof = e.prof;
     if (w.ups_u) BV2_CHECK(w.ups_cout % 8 == 0 && !e.accumulate, "g2_conv ups");
     p.T = x.T; p.K = w.K; p.dil = e.dil; p.pad = (w.K - 1) / 2 * e.dil;
     BV2_CHECK(p.pad <= G2_PADL && p.pad <= G2_PADR, "g2_conv padding exceeds the tensor halo");

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <string>
 #include <vector>
 #include "../../bert_vits2_b200/csrc/tc_gen.cuh"
 
@@ -100,6 +101,22 @@ static int run_conv(int Cin, int Cout, int K, int dil, int T, int B, bool res, b
     if (iters > 0) {
         cudaEvent_t a, c; cudaEventCreate(&a); cudaEventCreate(&c);
         e.accumulate = 0;
+        if (getenv("G2_PROF")) {  // per-CTA phase timeline of the last of three back-to-back launches
+            long long* dprof = (long long*)dalloc(4096 * 16 * 8);
+            cudaMemset(dprof, 0, 4096 * 16 * 8);
+            for (int i = 0; i < 3; i++) { e.prof = i == 2 ? dprof : nullptr; g2_conv(tw, dbias, hx, hy, e, 0, 148); }
+            e.prof = nullptr;
+            cudaDeviceSynchronize();
+            std::vector<long long> hp(4096 * 16);
+            cudaMemcpy(hp.data(), dprof, hp.size() * 8, cudaMemcpyDeviceToHost);
+            long long t0 = 0; int n = 0;
+            for (int i = 0; i < 4096; i++) if (hp[i * 16]) { n++; if (!t0 || hp[i * 16] < t0) t0 = hp[i * 16]; }
+            printf("  prof (%d CTAs; ns since first CTA start): cta: start | pdl-wait begin/end | first A | mma issue end | acc0 full | accN full | tail end || clk waitA waitW\n", n);
+            for (int i : {0, 1, n / 2, n - 1}) {
+                const long long* q = &hp[(size_t)i * 16];
+                printf("   cta %4d: %6lld | %6lld %6lld | %6lld | %6lld | %6lld | %6lld | %6lld || %8lld %8lld\n", i, q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0, q[4] - t0, q[5] - t0, q[6] - t0, q[7] - t0, q[8], q[9]);
+            }
+        }
         for (int i = 0; i < 3; i++) g2_conv(tw, dbias, hx, hy, e, 0, 148);
         cudaEventRecord(a);
         for (int i = 0; i < iters; i++) g2_conv(tw, dbias, hx, hy, e, 0, 148);
@@ -169,6 +186,12 @@ int main(int argc, char** argv) {
     g_flag = tc_init_device();
     g2_init_device();
     int fails = 0;
+    if (argc > 1 && std::string(argv[1]) == "case") {  // g2_probe case Cin Cout K dil T st iters res [more cases ...]
+        for (int a = 2; a + 7 < argc; a += 8) {
+            run_conv(atoi(argv[a]), atoi(argv[a + 1]), atoi(argv[a + 2]), atoi(argv[a + 3]), atoi(argv[a + 4]), 1, atoi(argv[a + 7]) != 0, false, 1.f, atoi(argv[a + 5]), atoi(argv[a + 6]));
+        }
+        return 0;
+    }
     // ---- correctness: small shapes, every tail, edge tiles, both weight modes
     fails += run_conv(16, 16, 3, 1, 300, 1, false, false, 1.f, 0, 0);
     fails += run_conv(16, 16, 11, 5, 1000, 2, true, false, 1.f, 0, 0);
