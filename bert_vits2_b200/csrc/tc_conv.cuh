@@ -189,6 +189,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
                    "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+                   "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+                   "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -285,6 +291,24 @@ __device__ __forceinline__ void umma_e(uint32_t tmem_d, uint64_t adesc, uint64_t
     if (elect_one()) umma<F16>(tmem_d, adesc, bdesc, idesc, accumulate);
 }
 __device__ __forceinline__ void umma_commit_e(uint32_t bar) { if (elect_one()) umma_commit(bar); }
+// nk accumulating k-steps on one accumulator, unrolled for the common counts: a rolled loop re-uses one uniform-register set for the
+// descriptors and serialises every UTCHMMA behind the R2UR round trip of its predecessor (~190 cycles per MMA of any size, round 2)
+template <int F16, int NK>
+__device__ __forceinline__ void umma_ksteps_n(uint32_t d, uint64_t ad, uint64_t bd, uint64_t a_kstep, uint64_t b_kstep, uint32_t idesc, uint32_t acc_first) {
+#pragma unroll
+    for (int kk = 0; kk < NK; kk++) umma_e<F16>(d, ad + kk * a_kstep, bd + kk * b_kstep, idesc, kk ? 1u : acc_first);
+}
+template <int F16>
+__device__ __forceinline__ void umma_ksteps(uint32_t d, uint64_t ad, uint64_t bd, uint64_t a_kstep, uint64_t b_kstep, uint32_t idesc, int nk, uint32_t acc_first) {
+    switch (nk) {
+        case 1: umma_ksteps_n<F16, 1>(d, ad, bd, a_kstep, b_kstep, idesc, acc_first); break;
+        case 2: umma_ksteps_n<F16, 2>(d, ad, bd, a_kstep, b_kstep, idesc, acc_first); break;
+        case 4: umma_ksteps_n<F16, 4>(d, ad, bd, a_kstep, b_kstep, idesc, acc_first); break;
+        case 8: umma_ksteps_n<F16, 8>(d, ad, bd, a_kstep, b_kstep, idesc, acc_first); break;
+        default:
+            for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_e<F16>(d, ad, bd, idesc, kk ? 1u : acc_first);
+    }
+}
 // round-to-nearest (ties away) TF32 with two integer instructions: identical bits to cvt.rna.tf32.f32 for finite inputs,
 // but issued on the ALU pipe (round 1 ncu: the cvt saturated the XU pipe at 94-98 % in the operand prologue)
 __device__ __forceinline__ float to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
@@ -661,7 +685,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
                     for (int mt = 0; mt < MT; mt++) {
                         uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(mt * 128 + j * p.dil), bd = b_desc0;
                         const uint32_t d = tmem + (uint32_t)(mt * nt);
-                        for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_e<F16>(d, ad, bd, p.idesc, 1u);
+                        umma_ksteps<F16>(d, ad, bd, a_kstep, b_kstep, p.idesc, nk, 1u);
                     }
                     umma_commit_e(BAR(B_WEMPTY + sw));
                 }
@@ -790,7 +814,7 @@ __global__ void __launch_bounds__(320, OCC) k_tc_conv1d_persist(TcParams p, int 
                 uint64_t bd_tap = b_desc0;
                 for (int j = 0; j < p.K; j++, bd_tap += b_tap) {
                     uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(j * p.dil), bd = bd_tap;
-                    for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_e<F16>(d, ad, bd, p.idesc, 1u);
+                    umma_ksteps<F16>(d, ad, bd, a_kstep, b_kstep, p.idesc, nk, 1u);
                 }
                 umma_commit_e(BAR(B_AEMPTY + sa));
                 umma_commit_e(BAR(B_ACC + ab));
@@ -964,7 +988,7 @@ __global__ void __launch_bounds__(352, 1) k_tc_conv1d_pstream(TcParams p, int mt
                         for (int mt = 0; mt < MT; mt++) {
                             uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(mt * 128 + j * p.dil), bd = bd0;
                             const uint32_t d = d0 + (uint32_t)(mt * nt);
-                            for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_e<F16>(d, ad, bd, p.idesc, 1u);
+                            umma_ksteps<F16>(d, ad, bd, a_kstep, b_kstep, p.idesc, nk, 1u);
                         }
                         umma_commit_e(BAR(B_WEMPTY + sw));
                     }
@@ -1133,7 +1157,7 @@ __global__ void __launch_bounds__(320, 2) k_tc_pair_persist(TcPairPParams p) {
                 for (int j = 0; j < p.K; j++) {
                     uint64_t ad = xt0 + (uint64_t)(uint32_t)j;
                     uint64_t bd = make_desc(smem_u32(sW2) + (uint32_t)j * tap_bytes, b_lbo, 128u);
-                    for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_e<F16>(d2, ad, bd, p.idesc, 1u);
+                    umma_ksteps<F16>(d2, ad, bd, a_kstep, b_kstep, p.idesc, nk, 1u);
                 }
                 umma_commit_e(BAR(B_D2FULL + buf));
             };
@@ -1148,7 +1172,7 @@ __global__ void __launch_bounds__(320, 2) k_tc_pair_persist(TcPairPParams p) {
                 for (int j = 0; j < p.K; j++) {
                     uint64_t ad = a0 + (uint64_t)(uint32_t)(j * p.dil);
                     uint64_t bd = make_desc(smem_u32(sW1) + (uint32_t)j * tap_bytes, b_lbo, 128u);
-                    for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_e<F16>(d1, ad, bd, p.idesc, (j | kk) ? 1u : 0u);
+                    umma_ksteps<F16>(d1, ad, bd, a_kstep, b_kstep, p.idesc, nk, j ? 1u : 0u);
                 }
                 umma_commit_e(BAR(B_AEMPTY + sa));
                 umma_commit_e(BAR(B_D1FULL + buf));

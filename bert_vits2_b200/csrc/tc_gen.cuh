@@ -21,8 +21,9 @@
 //   streamed weights (C >= 64): NG = 1, MG = 2..8 -- weights cross L2->SM once per MG*128 rows, ring of up to 16 stages;
 //   resident weights (C <= 32): all taps loaded once, the M-groups pipeline through the activation ring and the tail of
 //   group g overlaps the MMAs of group g+1.
-// 384 threads: warp 0 activation producer, warp 1 MMA issuer, warp 2 weight producer, warp 3 TMEM allocator,
-// warps 4-11 epilogue (TMEM -> +bias [+ residual] [+ MRF running sum] -> lrelu -> f16 -> 16-byte coalesced stores).
+// 512 threads: warp 0 activation producer, warp 1 MMA issuer, warp 2 weight producer, warp 3 TMEM allocator,
+// warps 4-15 epilogue (accumulator init with the bias before the MMAs; tail TMEM -> [+ residual] [+ MRF running sum] -> lrelu -> f16
+// -> 16-byte coalesced stores).
 #pragma once
 #include "tc_conv.cuh"
 
@@ -44,6 +45,7 @@ struct G2Params {
     uint32_t a_stage_bytes, w_stage_bytes, tmem_cols, idesc;
     int residual, accumulate, ups_u, ups_cout;
     float out_scale;
+    int dbg_skip_wcommit;  // probes only: no weight-stage commits (valid only when every weight stage fits the ring)
     long long* prof;  // probes only: per-CTA timestamps [grid][16] (globaltimer ns / clock64 sums); nullptr in the engine
 };
 
@@ -57,7 +59,28 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 __device__ __forceinline__ float unlrelu10(float a) { return a >= 0.f ? a : a * 10.f; }
 }  // namespace tc
 
-__global__ void __launch_bounds__(384, 1) k_g2_conv(G2Params p) {
+// MMAs of one weight stage (chunk c, tap j): MG m-tiles x NK k-steps.  Unrolled in bodies of 4 m-tiles so that the compiler rotates the
+// uniform registers that carry descriptors into UTCHMMA: a rolled loop re-uses one register set and serialises every MMA behind the
+// R2UR round trip of its predecessor (measured: ~190 cycles per MMA of any size; the unrolled issue path runs at the 64-cycle floor of
+// an N = 128 MMA, tests/cuda/mma_rate.cu).
+template <int NK>
+__device__ __forceinline__ void g2_issue_stage(uint32_t d0, uint32_t a_lo0, uint32_t b_lo0, uint32_t a_kstep, uint32_t b_kstep, uint32_t desc_hi, uint32_t nt, int MG,
+                                               uint32_t idesc, uint32_t acc0) {
+    const uint64_t hi = (uint64_t)desc_hi << 32;
+    for (int mt0 = 0; mt0 < MG; mt0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (mt0 + u < MG) {
+                const uint32_t d = d0 + (uint32_t)(mt0 + u) * nt, a_lo = a_lo0 + (uint32_t)(mt0 + u) * 128u;
+#pragma unroll
+                for (int kk = 0; kk < NK; kk++)
+                    if (tc::elect_one()) tc::umma<1>(d, hi | (a_lo + kk * a_kstep), hi | (b_lo0 + kk * b_kstep), idesc, kk ? 1u : acc0);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -71,14 +94,15 @@ __global__ void __launch_bounds__(384, 1) k_g2_conv(G2Params p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)nwst * p.w_stage_bytes);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    // barrier map: a_full[NAS], a_empty[NAS], w_full[NWS], w_empty[NWS], acc_full[NG]
-    const int B_AFULL = 0, B_AEMPTY = NAS, B_WFULL = 2 * NAS, B_WEMPTY = 2 * NAS + NWS, B_ACC = 2 * NAS + 2 * NWS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_ACC + NG);
+    // barrier map: a_full[NAS], a_empty[NAS], w_full[NWS], w_empty[NWS], acc_full[NG], acc_init
+    const int B_AFULL = 0, B_AEMPTY = NAS, B_WFULL = 2 * NAS, B_WEMPTY = 2 * NAS + NWS, B_ACC = 2 * NAS + 2 * NWS, B_INIT = B_ACC + NG;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_INIT + 1);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NAS; i++) { mbar_init(BAR(B_AFULL + i), 1); mbar_init(BAR(B_AEMPTY + i), 1); }
         for (int i = 0; i < NWS; i++) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
         for (int i = 0; i < NG; i++) mbar_init(BAR(B_ACC + i), 1);
+        mbar_init(BAR(B_INIT), 12 * 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 3) {
@@ -145,6 +169,8 @@ __global__ void __launch_bounds__(384, 1) k_g2_conv(G2Params p) {
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
         const int nk = p.KC / 16;
         if (p.resident) { mbar_wait(BAR(B_WFULL), 0); fence_after(); }
+        mbar_wait(BAR(B_INIT), 0);  // accumulators hold the bias: every MMA accumulates
+        fence_after();
         int wi = 0, s = 0;
         long long waitA = 0, waitW = 0;
         for (int g = 0; g < NG; g++) {
@@ -153,7 +179,7 @@ __global__ void __launch_bounds__(384, 1) k_g2_conv(G2Params p) {
                 long long c0 = prof ? clock64() : 0;
                 mbar_wait(BAR(B_AFULL + sa), (s / NAS) & 1);
                 fence_after();
-                if (prof) { waitA += clock64() - c0; if (s == 0 && lane == 0) prof[3] = gtime(); }
+                if (prof) { waitA += clock64() - c0; if (s == 0 && lane == 0) { prof[3] = gtime(); prof[10] = clock64(); } }
                 const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa * p.a_stage_bytes) & 0x3ffffu) >> 4) | a_lo_c;
                 for (int j = 0; j < p.K; j++, wi++) {
                     uint32_t b_lo0;
@@ -168,79 +194,114 @@ __global__ void __launch_bounds__(384, 1) k_g2_conv(G2Params p) {
                         if (prof) waitW += clock64() - c0;
                         b_lo0 = ((smem_u32(sW + (size_t)sw * p.w_stage_bytes) & 0x3ffffu) >> 4) | b_lo_c;
                     }
-                    const uint32_t acc0 = (c | j) ? 1u : 0u;  // the very first MMA of an accumulator overwrites it
-                    for (int mt = 0; mt < MG; mt++) {
-                        uint32_t a_lo = a_lo0 + (uint32_t)(mt * 128 + j * p.dil), b_lo = b_lo0;
-                        const uint32_t d = tm + (uint32_t)((g * MG + mt) * nt);
-                        for (int kk = 0; kk < nk; kk++, a_lo += a_kstep, b_lo += b_kstep)
-                            if (elect_one()) umma<1>(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, p.idesc, kk ? 1u : acc0);
-                    }
-                    if (!p.resident && elect_one()) umma_commit(BAR(B_WEMPTY + sw));
+                    const uint32_t acc0 = 1u;
+                    if (nk == 2) g2_issue_stage<2>(tm + (uint32_t)(g * MG * nt), a_lo0 + (uint32_t)(j * p.dil), b_lo0, a_kstep, b_kstep, desc_hi, (uint32_t)nt, MG, p.idesc, acc0);
+                    else if (nk == 1) g2_issue_stage<1>(tm + (uint32_t)(g * MG * nt), a_lo0 + (uint32_t)(j * p.dil), b_lo0, a_kstep, b_kstep, desc_hi, (uint32_t)nt, MG, p.idesc, acc0);
+                    else
+                        for (int mt = 0; mt < MG; mt++) {
+                            uint32_t a_lo = a_lo0 + (uint32_t)(mt * 128 + j * p.dil), b_lo = b_lo0;
+                            const uint32_t d = tm + (uint32_t)((g * MG + mt) * nt);
+                            for (int kk = 0; kk < nk; kk++, a_lo += a_kstep, b_lo += b_kstep)
+                                if (elect_one()) umma<1>(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, p.idesc, kk ? 1u : acc0);
+                        }
+                    if (!p.resident && !p.dbg_skip_wcommit && elect_one()) umma_commit(BAR(B_WEMPTY + sw));
                 }
                 if (elect_one()) umma_commit(BAR(B_AEMPTY + sa));
             }
             if (elect_one()) umma_commit(BAR(B_ACC + g));
         }
-        if (prof && lane == 0) { prof[4] = gtime(); prof[8] = waitA; prof[9] = waitW; }
+        if (prof && lane == 0) { prof[4] = gtime(); prof[8] = waitA; prof[9] = waitW; prof[11] = clock64(); prof[12] = (long long)NG * NCH * p.K * MG * nk; }
     } else if (warp >= 4) {
-        // ===== epilogue: warp e = 0..7; TMEM lane quarter q = warp & 3, the two warps of a quarter take alternate m-tiles
-        asm volatile("griddepcontrol.wait;" ::: "memory");
+        // ===== epilogue, 12 warps: TMEM lane quarter q = warp & 3; the 3 warps of a quarter share the (m-tile, 32-column batch) items
+        // round-robin.  Two phases:
+        //   init (before the MMAs, before the PDL wait: touches only static data and CTA-private TMEM): the accumulators are pre-loaded
+        //        with bias (+ per-batch bias) by tcgen05.st, so every MMA accumulates and the tail has no bias loads / adds;
+        //   tail: TMEM -> [+ residual] [+ MRF running sum] -> lrelu -> f16 -> coalesced 16-byte stores.
+        // The tail is instruction-bound (two-three warps per scheduler cannot hide ALU latency: round-2 ncu), so it is kept lean.
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        const int e = warp - 4, q = warp & 3, half = e >> 2;
+        const int e = warp - 4, q = warp & 3, part = e >> 2;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         const int u = p.ups_u;
+        const int ncb = nt >= 32 ? nt / 32 : 1, cw = nt >= 32 ? 32 : 16;  // column batches per m-tile, columns per batch
+        {
+            for (int cb = part; cb < ncb; cb += 3) {
+                const int col0 = cb * cw;
+                uint32_t v[32];
+#pragma unroll
+                for (int h = 0; h < 8; h++) {
+                    if (4 * h < cw) {
+                        const int n = n0 + col0 + 4 * h;
+                        float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + (u ? n % p.ups_cout : n)));
+                        if (p.bias_b) {
+                            const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + n));
+                            b4.x += c4.x; b4.y += c4.y; b4.z += c4.z; b4.w += c4.w;
+                        }
+                        v[4 * h] = __float_as_uint(b4.x); v[4 * h + 1] = __float_as_uint(b4.y); v[4 * h + 2] = __float_as_uint(b4.z); v[4 * h + 3] = __float_as_uint(b4.w);
+                    }
+                }
+                for (int m = 0; m < NG * MG; m++) {
+                    if (cw == 32) tmem_st32(trow + (uint32_t)(m * nt + col0), v); else tmem_st16(trow + (uint32_t)(m * nt + col0), v);
+                }
+            }
+            tmem_wait_st();
+            fence_before();
+            mbar_arrive(BAR(B_INIT));
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const bool scaled = p.out_scale != 1.f;
         for (int g = 0; g < NG; g++) {
             mbar_wait(BAR(B_ACC + g), 0);
             fence_after();
             if (prof && e == 0 && lane == 0 && g == 0) prof[5] = gtime();
             if (prof && e == 0 && lane == 0 && g == NG - 1) prof[6] = gtime();
-            for (int mt = half; mt < MG; mt += 2) {
+            for (int it = part; it < MG * ncb; it += 3) {
+                const int mt = it / ncb, col0 = (it - mt * ncb) * cw;
                 const int t = t0 + (g * MG + mt) * 128 + q * 32 + lane;
                 const bool ok = t < p.T;
-                const uint32_t tcol = trow + (uint32_t)((g * MG + mt) * nt);
-                for (int col0 = 0; col0 < nt; col0 += 32) {
-                    uint32_t v[32];
-                    const bool wide = col0 + 32 <= nt;
-                    if (wide) tmem_ld32(tcol + (uint32_t)col0, v); else tmem_ld16(tcol + (uint32_t)col0, v);
-                    tmem_wait_ld();
-                    if (!ok) continue;
+                uint32_t v[32];
+                if (cw == 32) tmem_ld32(trow + (uint32_t)((g * MG + mt) * nt + col0), v); else tmem_ld16(trow + (uint32_t)((g * MG + mt) * nt + col0), v);
+                // residual / running-sum operands are fetched while the TMEM load is in flight
+                uint4 r4[4], a4[4];
+                size_t yo[4];
 #pragma unroll
-                    for (int h = 0; h < 4; h++) {
-                        if (h < 2 || wide) {
-                            const int n = n0 + col0 + 8 * h;  // first of 8 consecutive output columns
-                            float f[8];
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + (u ? n % p.ups_cout : n)));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + (u ? n % p.ups_cout : n) + 4));
-                            f[0] = __uint_as_float(v[8 * h]) + b0.x; f[1] = __uint_as_float(v[8 * h + 1]) + b0.y;
-                            f[2] = __uint_as_float(v[8 * h + 2]) + b0.z; f[3] = __uint_as_float(v[8 * h + 3]) + b0.w;
-                            f[4] = __uint_as_float(v[8 * h + 4]) + b1.x; f[5] = __uint_as_float(v[8 * h + 5]) + b1.y;
-                            f[6] = __uint_as_float(v[8 * h + 6]) + b1.z; f[7] = __uint_as_float(v[8 * h + 7]) + b1.w;
-                            if (p.bias_b) {
-                                const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + n));
-                                const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.bias_b + (size_t)b * p.bias_b_stride + n + 4));
-                                f[0] += c0.x; f[1] += c0.y; f[2] += c0.z; f[3] += c0.w; f[4] += c1.x; f[5] += c1.y; f[6] += c1.z; f[7] += c1.w;
-                            }
-                            size_t yo;
-                            if (u) { const int r = n / p.ups_cout, co = n - r * p.ups_cout; yo = ((size_t)b * p.y_cg + co / 8) * p.y_Tp + (size_t)t * u + r; }
-                            else yo = ((size_t)b * p.y_cg + n / 8) * p.y_Tp + t;
-                            if (p.residual) {
-                                float r8[8];
-                                unpack8(p.res[((size_t)b * p.res_cg + n / 8) * p.res_Tp + t], r8);
+                for (int h = 0; h < 4; h++) {
+                    if (8 * h < cw) {
+                        const int n = n0 + col0 + 8 * h;  // first of 8 consecutive output columns
+                        if (u) { const int r = n / p.ups_cout, co = n - r * p.ups_cout; yo[h] = ((size_t)b * p.y_cg + co / 8) * p.y_Tp + (size_t)t * u + r; }
+                        else yo[h] = ((size_t)b * p.y_cg + n / 8) * p.y_Tp + t;
+                        if (p.residual && ok) r4[h] = p.res[((size_t)b * p.res_cg + n / 8) * p.res_Tp + t];
+                        if (p.accumulate && ok) a4[h] = p.y[yo[h]];
+                    }
+                }
+                tmem_wait_ld();
+                if (!ok) continue;
 #pragma unroll
-                                for (int k = 0; k < 8; k++) f[k] += unlrelu10(r8[k]);
-                            }
-                            if (p.accumulate) {
-                                float a8[8];
-                                unpack8(p.y[yo], a8);
+                for (int h = 0; h < 4; h++) {
+                    if (8 * h < cw) {
+                        float f[8];
 #pragma unroll
-                                for (int k = 0; k < 8; k++) f[k] += unlrelu10(a8[k]);
-                            }
+                        for (int k = 0; k < 8; k++) f[k] = __uint_as_float(v[8 * h + k]);
+                        if (p.residual) {
+                            float r8[8];
+                            unpack8(r4[h], r8);
 #pragma unroll
-                            for (int k = 0; k < 8; k++) f[k] = lrelu(f[k] * p.out_scale, 0.1f);
-                            uint4 o;
-                            o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
-                            p.y[yo] = o;
+                            for (int k = 0; k < 8; k++) f[k] += unlrelu10(r8[k]);
                         }
+                        if (p.accumulate) {
+                            float a8[8];
+                            unpack8(a4[h], a8);
+#pragma unroll
+                            for (int k = 0; k < 8; k++) f[k] += unlrelu10(a8[k]);
+                        }
+                        if (scaled) {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) f[k] *= p.out_scale;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; k++) f[k] = fmaxf(f[k], 0.1f * f[k]);  // lrelu(x, 0.1) = max(x, 0.1 x)
+                        uint4 o;
+                        o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+                        p.y[yo[h]] = o;
                     }
                 }
             }
@@ -317,6 +378,7 @@ struct G2Epi {
     int dil = 1;
     int st_override = 0;      // probes: force the super-tile size (m-tiles per CTA)
     long long* prof = nullptr;  // probes: per-CTA timestamps
+    int dbg_skip_wcommit = 0;
 };
 
 // Static part of the plan (fixed at weight-pack time): N tile and K chunk for a conv with `cols` output columns.
@@ -379,10 +441,11 @@ inline void g2_conv(const TcConvW& w, const float* bias, const H8& x, const H8& 
     if (!p.resident) p.nws = std::min(p.nws, NG * w.nchunks * w.K);
     uint32_t cols = 32; while ((int)cols < NG * MG * w.nt) cols <<= 1;
     p.tmem_cols = cols;
-    const size_t smem = (size_t)nas * p.a_stage_bytes + (p.resident ? w_all : (size_t)p.nws * p.w_stage_bytes) + (size_t)(2 * nas + 2 * p.nws + NG + 2) * 8 + 16;
+    const size_t smem = (size_t)nas * p.a_stage_bytes + (p.resident ? w_all : (size_t)p.nws * p.w_stage_bytes) + (size_t)(2 * nas + 2 * p.nws + NG + 3) * 8 + 16;
     BV2_CHECK(smem <= 227 * 1024 && cols <= 512, "g2_conv shared memory / TMEM");
     dim3 grid(cdiv(mtiles, NG * MG), ntiles, x.B);
-    launch_pdl(k_g2_conv, grid, dim3(384), smem, st, p);
+    if (e.dbg_skip_wcommit && !p.resident && p.nws >= NG * w.nchunks * w.K) p.dbg_skip_wcommit = 1;
+    launch_pdl(k_g2_conv, grid, dim3(512), smem, st, p);
 }
 
 }  // namespace bv2

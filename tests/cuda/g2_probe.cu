@@ -101,6 +101,7 @@ static int run_conv(int Cin, int Cout, int K, int dil, int T, int B, bool res, b
     if (iters > 0) {
         cudaEvent_t a, c; cudaEventCreate(&a); cudaEventCreate(&c);
         e.accumulate = 0;
+        e.dbg_skip_wcommit = getenv("G2_SKIP_WCOMMIT") ? 1 : 0;
         if (getenv("G2_PROF")) {  // per-CTA phase timeline of the last of three back-to-back launches
             long long* dprof = (long long*)dalloc(4096 * 16 * 8);
             cudaMemset(dprof, 0, 4096 * 16 * 8);
@@ -114,7 +115,8 @@ static int run_conv(int Cin, int Cout, int K, int dil, int T, int B, bool res, b
             printf("  prof (%d CTAs; ns since first CTA start): cta: start | pdl-wait begin/end | first A | mma issue end | acc0 full | accN full | tail end || clk waitA waitW\n", n);
             for (int i : {0, 1, n / 2, n - 1}) {
                 const long long* q = &hp[(size_t)i * 16];
-                printf("   cta %4d: %6lld | %6lld %6lld | %6lld | %6lld | %6lld | %6lld | %6lld || %8lld %8lld\n", i, q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0, q[4] - t0, q[5] - t0, q[6] - t0, q[7] - t0, q[8], q[9]);
+                printf("   cta %4d: %6lld | %6lld %6lld | %6lld | %6lld | %6lld | %6lld | %6lld || %8lld %8lld || mma phase %lld clk for %lld MMAs = %.1f clk/MMA, %.2f GHz\n", i, q[0] - t0, q[1] - t0, q[2] - t0, q[3] - t0, q[4] - t0, q[5] - t0, q[6] - t0, q[7] - t0, q[8], q[9],
+                       q[11] - q[10], q[12], (double)(q[11] - q[10]) / (double)std::max(1ll, q[12]), (double)(q[11] - q[10]) / (double)std::max(1ll, q[4] - q[3]));
             }
         }
         for (int i = 0; i < 3; i++) g2_conv(tw, dbias, hx, hy, e, 0, 148);
