@@ -122,11 +122,11 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
         }
     } else if (warp == 1) {
         if (NT > 0) {  // all 32 lanes run the issue loop convergently; elect_one() guards the MMAs / commits
-            mbar_wait(BAR(B_QFULL), 0);
+            mbar_wait_u(BAR(B_QFULL), 0);
             auto qk = [&](int s) {  // S[s&1] = Q . K_tile^T
                 const int st = s & 1;
-                mbar_wait(BAR(B_KFULL + st), (s >> 1) & 1);
-                mbar_wait(BAR(B_SEMPTY + st), ((s >> 1) & 1) ^ 1);
+                mbar_wait_u(BAR(B_KFULL + st), (s >> 1) & 1);
+                mbar_wait_u(BAR(B_SEMPTY + st), ((s >> 1) & 1) ^ 1);
                 fence_after();
                 uint64_t ad = make_desc(smem_u32(sQ), 128u * 16u, 128u);
                 uint64_t bd = make_desc(smem_u32(sK) + (uint32_t)st * KB, (uint32_t)KT * 16u, 128u);
@@ -141,8 +141,8 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                 if (s + 1 < 2 * NT) qk(s + 1);  // the next tile's scores are computed while the softmax warps work on this one
                 if (s >= NT) {
                     const int j = s - NT, pb = j & 1;
-                    mbar_wait(BAR(B_PFULL + pb), (j >> 1) & 1);
-                    mbar_wait(BAR(B_VFULL + pb), (j >> 1) & 1);
+                    mbar_wait_u(BAR(B_PFULL + pb), (j >> 1) & 1);
+                    mbar_wait_u(BAR(B_VFULL + pb), (j >> 1) & 1);
                     fence_after();
                     uint64_t ad = make_desc(smem_u32(sP) + (uint32_t)pb * PB, 128u * 16u, 128u);
                     uint64_t bd = make_desc(smem_u32(sV) + (uint32_t)pb * KB, p.v_lbo, p.v_sbo);

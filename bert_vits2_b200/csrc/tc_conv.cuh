@@ -247,6 +247,41 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(done) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
     if (!done) mbar_wait_slow(bar, parity);
 }
+// Bounded wait for the MMA-issuer warps, written as ONE asm block (no C++ control flow on a per-thread result, no call).
+// Why: ptxas keeps the issuer's descriptors / loop state in uniform registers and updates them with UIADD3 only while the
+// surrounding code is provably warp-uniform and free of calls (uniform registers do not survive a call).  mbar_wait() above
+// branches on a per-thread predicate into a noinline function with printf: every value that is live across it is demoted to
+// vector registers and each UTCHMMA then needs an ELECT + 5x R2UR.BROADCAST chain that re-uses one uniform-register set --
+// measured 180-570 cycles per MMA in k_g2_conv against the 64-cycle tensor time of an N = 128 MMA (profiles/r02_g2_issue.md).
+// Same timeout protocol as mbar_wait_slow (error flags raised, wait abandoned), minus the printf.
+__device__ __forceinline__ void mbar_wait_u(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 n, e;\n\t.reg .u64 t0, t1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "mov.u64 t0, %%clock64;\n\t"
+        "mov.u32 n, 0;\n"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "and.b32 e, n, 15;\n\t"
+        "setp.ne.u32 p, e, 0;\n\t"
+        "@p bra WAIT_%=;\n\t"
+        "ld.volatile.global.u32 e, [%3];\n\t"
+        "setp.ne.u32 p, e, 0;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "mov.u64 t1, %%clock64;\n\t"
+        "sub.u64 t1, t1, t0;\n\t"
+        "setp.lt.u64 p, t1, 4000000000;\n\t"
+        "@p bra WAIT_%=;\n\t"
+        "st.volatile.global.u32 [%3], 1;\n\t"
+        "ld.global.u64 t1, [%4];\n\t"
+        "setp.ne.u64 p, t1, 0;\n\t"
+        "@p st.volatile.global.u32 [t1], 1;\n"
+        "DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity), "r"(1000000u), "l"(&g_tc_err_dev), "l"(&g_tc_err_flag) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -269,6 +304,19 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+// tcgen05.mma / tcgen05.commit with the lane election inside the asm block (statement stays in warp-uniform control flow)
+template <int F16>
+__device__ __forceinline__ void umma_el(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (F16)
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_el(uint32_t bar) {
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -288,9 +336,9 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
 }
 template <int F16>
 __device__ __forceinline__ void umma_e(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if (elect_one()) umma<F16>(tmem_d, adesc, bdesc, idesc, accumulate);
+    umma_el<F16>(tmem_d, adesc, bdesc, idesc, accumulate);
 }
-__device__ __forceinline__ void umma_commit_e(uint32_t bar) { if (elect_one()) umma_commit(bar); }
+__device__ __forceinline__ void umma_commit_e(uint32_t bar) { umma_commit_el(bar); }
 // nk accumulating k-steps on one accumulator, unrolled for the common counts: a rolled loop re-uses one uniform-register set for the
 // descriptors and serialises every UTCHMMA behind the R2UR round trip of its predecessor (~190 cycles per MMA of any size, round 2)
 template <int F16, int NK>
@@ -300,14 +348,12 @@ __device__ __forceinline__ void umma_ksteps_n(uint32_t d, uint64_t ad, uint64_t 
 }
 template <int F16>
 __device__ __forceinline__ void umma_ksteps(uint32_t d, uint64_t ad, uint64_t bd, uint64_t a_kstep, uint64_t b_kstep, uint32_t idesc, int nk, uint32_t acc_first) {
-    switch (nk) {
-        case 1: umma_ksteps_n<F16, 1>(d, ad, bd, a_kstep, b_kstep, idesc, acc_first); break;
-        case 2: umma_ksteps_n<F16, 2>(d, ad, bd, a_kstep, b_kstep, idesc, acc_first); break;
-        case 4: umma_ksteps_n<F16, 4>(d, ad, bd, a_kstep, b_kstep, idesc, acc_first); break;
-        case 8: umma_ksteps_n<F16, 8>(d, ad, bd, a_kstep, b_kstep, idesc, acc_first); break;
-        default:
-            for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_e<F16>(d, ad, bd, idesc, kk ? 1u : acc_first);
-    }
+    // at most three alternatives: with four or more the compiler builds a jump table (BRX on a vector register) and ptxas then treats
+    // everything after it as divergent, which takes the descriptors out of the uniform datapath (see mbar_wait_u)
+    if (nk == 2) umma_ksteps_n<F16, 2>(d, ad, bd, a_kstep, b_kstep, idesc, acc_first);
+    else if (nk == 4) umma_ksteps_n<F16, 4>(d, ad, bd, a_kstep, b_kstep, idesc, acc_first);
+    else
+        for (int kk = 0; kk < nk; kk++, ad += a_kstep, bd += b_kstep) umma_e<F16>(d, ad, bd, idesc, kk ? 1u : acc_first);
 }
 // round-to-nearest (ties away) TF32 with two integer instructions: identical bits to cvt.rna.tf32.f32 for finite inputs,
 // but issued on the ALU pipe (round 1 ncu: the cvt saturated the XU pipe at 94-98 % in the operand prologue)
@@ -662,7 +708,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
             }
         }
     } else if (warp == 1) {
-        {  // all 32 lanes run the issue loop convergently; elect_one() guards the MMAs / commits
+        {  // all 32 lanes run the issue loop convergently; uniform-register issue path: mbar_wait_u + in-asm election (see mbar_wait_u)
             // ===== MMA issuer: per weight tile, MT x KC/(2G) tcgen05.mma (M=128, N=nt), always accumulating.
             // Descriptors are advanced with 64-bit adds on the (addr >> 4) field: this single thread is the issue
             // bottleneck for narrow N, so the loop body is kept to a handful of integer instructions.
@@ -670,16 +716,16 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
             const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R), b_kstep = (uint64_t)(2u * (uint32_t)nt);  // two channel groups per MMA
             const int nk = p.KC / (2 * G);
             int wi = 0;
-            mbar_wait(BAR(B_INIT), 0);
+            mbar_wait_u(BAR(B_INIT), 0);
             fence_after();
             for (int c = 0; c < p.nchunks; c++) {
                 const int sa = c % NAS;
-                mbar_wait(BAR(B_AREADY + sa), (c / NAS) & 1);
+                mbar_wait_u(BAR(B_AREADY + sa), (c / NAS) & 1);
                 fence_after();
                 const uint64_t a_desc0 = make_desc(smem_u32(sA + (size_t)sa * p.a_stage_bytes) + p.a_op_off, a_lbo, 128u);
                 for (int j = 0; j < p.K; j++, wi++) {
                     const int sw = wi % p.nws;
-                    mbar_wait(BAR(B_WFULL + sw), (wi / p.nws) & 1);
+                    mbar_wait_u(BAR(B_WFULL + sw), (wi / p.nws) & 1);
                     fence_after();
                     const uint64_t b_desc0 = make_desc(smem_u32(sW + (size_t)sw * p.w_stage_bytes), b_lbo, 128u);
                     for (int mt = 0; mt < MT; mt++) {
@@ -797,17 +843,17 @@ __global__ void __launch_bounds__(320, OCC) k_tc_conv1d_persist(TcParams p, int 
         }
     } else if (warp == 1) {
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        {  // all 32 lanes run the issue loop convergently; elect_one() guards the MMAs / commits
+        {  // all 32 lanes run the issue loop convergently; uniform-register issue path: mbar_wait_u + in-asm election (see mbar_wait_u)
             const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)nt * 16u;
             const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R), b_kstep = (uint64_t)(2u * (uint32_t)nt);
             const uint64_t b_tap = (uint64_t)((uint32_t)ncg * nt);  // next tap's weight tile, in 16-byte units
             const int nk = p.KC / (2 * G);
             const uint64_t b_desc0 = make_desc(smem_u32(sWt), b_lbo, 128u);
-            mbar_wait(BAR(B_WFULL), 0);
+            mbar_wait_u(BAR(B_WFULL), 0);
             for (int i = 0; i < n_mine; i++) {
                 const int sa = i % NAS, ab = i & 1;
-                mbar_wait(BAR(B_INIT + ab), (i >> 1) & 1);
-                mbar_wait(BAR(B_AREADY + sa), (i / NAS) & 1);
+                mbar_wait_u(BAR(B_INIT + ab), (i >> 1) & 1);
+                mbar_wait_u(BAR(B_AREADY + sa), (i / NAS) & 1);
                 fence_after();
                 const uint64_t a_desc0 = make_desc(smem_u32(sA + (size_t)sa * p.a_stage_bytes) + p.a_op_off, a_lbo, 128u);
                 const uint32_t d = tmem + (uint32_t)(ab * nt);
@@ -965,24 +1011,24 @@ __global__ void __launch_bounds__(352, 1) k_tc_conv1d_pstream(TcParams p, int mt
         }
     } else if (warp == 1) {
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        {  // all 32 lanes run the issue loop convergently; elect_one() guards the MMAs / commits
+        {  // all 32 lanes run the issue loop convergently; uniform-register issue path: mbar_wait_u + in-asm election (see mbar_wait_u)
             const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)nt * 16u;
             const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R), b_kstep = (uint64_t)(2u * (uint32_t)nt);
             const int nk = p.KC / (2 * G);
             int wi = 0, s_ = 0;
             for (int i = 0; i < n_mine; i++) {
                 const int ab = i & 1;
-                mbar_wait(BAR(B_INIT + ab), (i >> 1) & 1);
+                mbar_wait_u(BAR(B_INIT + ab), (i >> 1) & 1);
                 fence_after();
                 const uint32_t d0 = tmem + (uint32_t)(ab * MT * nt);
                 for (int c = 0; c < NCH; c++, s_++) {
                     const int sa = s_ % NAS;
-                    mbar_wait(BAR(B_AREADY + sa), (s_ / NAS) & 1);
+                    mbar_wait_u(BAR(B_AREADY + sa), (s_ / NAS) & 1);
                     fence_after();
                     const uint64_t a_desc0 = make_desc(smem_u32(sA + (size_t)sa * p.a_stage_bytes) + p.a_op_off, a_lbo, 128u);
                     for (int j = 0; j < p.K; j++, wi++) {
                         const int sw = wi % NWS;
-                        mbar_wait(BAR(B_WFULL + sw), (wi / NWS) & 1);
+                        mbar_wait_u(BAR(B_WFULL + sw), (wi / NWS) & 1);
                         fence_after();
                         const uint64_t bd0 = make_desc(smem_u32(sW + (size_t)sw * p.w_stage_bytes), b_lbo, 128u);
                         for (int mt = 0; mt < MT; mt++) {
@@ -1141,15 +1187,15 @@ __global__ void __launch_bounds__(320, 2) k_tc_pair_persist(TcPairPParams p) {
         }
     } else if (warp == 1) {
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        {  // all 32 lanes run the issue loop convergently; elect_one() guards the MMAs / commits
+        {  // all 32 lanes run the issue loop convergently; uniform-register issue path: mbar_wait_u + in-asm election (see mbar_wait_u)
             const uint32_t b_lbo = (uint32_t)C * 16u;
             const uint64_t b_kstep = (uint64_t)(2u * (uint32_t)C);
             const int nk = C / (2 * G);
             const uint32_t tap_bytes = (uint32_t)C * (uint32_t)C * (F16 ? 2u : 4u);
-            mbar_wait(BAR(B_W), 0);
+            mbar_wait_u(BAR(B_W), 0);
             auto conv2 = [&](int i) {  // D2[i&1] += conv2(XT[i&1])
                 const int buf = i & 1;
-                mbar_wait(BAR(B_XTFULL + buf), (i >> 1) & 1);
+                mbar_wait_u(BAR(B_XTFULL + buf), (i >> 1) & 1);
                 fence_after();
                 const uint64_t xt0 = make_desc(smem_u32(sXT + (size_t)buf * p.xt_bytes), (uint32_t)RT * 16u, 128u);
                 const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)RT);
@@ -1163,8 +1209,8 @@ __global__ void __launch_bounds__(320, 2) k_tc_pair_persist(TcPairPParams p) {
             };
             for (int i = 0; i < ntl; i++) {
                 const int sa = i % NAS, buf = i & 1;
-                mbar_wait(BAR(B_AREADY + sa), (i / NAS) & 1);
-                mbar_wait(BAR(B_D1EMPTY + buf), ((i >> 1) & 1) ^ 1);
+                mbar_wait_u(BAR(B_AREADY + sa), (i / NAS) & 1);
+                mbar_wait_u(BAR(B_D1EMPTY + buf), ((i >> 1) & 1) ^ 1);
                 fence_after();
                 const uint64_t a0 = make_desc(smem_u32(sA + (size_t)sa * p.a_stage_bytes) + p.a_op_off, (uint32_t)R * 16u, 128u);
                 const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R);

@@ -74,7 +74,7 @@ __device__ __forceinline__ void g2_issue_stage(uint32_t d0, uint32_t a_lo0, uint
                 const uint32_t d = d0 + (uint32_t)(mt0 + u) * nt, a_lo = a_lo0 + (uint32_t)(mt0 + u) * 128u;
 #pragma unroll
                 for (int kk = 0; kk < NK; kk++)
-                    if (tc::elect_one()) tc::umma<1>(d, hi | (a_lo + kk * a_kstep), hi | (b_lo0 + kk * b_kstep), idesc, kk ? 1u : acc0);
+                    tc::umma_el<1>(d, hi | (a_lo + kk * a_kstep), hi | (b_lo0 + kk * b_kstep), idesc, kk ? 1u : acc0);
             }
         }
     }
@@ -83,7 +83,7 @@ __device__ __forceinline__ void g2_issue_stage(uint32_t d0, uint32_t a_lo0, uint
 __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // shfl: warp-uniform for the compiler
     const int NAS = p.nas, NWS = p.nws, NG = p.NG, MG = p.MG, NCH = p.nchunks, nt = p.nt, R = p.R;
     const int t0 = blockIdx.x * NG * MG * 128, ntile = blockIdx.y, n0 = ntile * nt, b = blockIdx.z;
     long long* prof = p.prof ? p.prof + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
         const uint32_t a_kstep = 2u * (uint32_t)R, b_kstep = 2u * (uint32_t)nt;
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
         const int nk = p.KC / 16;
-        if (p.resident) { mbar_wait(BAR(B_WFULL), 0); fence_after(); }
-        mbar_wait(BAR(B_INIT), 0);  // accumulators hold the bias: every MMA accumulates
+        if (p.resident) { mbar_wait_u(BAR(B_WFULL), 0); fence_after(); }
+        mbar_wait_u(BAR(B_INIT), 0);  // accumulators hold the bias: every MMA accumulates
         fence_after();
         int wi = 0, s = 0;
         long long waitA = 0, waitW = 0;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
             for (int c = 0; c < NCH; c++, s++) {
                 const int sa = s % NAS;
                 long long c0 = prof ? clock64() : 0;
-                mbar_wait(BAR(B_AFULL + sa), (s / NAS) & 1);
+                mbar_wait_u(BAR(B_AFULL + sa), (s / NAS) & 1);
                 fence_after();
                 if (prof) { waitA += clock64() - c0; if (s == 0 && lane == 0) { prof[3] = gtime(); prof[10] = clock64(); } }
                 const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa * p.a_stage_bytes) & 0x3ffffu) >> 4) | a_lo_c;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
                     } else {
                         sw = wi % NWS;
                         c0 = prof ? clock64() : 0;
-                        mbar_wait(BAR(B_WFULL + sw), (wi / NWS) & 1);
+                        mbar_wait_u(BAR(B_WFULL + sw), (wi / NWS) & 1);
                         fence_after();
                         if (prof) waitW += clock64() - c0;
                         b_lo0 = ((smem_u32(sW + (size_t)sw * p.w_stage_bytes) & 0x3ffffu) >> 4) | b_lo_c;
@@ -202,13 +202,13 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
                             uint32_t a_lo = a_lo0 + (uint32_t)(mt * 128 + j * p.dil), b_lo = b_lo0;
                             const uint32_t d = tm + (uint32_t)((g * MG + mt) * nt);
                             for (int kk = 0; kk < nk; kk++, a_lo += a_kstep, b_lo += b_kstep)
-                                if (elect_one()) umma<1>(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, p.idesc, kk ? 1u : acc0);
+                                umma_el<1>(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, p.idesc, kk ? 1u : acc0);
                         }
-                    if (!p.resident && !p.dbg_skip_wcommit && elect_one()) umma_commit(BAR(B_WEMPTY + sw));
+                    if (!p.resident && !p.dbg_skip_wcommit) umma_commit_el(BAR(B_WEMPTY + sw));
                 }
-                if (elect_one()) umma_commit(BAR(B_AEMPTY + sa));
+                umma_commit_el(BAR(B_AEMPTY + sa));
             }
-            if (elect_one()) umma_commit(BAR(B_ACC + g));
+            umma_commit_el(BAR(B_ACC + g));
         }
         if (prof && lane == 0) { prof[4] = gtime(); prof[8] = waitA; prof[9] = waitW; prof[11] = clock64(); prof[12] = (long long)NG * NCH * p.K * MG * nk; }
     } else if (warp >= 4) {
