@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
     fence_before();
     __syncthreads();
     fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // shfl: a warp-uniform value for ptxas (uniform registers in the MMA issuer)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 

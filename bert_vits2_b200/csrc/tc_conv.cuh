@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
     fence_before();
     __syncthreads();
     fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // shfl: a warp-uniform value for ptxas (uniform registers in the MMA issuer)
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the
     // previous kernel in the stream; from here on this grid reads activations that kernel produced.
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(320, OCC) k_tc_conv1d_persist(TcParams p, int 
     fence_before();
     __syncthreads();
     fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // shfl: a warp-uniform value for ptxas (uniform registers in the MMA issuer)
     const int n_mine = (ntiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
 
     if (warp == 0) {
@@ -953,7 +953,7 @@ __global__ void __launch_bounds__(352, 1) k_tc_conv1d_pstream(TcParams p, int mt
     fence_before();
     __syncthreads();
     fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // shfl: a warp-uniform value for ptxas (uniform registers in the MMA issuer)
     const int n_mine = (tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     // tile -> (batch, m tile, n tile); n tile fastest
     auto decode = [&](int i, int& b, int& t0, int& ntile) {
@@ -1151,7 +1151,7 @@ __global__ void __launch_bounds__(320, 2) k_tc_pair_persist(TcPairPParams p) {
     fence_before();
     __syncthreads();
     fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // shfl: a warp-uniform value for ptxas (uniform registers in the MMA issuer)
     const int ntl = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA
     // tile i of this CTA -> (batch, first output row)
     auto tile_bt = [&](int i, int& b, int& t0) {

@@ -46,6 +46,9 @@ struct G2Params {
     int residual, accumulate, ups_u, ups_cout;
     float out_scale;
     int dbg_skip_wcommit;  // probes only: no weight-stage commits (valid only when every weight stage fits the ring)
+    int dbg_flags;         // probes only (timing studies, wrong results): 1 = no tap shift (aligned A operand), 2 = no tcgen05.fence after the stage waits,
+                           // 4 = no TMA traffic after the first ring fill (stale operands re-used: isolates shared-memory contention), 8 = epilogue warps
+                           // park in nanosleep polling instead of the hinted try_wait
     long long* prof;  // probes only: per-CTA timestamps [grid][16] (globaltimer ns / clock64 sums); nullptr in the engine
 };
 
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
             const int g = s / NCH, c = s - g * NCH, sa = s % NAS;
             const int row0 = t0 + g * MG * 128 - p.pad;
             const int nrows = max(0, min(R, p.T + G2_PADR - row0));  // never read past the tensor's halo; rows beyond feed discarded outputs only
+            if ((p.dbg_flags & 4) && s >= NAS) continue;
             if (lane == 0) {
                 mbar_wait(BAR(B_AEMPTY + sa), ((s / NAS) & 1) ^ 1);
                 mbar_expect_tx(BAR(B_AFULL + sa), (uint32_t)nrows * 16u * (uint32_t)ncg);
@@ -151,6 +155,7 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
                 for (int g = 0; g < NG; g++)
                     for (int cj = 0; cj < NCH * p.K; cj++, wi++) {
                         const int sw = wi % NWS;
+                        if ((p.dbg_flags & 4) && wi >= NWS) continue;
                         mbar_wait(BAR(B_WEMPTY + sw), ((wi / NWS) & 1) ^ 1);
                         mbar_expect_tx(BAR(B_WFULL + sw), p.w_stage_bytes);
                         bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), wt + (size_t)cj * p.w_stage_bytes, p.w_stage_bytes, BAR(B_WFULL + sw));
@@ -168,6 +173,7 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
         const uint32_t a_kstep = 2u * (uint32_t)R, b_kstep = 2u * (uint32_t)nt;
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
         const int nk = p.KC / 16;
+        const int tapstep = (p.dbg_flags & 1) ? 0 : p.dil;
         if (p.resident) { mbar_wait_u(BAR(B_WFULL), 0); fence_after(); }
         mbar_wait_u(BAR(B_INIT), 0);  // accumulators hold the bias: every MMA accumulates
         fence_after();
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
             for (int c = 0; c < NCH; c++, s++) {
                 const int sa = s % NAS;
                 long long c0 = prof ? clock64() : 0;
-                mbar_wait_u(BAR(B_AFULL + sa), (s / NAS) & 1);
+                if (!((p.dbg_flags & 4) && s >= NAS)) mbar_wait_u(BAR(B_AFULL + sa), (s / NAS) & 1);
                 fence_after();
                 if (prof) { waitA += clock64() - c0; if (s == 0 && lane == 0) { prof[3] = gtime(); prof[10] = clock64(); } }
                 const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa * p.a_stage_bytes) & 0x3ffffu) >> 4) | a_lo_c;
@@ -189,14 +195,14 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
                     } else {
                         sw = wi % NWS;
                         c0 = prof ? clock64() : 0;
-                        mbar_wait_u(BAR(B_WFULL + sw), (wi / NWS) & 1);
-                        fence_after();
+                        if (!((p.dbg_flags & 4) && wi >= NWS)) mbar_wait_u(BAR(B_WFULL + sw), (wi / NWS) & 1);
+                        if (!(p.dbg_flags & 2)) fence_after();
                         if (prof) waitW += clock64() - c0;
                         b_lo0 = ((smem_u32(sW + (size_t)sw * p.w_stage_bytes) & 0x3ffffu) >> 4) | b_lo_c;
                     }
                     const uint32_t acc0 = 1u;
-                    if (nk == 2) g2_issue_stage<2>(tm + (uint32_t)(g * MG * nt), a_lo0 + (uint32_t)(j * p.dil), b_lo0, a_kstep, b_kstep, desc_hi, (uint32_t)nt, MG, p.idesc, acc0);
-                    else if (nk == 1) g2_issue_stage<1>(tm + (uint32_t)(g * MG * nt), a_lo0 + (uint32_t)(j * p.dil), b_lo0, a_kstep, b_kstep, desc_hi, (uint32_t)nt, MG, p.idesc, acc0);
+                    if (nk == 2) g2_issue_stage<2>(tm + (uint32_t)(g * MG * nt), a_lo0 + (uint32_t)(j * tapstep), b_lo0, a_kstep, b_kstep, desc_hi, (uint32_t)nt, MG, p.idesc, acc0);
+                    else if (nk == 1) g2_issue_stage<1>(tm + (uint32_t)(g * MG * nt), a_lo0 + (uint32_t)(j * tapstep), b_lo0, a_kstep, b_kstep, desc_hi, (uint32_t)nt, MG, p.idesc, acc0);
                     else
                         for (int mt = 0; mt < MG; mt++) {
                             uint32_t a_lo = a_lo0 + (uint32_t)(mt * 128 + j * p.dil), b_lo = b_lo0;
@@ -250,7 +256,13 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
         const bool scaled = p.out_scale != 1.f;
         for (int g = 0; g < NG; g++) {
-            mbar_wait(BAR(B_ACC + g), 0);
+            if (p.dbg_flags & 8) {
+                uint32_t done = 0;
+                while (!done) {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(BAR(B_ACC + g)), "r"(0u) : "memory");
+                    if (!done) __nanosleep(2000);
+                }
+            } else mbar_wait(BAR(B_ACC + g), 0);
             fence_after();
             if (prof && e == 0 && lane == 0 && g == 0) prof[5] = gtime();
             if (prof && e == 0 && lane == 0 && g == NG - 1) prof[6] = gtime();
@@ -379,6 +391,7 @@ struct G2Epi {
     int st_override = 0;      // probes: force the super-tile size (m-tiles per CTA)
     long long* prof = nullptr;  // probes: per-CTA timestamps
     int dbg_skip_wcommit = 0;
+    int dbg_flags = 0;
 };
 
 // Static part of the plan (fixed at weight-pack time): N tile and K chunk for a conv with `cols` output columns.
@@ -394,7 +407,7 @@ inline void g2_conv(const TcConvW& w, const float* bias, const H8& x, const H8& 
     p.x = x.p; p.y = y.p; p.w = w.w; p.bias = bias; p.bias_b = e.bias_b; p.bias_b_stride = e.bias_b_stride;
     p.x_cg = x.C / 8; p.x_Tp = x.Tp; p.y_cg = y.C / 8; p.y_Tp = y.Tp;
     if (e.res) { BV2_CHECK(!w.ups_u && e.res->C == y.C && e.res->T == y.T && e.res->B == y.B, "g2_conv residual"); p.res = e.res->p; p.res_cg = e.res->C / 8; p.res_Tp = e.res->Tp; p.residual = 1; }
-    p.accumulate = e.accumulate; p.out_scale = e.out_scale; p.ups_u = w.ups_u; p.ups_cout = w.ups_cout; p.prof = e.prof;
+    p.accumulate = e.accumulate; p.out_scale = e.out_scale; p.ups_u = w.ups_u; p.ups_cout = w.ups_cout; p.prof = e.prof; p.dbg_flags = e.dbg_flags;
     if (w.ups_u) BV2_CHECK(w.ups_cout % 8 == 0 && !e.accumulate, "g2_conv ups");
     p.T = x.T; p.K = w.K; p.dil = e.dil; p.pad = (w.K - 1) / 2 * e.dil;
     BV2_CHECK(p.pad <= G2_PADL && p.pad <= G2_PADR, "g2_conv padding exceeds the tensor halo");

@@ -102,6 +102,7 @@ static int run_conv(int Cin, int Cout, int K, int dil, int T, int B, bool res, b
         cudaEvent_t a, c; cudaEventCreate(&a); cudaEventCreate(&c);
         e.accumulate = 0;
         e.dbg_skip_wcommit = getenv("G2_SKIP_WCOMMIT") ? 1 : 0;
+        e.dbg_flags = getenv("G2_DBG") ? atoi(getenv("G2_DBG")) : 0;
         if (getenv("G2_PROF")) {  // per-CTA phase timeline of the last of three back-to-back launches
             long long* dprof = (long long*)dalloc(4096 * 16 * 8);
             cudaMemset(dprof, 0, 4096 * 16 * 8);

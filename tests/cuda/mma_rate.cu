@@ -313,11 +313,71 @@ static void run_waiters(long long* d, int nmma) {
             }
 }
 
+
+// Descriptor-update / tap-shift study on the uniform-register issue path (umma_el, no per-thread control flow): 8 unrolled MMAs per
+// iteration; slot u uses A start = a_base + u * shift rows (the tap shift of a dilated conv) and B k-step u & 3.
+// UPD = 0: descriptors are loop-invariant per slot; UPD = 1: both bases advance by a runtime step every iteration (UIADD3 updates of
+// the uniform registers feeding UTCHMMA).  commit = 1: a tcgen05.commit + fence after every 4 MMAs (one weight stage of k_g2_conv).
+template <int UPD>
+__global__ void __launch_bounds__(128, 1) k_desc(int N, int nmma, int shift, int step, int commit, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar, bar2;
+    __shared__ uint32_t tslot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 64 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); mbar_init(smem_u32(&bar2), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem(); fence_before(); __syncthreads(); fence_after();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tslot, 0);
+    if (warp == 1) {
+        const uint32_t idesc = make_idesc(1, N), R = 320;
+        const uint64_t hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;
+        const uint32_t a0 = ((smem_u32(smem) & 0x3ffffu) >> 4) | (((R * 16u) >> 4) << 16), b0 = ((smem_u32(smem + 40 * 1024) & 0x3ffffu) >> 4) | ((((uint32_t)N * 16u) >> 4) << 16);
+        uint32_t aoff = 0, boff = 0;
+        const uint32_t bar2a = smem_u32(&bar2);
+        long long t0 = clock64();
+        for (int i = 0; i < nmma; i += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                umma_el<1>(tmem, hi | (a0 + aoff + (uint32_t)(u * shift)), hi | (b0 + boff + (uint32_t)((u & 3) * 2 * N)), idesc, 1u);
+                if (commit && (u & 3) == 3) { umma_commit_el(bar2a); fence_after(); }
+            }
+            if (UPD) { aoff = (aoff + (uint32_t)step) & 63u; boff = (boff + (uint32_t)step) & 15u; }
+        }
+        long long t1 = clock64();
+        umma_commit_el(smem_u32(&bar));
+        mbar_wait_u(smem_u32(&bar), 0);
+        long long t2 = clock64();
+        if (lane == 0) { out[blockIdx.x * 2] = t1 - t0; out[blockIdx.x * 2 + 1] = t2 - t0; }
+    }
+    fence_before(); __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+template <int UPD>
+static void run_desc(long long* d, int nmma) {
+    cudaFuncSetAttribute(k_desc<UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    for (int N : {16, 64, 128})
+        for (int shift : {0, 1, 5, 8})
+            for (int commit : {0, 1}) {
+                k_desc<UPD><<<148, 128, 64 * 1024>>>(N, nmma, shift, 1, commit, d);
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("desc: CUDA error %s\n", cudaGetErrorString(e)); exit(1); }
+                long long h[296]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+                double a = 0, b = 0; for (int i = 0; i < 148; i++) { a += h[2 * i]; b += h[2 * i + 1]; }
+                printf("  desc study: %s N=%3d tap-shift=%d rows commit/4=%d : issue %.1f  complete %.1f cycles per MMA\n", UPD ? "bases updated per iteration" : "loop-invariant descriptors ", N, shift, commit,
+                       a / 148 / nmma, b / 148 / nmma);
+            }
+}
+
 int main() {
     cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
     int* flag = tc_init_device(); (void)flag;
     long long* d; cudaMalloc(&d, 148 * 2 * 8);
     const int nmma = 512;
+    if (getenv("MMA_RATE_DESC")) { run_desc<0>(d, 2048); run_desc<1>(d, 2048); return 0; }
     run_issue<0>(d, 2048); run_issue<1>(d, 2048); run_issue<2>(d, 2048);
     if (getenv("MMA_RATE_WAITERS")) { run_waiters(d, 2048); return 0; }
     if (getenv("MMA_RATE_STREAM")) { run_stream<0>(d, 2048); run_stream<1>(d, 2048); return 0; }
