@@ -252,7 +252,7 @@ struct bv2_engine {
             L.relv = upload(W(a + ".emb_rel_v").data);
             L.n1 = ln_from(name + ".norm_layers_1." + std::to_string(i));
             L.f1 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_1", false, tc_mode, 128, 64);
-            L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2", false, tc_mode, tune_env("BV2_F2_NT", 32), 64);
+            L.f2 = conv_from(name + ".ffn_layers." + std::to_string(i) + ".conv_2", false, tc_mode, tc_mode == 2 ? tune_env("BV2_F2_NT", H) : 32, tc_mode == 2 ? 32 : 64);  // FP16 flow: one N tile (LayerNorm tail)
             L.n2 = ln_from(name + ".norm_layers_2." + std::to_string(i));
             e.layers.push_back(L);
         }
@@ -677,6 +677,14 @@ void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const fl
             ws.release(mk);
             ConvArgs a1; a1.in_mask = 1; a1.act = 1; a1.lens = lens;
             conv(L.f1, x, f, s, a1, 0, 0, true);
+            if (L.f2.tc.nt == H) {
+                // x = norm_2(x + ffn(x)): conv_2 on one full-width N tile, residual pre-loaded into the accumulator, LayerNorm in the tail
+                // (rows t >= len skip the reference's y * x_mask; they only ever feed masked positions and are zeroed by the last layer)
+                ConvArgs a2; a2.in_mask = 1; a2.lens = lens; a2.res = x.p; a2.res_mode = 1; a2.res_C_total = H; a2.out_mask = i == nl - 1 ? 1 : 0;
+                tc_ln = &L.n2;
+                conv(L.f2, f, x, s, a2, 0, 0, true);
+                continue;
+            }
             ConvArgs a2; a2.in_mask = 1; a2.out_mask = 1; a2.lens = lens;
             conv(L.f2, f, y, s, a2, 0, 0, true);
             layernorm(L.n2, x, y.p, x, s, 0, nullptr, lens, i == nl - 1 ? 1 : 0);

@@ -695,16 +695,17 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
             }
         } else if (lane == 0) {
             // ===== weight producer: its own thread so the weight ring runs ahead across chunk boundaries
-            int wi = 0;
-            const float* wtile = p.w + (size_t)z * p.w_zstride + (size_t)blockIdx.y * p.nchunks * p.K * (p.w_stage_bytes / 4);
-            for (int c = 0; c < p.nchunks; c++) {
-                for (int j = 0; j < p.K; j++, wi++) {
-                    const int sw = wi % p.nws;
-                    mbar_wait(BAR(B_WEMPTY + sw), ((wi / p.nws) & 1) ^ 1);
-                    mbar_expect_tx(BAR(B_WFULL + sw), p.w_stage_bytes);
-                    bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), wtile + ((size_t)c * p.K + j) * (p.w_stage_bytes / 4), p.w_stage_bytes,
-                             BAR(B_WFULL + sw));
-                }
+            // slot / parity / addresses carried incrementally (one stage per ~20 instructions: the producer has to out-run the MMA issuer)
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w + (size_t)z * p.w_zstride + (size_t)blockIdx.y * p.nchunks * p.K * (p.w_stage_bytes / 4));
+            const uint32_t bar_wf = BAR(B_WFULL), bar_we = BAR(B_WEMPTY), dst0 = smem_u32(sW), nws_u = (uint32_t)p.nws;
+            uint32_t sw = 0, ph = 1u, dst = dst0;
+            const int nst = p.nchunks * p.K;
+            for (int i = 0; i < nst; i++, src += p.w_stage_bytes) {
+                mbar_wait_u(bar_we + 8u * sw, ph);
+                mbar_expect_tx(bar_wf + 8u * sw, p.w_stage_bytes);
+                bulk_g2s(dst, src, p.w_stage_bytes, bar_wf + 8u * sw);
+                dst += p.w_stage_bytes;
+                if (++sw == nws_u) { sw = 0; ph ^= 1u; dst = dst0; }
             }
         }
     } else if (warp == 1) {
@@ -715,27 +716,31 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
             const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)nt * 16u;
             const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R), b_kstep = (uint64_t)(2u * (uint32_t)nt);  // two channel groups per MMA
             const int nk = p.KC / (2 * G);
-            int wi = 0;
             mbar_wait_u(BAR(B_INIT), 0);
             fence_after();
+            // ring slot / parity / descriptor state carried incrementally: no runtime division or multiply per stage (see tc_gen.cuh)
+            const uint64_t a_stage16 = (uint64_t)(p.a_stage_bytes >> 4), w_stage16 = (uint64_t)(p.w_stage_bytes >> 4);
+            const uint64_t a_desc_base = make_desc(smem_u32(sA) + p.a_op_off, a_lbo, 128u), b_desc_base = make_desc(smem_u32(sW), b_lbo, 128u);
+            const uint32_t bar_ar = BAR(B_AREADY), bar_ae = BAR(B_AEMPTY), bar_wf = BAR(B_WFULL), bar_we = BAR(B_WEMPTY);
+            const uint32_t nas_u = (uint32_t)NAS, nws_u = (uint32_t)p.nws;
+            uint32_t sa = 0, aph = 0, sw = 0, wph = 0;
+            uint64_t a_cur = a_desc_base, b_cur = b_desc_base;
             for (int c = 0; c < p.nchunks; c++) {
-                const int sa = c % NAS;
-                mbar_wait_u(BAR(B_AREADY + sa), (c / NAS) & 1);
+                mbar_wait_u(bar_ar + 8u * sa, aph);
                 fence_after();
-                const uint64_t a_desc0 = make_desc(smem_u32(sA + (size_t)sa * p.a_stage_bytes) + p.a_op_off, a_lbo, 128u);
-                for (int j = 0; j < p.K; j++, wi++) {
-                    const int sw = wi % p.nws;
-                    mbar_wait_u(BAR(B_WFULL + sw), (wi / p.nws) & 1);
+                uint64_t a_tap = a_cur;
+                for (int j = 0; j < p.K; j++, a_tap += (uint64_t)(uint32_t)p.dil) {
+                    mbar_wait_u(bar_wf + 8u * sw, wph);
                     fence_after();
-                    const uint64_t b_desc0 = make_desc(smem_u32(sW + (size_t)sw * p.w_stage_bytes), b_lbo, 128u);
-                    for (int mt = 0; mt < MT; mt++) {
-                        uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(mt * 128 + j * p.dil), bd = b_desc0;
-                        const uint32_t d = tmem + (uint32_t)(mt * nt);
-                        umma_ksteps<F16>(d, ad, bd, a_kstep, b_kstep, p.idesc, nk, 1u);
-                    }
-                    umma_commit_e(BAR(B_WEMPTY + sw));
+                    for (int mt = 0; mt < MT; mt++)
+                        umma_ksteps<F16>(tmem + (uint32_t)(mt * nt), a_tap + (uint64_t)(uint32_t)(mt * 128), b_cur, a_kstep, b_kstep, p.idesc, nk, 1u);
+                    umma_commit_e(bar_we + 8u * sw);
+                    b_cur += w_stage16;
+                    if (++sw == nws_u) { sw = 0; wph ^= 1u; b_cur = b_desc_base; }
                 }
-                umma_commit_e(BAR(B_AEMPTY + sa));
+                umma_commit_e(bar_ae + 8u * sa);
+                a_cur += a_stage16;
+                if (++sa == nas_u) { sa = 0; aph ^= 1u; a_cur = a_desc_base; }
             }
             umma_commit_e(BAR(B_ACC));
         }
@@ -996,16 +1001,19 @@ __global__ void __launch_bounds__(352, 1) k_tc_conv1d_pstream(TcParams p, int mt
             const int steps = n_mine * NCH;
             int wi = 0;
             const size_t wstage_f = p.w_stage_bytes / 4;
+            const uint32_t bar_wf = BAR(B_WFULL), bar_we = BAR(B_WEMPTY), dst0 = smem_u32(sW), nws_u = (uint32_t)NWS;
+            uint32_t sw = 0, ph = 1u, dst = dst0;
             for (int s_ = 0; s_ < steps; s_++) {
                 int b, t0, ntile;
                 decode(s_ / NCH, b, t0, ntile);
                 const int c = s_ % NCH;
                 const float* wsrc = p.w + ((size_t)ntile * NCH + c) * p.K * wstage_f;
                 for (int j = 0; j < p.K; j++, wi++) {
-                    const int sw = wi % NWS;
-                    mbar_wait(BAR(B_WEMPTY + sw), ((wi / NWS) & 1) ^ 1);
-                    mbar_expect_tx(BAR(B_WFULL + sw), p.w_stage_bytes);
-                    bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), wsrc + (size_t)j * wstage_f, p.w_stage_bytes, BAR(B_WFULL + sw));
+                    mbar_wait_u(bar_we + 8u * sw, ph);
+                    mbar_expect_tx(bar_wf + 8u * sw, p.w_stage_bytes);
+                    bulk_g2s(dst, wsrc + (size_t)j * wstage_f, p.w_stage_bytes, bar_wf + 8u * sw);
+                    dst += p.w_stage_bytes;
+                    if (++sw == nws_u) { sw = 0; ph ^= 1u; dst = dst0; }
                 }
             }
         }
@@ -1015,30 +1023,33 @@ __global__ void __launch_bounds__(352, 1) k_tc_conv1d_pstream(TcParams p, int mt
             const uint32_t a_lbo = (uint32_t)R * 16u, b_lbo = (uint32_t)nt * 16u;
             const uint64_t a_kstep = (uint64_t)(2u * (uint32_t)R), b_kstep = (uint64_t)(2u * (uint32_t)nt);
             const int nk = p.KC / (2 * G);
-            int wi = 0, s_ = 0;
+            const uint64_t a_stage16 = (uint64_t)(p.a_stage_bytes >> 4), w_stage16 = (uint64_t)(p.w_stage_bytes >> 4);
+            const uint64_t a_desc_base = make_desc(smem_u32(sA) + p.a_op_off, a_lbo, 128u), b_desc_base = make_desc(smem_u32(sW), b_lbo, 128u);
+            const uint32_t bar_ar = BAR(B_AREADY), bar_ae = BAR(B_AEMPTY), bar_wf = BAR(B_WFULL), bar_we = BAR(B_WEMPTY);
+            const uint32_t nas_u = (uint32_t)NAS, nws_u = (uint32_t)NWS;
+            uint32_t sa = 0, aph = 0, sw = 0, wph = 0;
+            uint64_t a_cur = a_desc_base, b_cur = b_desc_base;
             for (int i = 0; i < n_mine; i++) {
                 const int ab = i & 1;
                 mbar_wait_u(BAR(B_INIT + ab), (i >> 1) & 1);
                 fence_after();
                 const uint32_t d0 = tmem + (uint32_t)(ab * MT * nt);
-                for (int c = 0; c < NCH; c++, s_++) {
-                    const int sa = s_ % NAS;
-                    mbar_wait_u(BAR(B_AREADY + sa), (s_ / NAS) & 1);
+                for (int c = 0; c < NCH; c++) {
+                    mbar_wait_u(bar_ar + 8u * sa, aph);
                     fence_after();
-                    const uint64_t a_desc0 = make_desc(smem_u32(sA + (size_t)sa * p.a_stage_bytes) + p.a_op_off, a_lbo, 128u);
-                    for (int j = 0; j < p.K; j++, wi++) {
-                        const int sw = wi % NWS;
-                        mbar_wait_u(BAR(B_WFULL + sw), (wi / NWS) & 1);
+                    uint64_t a_tap = a_cur;
+                    for (int j = 0; j < p.K; j++, a_tap += (uint64_t)(uint32_t)p.dil) {
+                        mbar_wait_u(bar_wf + 8u * sw, wph);
                         fence_after();
-                        const uint64_t bd0 = make_desc(smem_u32(sW + (size_t)sw * p.w_stage_bytes), b_lbo, 128u);
-                        for (int mt = 0; mt < MT; mt++) {
-                            uint64_t ad = a_desc0 + (uint64_t)(uint32_t)(mt * 128 + j * p.dil), bd = bd0;
-                            const uint32_t d = d0 + (uint32_t)(mt * nt);
-                            umma_ksteps<F16>(d, ad, bd, a_kstep, b_kstep, p.idesc, nk, 1u);
-                        }
-                        umma_commit_e(BAR(B_WEMPTY + sw));
+                        for (int mt = 0; mt < MT; mt++)
+                            umma_ksteps<F16>(d0 + (uint32_t)(mt * nt), a_tap + (uint64_t)(uint32_t)(mt * 128), b_cur, a_kstep, b_kstep, p.idesc, nk, 1u);
+                        umma_commit_e(bar_we + 8u * sw);
+                        b_cur += w_stage16;
+                        if (++sw == nws_u) { sw = 0; wph ^= 1u; b_cur = b_desc_base; }
                     }
-                    umma_commit_e(BAR(B_AEMPTY + sa));
+                    umma_commit_e(bar_ae + 8u * sa);
+                    a_cur += a_stage16;
+                    if (++sa == nas_u) { sa = 0; aph ^= 1u; a_cur = a_desc_base; }
                 }
                 umma_commit_e(BAR(B_ACC + ab));
             }

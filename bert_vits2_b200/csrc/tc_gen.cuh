@@ -151,15 +151,21 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
                 for (uint32_t off = 0; off < total; off += 32768u)
                     bulk_g2s(smem_u32(sW) + off, wt + off, min(32768u, total - off), BAR(B_WFULL));
             } else {
+                // slot / parity / addresses carried incrementally (the producer has to out-run the MMA issuer: no division, no call)
+                const uint32_t bar_wf = BAR(B_WFULL), bar_we = BAR(B_WEMPTY), dst0 = smem_u32(sW), nws_u = (uint32_t)NWS;
+                uint32_t sw = 0, ph = 1u, dst = dst0;
                 int wi = 0;
-                for (int g = 0; g < NG; g++)
-                    for (int cj = 0; cj < NCH * p.K; cj++, wi++) {
-                        const int sw = wi % NWS;
+                for (int g = 0; g < NG; g++) {
+                    const uint8_t* src = wt;
+                    for (int cj = 0; cj < NCH * p.K; cj++, wi++, src += p.w_stage_bytes) {
                         if ((p.dbg_flags & 4) && wi >= NWS) continue;
-                        mbar_wait(BAR(B_WEMPTY + sw), ((wi / NWS) & 1) ^ 1);
-                        mbar_expect_tx(BAR(B_WFULL + sw), p.w_stage_bytes);
-                        bulk_g2s(smem_u32(sW + (size_t)sw * p.w_stage_bytes), wt + (size_t)cj * p.w_stage_bytes, p.w_stage_bytes, BAR(B_WFULL + sw));
+                        mbar_wait_u(bar_we + 8u * sw, ph);
+                        mbar_expect_tx(bar_wf + 8u * sw, p.w_stage_bytes);
+                        bulk_g2s(dst, src, p.w_stage_bytes, bar_wf + 8u * sw);
+                        dst += p.w_stage_bytes;
+                        if (++sw == nws_u) { sw = 0; ph ^= 1u; dst = dst0; }
                     }
+                }
             }
         }
     } else if (warp == 1) {
@@ -173,46 +179,55 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
         const uint32_t a_kstep = 2u * (uint32_t)R, b_kstep = 2u * (uint32_t)nt;
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
         const int nk = p.KC / 16;
-        const int tapstep = (p.dbg_flags & 1) ? 0 : p.dil;
+        const uint32_t tapstep = (p.dbg_flags & 1) ? 0u : (uint32_t)p.dil;
         if (p.resident) { mbar_wait_u(BAR(B_WFULL), 0); fence_after(); }
         mbar_wait_u(BAR(B_INIT), 0);  // accumulators hold the bias: every MMA accumulates
         fence_after();
-        int wi = 0, s = 0;
+        // Ring slots, parities, barrier addresses and descriptor words are carried incrementally (adds and compares only): the first
+        // uniform-path version recomputed slot = i % n, parity = (i / n) & 1 and the descriptor bases per stage -- ~120 dependent
+        // uniform/ALU instructions (integer division by a runtime value) in front of every 2-8 MMAs, which ncu's source view showed as the
+        // whole MMA phase (tensor pipe active 21 %, no single stall site: profiles/r02c_g2_c128k11_ncu.md).
+        const uint32_t a_stage16 = p.a_stage_bytes >> 4, w_stage16 = p.w_stage_bytes >> 4;
+        const uint32_t a_lo_base = ((smem_u32(sA) & 0x3ffffu) >> 4) | a_lo_c, w_lo_base = ((smem_u32(sW) & 0x3ffffu) >> 4) | b_lo_c;
+        const uint32_t bar_af = BAR(B_AFULL), bar_ae = BAR(B_AEMPTY), bar_wf = BAR(B_WFULL), bar_we = BAR(B_WEMPTY);
+        const uint32_t nas_u = (uint32_t)NAS, nws_u = (uint32_t)NWS, gcols = (uint32_t)(MG * nt);
+        const bool streamed = !p.resident, wcommit = streamed && !p.dbg_skip_wcommit, nostale = !(p.dbg_flags & 4);
+        uint32_t sa = 0, aph = 0, a_cur = a_lo_base;   // activation ring slot, parity, descriptor low word of the slot
+        uint32_t sw = 0, wph = 0, w_cur = w_lo_base;   // weight ring (streamed) / tap cursor (resident)
+        uint32_t dg = tm;
+        int s = 0, wi = 0;
         long long waitA = 0, waitW = 0;
-        for (int g = 0; g < NG; g++) {
+        for (int g = 0; g < NG; g++, dg += gcols) {
+            if (!streamed) w_cur = w_lo_base;
             for (int c = 0; c < NCH; c++, s++) {
-                const int sa = s % NAS;
                 long long c0 = prof ? clock64() : 0;
-                if (!((p.dbg_flags & 4) && s >= NAS)) mbar_wait_u(BAR(B_AFULL + sa), (s / NAS) & 1);
+                if (nostale || s < NAS) mbar_wait_u(bar_af + 8u * sa, aph);
                 fence_after();
                 if (prof) { waitA += clock64() - c0; if (s == 0 && lane == 0) { prof[3] = gtime(); prof[10] = clock64(); } }
-                const uint32_t a_lo0 = ((smem_u32(sA + (size_t)sa * p.a_stage_bytes) & 0x3ffffu) >> 4) | a_lo_c;
-                for (int j = 0; j < p.K; j++, wi++) {
-                    uint32_t b_lo0;
-                    int sw = 0;
-                    if (p.resident) {
-                        b_lo0 = ((smem_u32(sW + (size_t)(c * p.K + j) * p.w_stage_bytes) & 0x3ffffu) >> 4) | b_lo_c;
-                    } else {
-                        sw = wi % NWS;
+                uint32_t a_tap = a_cur;
+                for (int j = 0; j < p.K; j++, wi++, a_tap += tapstep) {
+                    if (streamed) {
                         c0 = prof ? clock64() : 0;
-                        if (!((p.dbg_flags & 4) && wi >= NWS)) mbar_wait_u(BAR(B_WFULL + sw), (wi / NWS) & 1);
+                        if (nostale || wi < NWS) mbar_wait_u(bar_wf + 8u * sw, wph);
                         if (!(p.dbg_flags & 2)) fence_after();
                         if (prof) waitW += clock64() - c0;
-                        b_lo0 = ((smem_u32(sW + (size_t)sw * p.w_stage_bytes) & 0x3ffffu) >> 4) | b_lo_c;
                     }
-                    const uint32_t acc0 = 1u;
-                    if (nk == 2) g2_issue_stage<2>(tm + (uint32_t)(g * MG * nt), a_lo0 + (uint32_t)(j * tapstep), b_lo0, a_kstep, b_kstep, desc_hi, (uint32_t)nt, MG, p.idesc, acc0);
-                    else if (nk == 1) g2_issue_stage<1>(tm + (uint32_t)(g * MG * nt), a_lo0 + (uint32_t)(j * tapstep), b_lo0, a_kstep, b_kstep, desc_hi, (uint32_t)nt, MG, p.idesc, acc0);
+                    if (nk == 2) g2_issue_stage<2>(dg, a_tap, w_cur, a_kstep, b_kstep, desc_hi, (uint32_t)nt, MG, p.idesc, 1u);
+                    else if (nk == 1) g2_issue_stage<1>(dg, a_tap, w_cur, a_kstep, b_kstep, desc_hi, (uint32_t)nt, MG, p.idesc, 1u);
                     else
                         for (int mt = 0; mt < MG; mt++) {
-                            uint32_t a_lo = a_lo0 + (uint32_t)(mt * 128 + j * p.dil), b_lo = b_lo0;
-                            const uint32_t d = tm + (uint32_t)((g * MG + mt) * nt);
+                            uint32_t a_lo = a_tap + (uint32_t)(mt * 128), b_lo = w_cur;
+                            const uint32_t d = dg + (uint32_t)(mt * nt);
                             for (int kk = 0; kk < nk; kk++, a_lo += a_kstep, b_lo += b_kstep)
-                                umma_el<1>(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, p.idesc, kk ? 1u : acc0);
+                                umma_el<1>(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, p.idesc, 1u);
                         }
-                    if (!p.resident && !p.dbg_skip_wcommit) umma_commit_el(BAR(B_WEMPTY + sw));
+                    if (wcommit) umma_commit_el(bar_we + 8u * sw);
+                    w_cur += w_stage16;
+                    if (streamed && ++sw == nws_u) { sw = 0; wph ^= 1u; w_cur = w_lo_base; }
                 }
-                umma_commit_el(BAR(B_AEMPTY + sa));
+                umma_commit_el(bar_ae + 8u * sa);
+                a_cur += a_stage16;
+                if (++sa == nas_u) { sa = 0; aph ^= 1u; a_cur = a_lo_base; }
             }
             umma_commit_el(BAR(B_ACC + g));
         }
