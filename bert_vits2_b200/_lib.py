@@ -82,7 +82,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with _lock:
         if not force and not needs_build():
             return LIB_PATH
-        cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB_PATH] + SOURCES
+        tmp = LIB_PATH + ".tmp"  # link to a temporary name, then rename: a reader never sees a half-written library
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-o", tmp] + SOURCES
         if os.environ.get("BV2_BUILD_TUNING"):  # development builds: BV2_* environment knobs of the probes become active (tc_conv.cuh tune_env)
             cmd.insert(1, "-DBV2_TUNING")
         if verbose:
@@ -90,6 +91,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        os.replace(tmp, LIB_PATH)
         if verbose:
             print(r.stderr)
         return LIB_PATH

@@ -79,6 +79,19 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     cfg.attrs = attr; cfg.numAttrs = pdl_env ? 1 : 0;
     BV2_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
 }
+// Same, with a thread-block cluster of cluster_x CTAs along x (grid.x must be a multiple of cluster_x)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)cluster_x; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 2;
+    BV2_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

@@ -14,6 +14,12 @@
 // recomputes Q.K^T, exponentiates against the final maximum and feeds P.V -- no accumulator rescaling, i.e. no TMEM
 // read-modify-write in the MMA dependency chain, at the price of 12 extra (cheap, overlapped) MMAs per key tile.
 //
+// Key split (B = 1 leaves only 2 heads x F/128 query tiles = 16 CTAs for 148 SMs, each walking every key tile twice): a cluster of
+// ks CTAs shares a query tile, CTA r handles key tiles r, r + ks, ... with its OWN running maximum, and the partial results
+// (m_r, l_r, relative-value weights, unnormalised P.V rows) are merged flash-decoding style over distributed shared memory:
+//     m = max_r m_r,  w_r = 2^((m_r - m) log2 e),  out = (sum_r w_r O_r + sum_r w_r prel_r . Ev) / sum_r w_r l_r
+// Each CTA parks its partial rows in its own shared memory (the K/V stages are free by then), one cluster barrier, CTA c pulls
+// rows [c*128/ks, (c+1)*128/ks) of every peer (ld.shared::cluster) in fixed rank order -- deterministic -- and writes them.
 // 192 threads: warp 0 TMA producer (Q once, K tiles twice, V tiles once), warp 1 TMEM allocator + MMA issuer,
 // warps 2-5 softmax / epilogue (one thread per query row).
 #pragma once
@@ -27,6 +33,7 @@ struct AttnParams {
     const float* rel_k; const float* rel_v;  // [2w+1][dk]
     const int* lens;    // valid length per batch (keys >= len excluded, query rows >= len produce zeros)
     int B, T, H, heads, window;
+    int ks;             // key split: a cluster of ks CTAs shares one 128-query tile, CTA r takes key tiles r, r + ks, ... (1 = no cluster)
     uint32_t idesc_qk, idesc_pv, v_lbo, v_sbo;
 };
 
@@ -59,7 +66,8 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
     enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_SEMPTY = 11, B_PFULL = 13, B_PEMPTY = 15, B_OFULL = 17, NBARS = 18 };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NBARS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int KS = p.ks, rk = (int)blockIdx.x % KS;  // cluster dims (KS,1,1): rank in cluster == blockIdx.x % KS
+    const int q0 = ((int)blockIdx.x / KS) * 128, h = blockIdx.y, b = blockIdx.z;
     const int H8 = p.H / 8;
     const int w = p.window, nrel = 2 * w + 1;
 
@@ -88,7 +96,8 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int len = min(p.lens ? p.lens[b] : p.T, p.T);
-    const int NT = q0 < len ? (len + KT - 1) / KT : 0;  // key tiles that hold at least one valid key
+    const int NT_all = q0 < len ? (len + KT - 1) / KT : 0;  // key tiles that hold at least one valid key (same for the whole cluster)
+    const int NT = NT_all > rk ? (NT_all - rk + KS - 1) / KS : 0;  // ... of which this CTA takes tiles rk, rk + KS, ...
     const uint4* qbase = p.qkv + ((size_t)b * 3 * H8 + (size_t)h * NG) * p.T;
     const uint4* kbase = qbase + (size_t)H8 * p.T;
     const uint4* vbase = kbase + (size_t)H8 * p.T;
@@ -100,7 +109,7 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
             __syncwarp();
             if (lane < NG) bulk_g2s(smem_u32(sQ) + (uint32_t)lane * 128u * 16u, qbase + (size_t)lane * p.T + q0, (uint32_t)nq * 16u, BAR(B_QFULL));
             for (int s = 0; s < 2 * NT; s++) {
-                const int j = s < NT ? s : s - NT, k0 = j * KT, nk = min(KT, p.T - k0), st = s & 1;
+                const int j = s < NT ? s : s - NT, k0 = (rk + KS * j) * KT, nk = min(KT, p.T - k0), st = s & 1;
                 if (lane == 0) {
                     mbar_wait(BAR(B_KEMPTY + st), ((s >> 1) & 1) ^ 1);
                     mbar_expect_tx(BAR(B_KFULL + st), (uint32_t)nk * 16u * NG);
@@ -159,10 +168,15 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
         const int q = warp & 3, m = q * 32 + lane, i = q0 + m;
         const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
         uint4* obase = p.att + ((size_t)b * H8 + (size_t)h * NG) * p.T;
-        if (NT == 0) {  // every query of this tile is padding: zeros
-            if (i < p.T)
+        if (NT_all == 0) {  // every query of this tile is padding: zeros (written once per cluster)
+            if (i < p.T && rk == 0)
                 for (int g = 0; g < NG; g++) obase[(size_t)g * p.T + i] = make_uint4(0u, 0u, 0u, 0u);
         } else {
+            float M = -INFINITY, L = 0.f;
+            float prel[NREL];
+#pragma unroll
+            for (int r = 0; r < NREL; r++) prel[r] = 0.f;
+            if (NT > 0) {
             // ---- relative-key logits of this row: qrel[r] = q_i . Ek[r]
             float qrel[NREL];
 #pragma unroll
@@ -184,10 +198,9 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
 #pragma unroll
                 for (int r = 0; r < NREL; r++) v = (r == d) ? qrel[r] : v;
                 return v; };
-            // ---- pass A: row maximum over the valid keys
-            float M = -INFINITY;
+            // ---- pass A: row maximum over the valid keys (of this CTA's key tiles)
             for (int s = 0; s < NT; s++) {
-                const int st = s & 1, k0 = s * KT, nvalid = len - k0;
+                const int st = s & 1, k0 = (rk + KS * s) * KT, nvalid = len - k0;
                 const bool band = (k0 <= q0 + 127 + w) && (k0 + KT - 1 >= q0 - w);
                 mbar_wait(BAR(B_SFULL + st), (s >> 1) & 1);
                 fence_after();
@@ -214,12 +227,8 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
             }
             // ---- pass B: p = exp(s - M) -> FP16 operand image in shared memory; row sum; relative-value weights
             const float M2 = M * LOG2E;
-            float L = 0.f;
-            float prel[NREL];
-#pragma unroll
-            for (int r = 0; r < NREL; r++) prel[r] = 0.f;
             for (int j = 0; j < NT; j++) {
-                const int s = NT + j, st = s & 1, pb = j & 1, k0 = j * KT, nvalid = len - k0;
+                const int s = NT + j, st = s & 1, pb = j & 1, k0 = (rk + KS * j) * KT, nvalid = len - k0;
                 const bool band = (k0 <= q0 + 127 + w) && (k0 + KT - 1 >= q0 - w);
                 mbar_wait(BAR(B_SFULL + st), (s >> 1) & 1);
                 mbar_wait(BAR(B_PEMPTY + pb), ((j >> 1) & 1) ^ 1);
@@ -262,9 +271,29 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                 mbar_arrive(BAR(B_PFULL + pb));
                 mbar_arrive(BAR(B_SEMPTY + st));
             }
-            // ---- epilogue: out = (P.V + sum_r p_rel[r] Ev[r]) / L  -> 16-bit c8 (the operand image of conv_o)
-            mbar_wait(BAR(B_OFULL), 0);
+            mbar_wait(BAR(B_OFULL), 0);  // every MMA of this CTA has completed: O is final, the K/V/P stages are free
             fence_after();
+            }  // NT > 0
+            if (KS > 1) {
+                // ---- park this CTA's partial row in its own shared memory (the K stages): [27 float4][128 rows]
+                //      slots 0..23 unnormalised P.V (96 channels), 24 = (m, l, prel0, prel1), 25 = prel2..5, 26 = prel6..8
+                float4* part = reinterpret_cast<float4*>(sK);
+                for (int c0 = 0; c0 < DK; c0 += 32) {
+                    uint32_t v[32];
+                    if (NT > 0) { tmem_ld32(trow + (uint32_t)(2 * KT + c0), v); tmem_wait_ld(); }
+                    else {
+#pragma unroll
+                        for (int e = 0; e < 32; e++) v[e] = 0u;
+                    }
+#pragma unroll
+                    for (int g = 0; g < 8; g++)
+                        part[(size_t)(c0 / 4 + g) * 128 + m] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+                }
+                part[(size_t)24 * 128 + m] = make_float4(M, L, prel[0], prel[1]);
+                part[(size_t)25 * 128 + m] = make_float4(prel[2], prel[3], prel[4], prel[5]);
+                part[(size_t)26 * 128 + m] = make_float4(prel[6], prel[7], prel[8], 0.f);
+            } else {
+            // ---- epilogue: out = (P.V + sum_r p_rel[r] Ev[r]) / L  -> 16-bit c8 (the operand image of conv_o)
             const float inv = (i < len && L > 0.f) ? 1.f / L : 0.f;
             for (int c0 = 0; c0 < DK; c0 += 32) {
                 uint32_t v[32];
@@ -292,7 +321,93 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                     }
                 }
             }
+            }  // KS == 1
         }
+    }
+    if (KS > 1 && NT_all > 0) {
+        // ---- merge the key splits (every thread of every CTA of the cluster takes part in both barriers)
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        // CTA rk merges rows [rk * 128/KS, (rk + 1) * 128/KS); KS threads share a row (96/KS channels each), consecutive lanes take
+        // consecutive rows (coalesced distributed-shared-memory reads)
+        if (warp >= 2) {
+            const int t = (warp - 2) * 32 + lane, rows_per = 128 / KS;
+            const int m = rk * rows_per + t % rows_per, part = t / rows_per, i = q0 + m;
+            const int nf4 = 24 / KS;  // float4 slots (4 channels each) of this thread: 12 (KS = 2) or 6 (KS = 4)
+            const uint32_t local = smem_u32(sK) + (uint32_t)m * 16u;
+            float Mr[4], wr[4];
+            float M = -INFINITY;
+#pragma unroll
+            for (int r2 = 0; r2 < 4; r2++) {
+                Mr[r2] = -INFINITY;
+                if (r2 < KS) {
+                    uint32_t remote;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local + 24u * 2048u), "r"(r2));
+                    float4 s4;
+                    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w) : "r"(remote));
+                    Mr[r2] = s4.x; M = fmaxf(M, s4.x);
+                }
+            }
+            float L = 0.f;
+            float prel[NREL];
+#pragma unroll
+            for (int r = 0; r < NREL; r++) prel[r] = 0.f;
+            float o[48];
+#pragma unroll
+            for (int e = 0; e < 48; e++) o[e] = 0.f;
+#pragma unroll
+            for (int r2 = 0; r2 < 4; r2++) {  // fixed rank order: deterministic
+                wr[r2] = 0.f;
+                if (r2 < KS) {
+                    const float wgt = Mr[r2] == -INFINITY ? 0.f : ex2_approx((Mr[r2] - M) * LOG2E);
+                    wr[r2] = wgt;
+                    uint32_t remote;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r2));
+                    float4 a4, b4, c4;
+                    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(remote + 24u * 2048u));
+                    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(remote + 25u * 2048u));
+                    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w) : "r"(remote + 26u * 2048u));
+                    L = fmaf(wgt, a4.y, L);
+                    prel[0] = fmaf(wgt, a4.z, prel[0]); prel[1] = fmaf(wgt, a4.w, prel[1]);
+                    prel[2] = fmaf(wgt, b4.x, prel[2]); prel[3] = fmaf(wgt, b4.y, prel[3]); prel[4] = fmaf(wgt, b4.z, prel[4]); prel[5] = fmaf(wgt, b4.w, prel[5]);
+                    prel[6] = fmaf(wgt, c4.x, prel[6]); prel[7] = fmaf(wgt, c4.y, prel[7]); prel[8] = fmaf(wgt, c4.z, prel[8]);
+                    const uint32_t rbase = remote + (uint32_t)(part * nf4) * 2048u;
+#pragma unroll
+                    for (int g = 0; g < 12; g++) {
+                        if (g < nf4) {
+                            float4 v4;
+                            asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v4.x), "=f"(v4.y), "=f"(v4.z), "=f"(v4.w) : "r"(rbase + (uint32_t)g * 2048u));
+                            o[4 * g] = fmaf(wgt, v4.x, o[4 * g]); o[4 * g + 1] = fmaf(wgt, v4.y, o[4 * g + 1]);
+                            o[4 * g + 2] = fmaf(wgt, v4.z, o[4 * g + 2]); o[4 * g + 3] = fmaf(wgt, v4.w, o[4 * g + 3]);
+                        }
+                    }
+                }
+            }
+            const float inv = (i < len && L > 0.f) ? 1.f / L : 0.f;
+            const int ch0 = part * nf4 * 4;  // first channel of this thread
+#pragma unroll
+            for (int r = 0; r < NREL; r++) {
+                if (r < nrel) {
+                    const float pw = prel[r];
+                    const float* ev = &sEv[r * DK + ch0];
+#pragma unroll
+                    for (int e = 0; e < 48; e++)
+                        if (e < 4 * nf4) o[e] = fmaf(pw, ev[e], o[e]);
+                }
+            }
+            if (i < p.T) {
+                uint4* obase = p.att + ((size_t)b * H8 + (size_t)h * NG) * p.T;
+#pragma unroll
+                for (int g = 0; g < 6; g++) {
+                    if (2 * g < nf4) {
+                        uint4 u;
+                        u.x = pack_h2(o[8 * g] * inv, o[8 * g + 1] * inv); u.y = pack_h2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
+                        u.z = pack_h2(o[8 * g + 4] * inv, o[8 * g + 5] * inv); u.w = pack_h2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
+                        obase[(size_t)(ch0 / 8 + g) * p.T + i] = u;
+                    }
+                }
+            }
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");  // peers are done reading this CTA's rows
     }
     fence_before();
     __syncthreads();
@@ -313,7 +428,7 @@ inline void tc_flow_attn_init_device() {
 
 // qkv16: 16-bit c8 tensor with C = 3H channels (Act.p reinterpreted); att16: 16-bit c8 tensor with C = H channels.
 inline void tc_flow_attn(const Act& qkv16, const Act& att16, const float* rel_k, const float* rel_v, const int* lens, int heads, int window,
-                         cudaStream_t st, AttnMnConv mn = AttnMnConv()) {
+                         cudaStream_t st, AttnMnConv mn = AttnMnConv(), int num_sms = 148, int ks_override = 0) {
     const int H = att16.C, dk = H / heads, KT = 128;
     BV2_CHECK(qkv16.C == 3 * H && dk == 96 && H % 8 == 0 && window <= 4 && qkv16.T == att16.T && qkv16.B == att16.B, "tc_flow_attn shapes (head dim 96, window <= 4)");
     AttnParams p{};
@@ -324,7 +439,14 @@ inline void tc_flow_attn(const Act& qkv16, const Act& att16, const float* rel_k,
     p.idesc_pv = tc::make_idesc(1, dk) | (1u << 16);  // b_major = MN
     const uint32_t kblk = 128u, nblk = (uint32_t)KT * 16u;
     p.v_lbo = mn.lbo_is_kblock ? kblk : nblk; p.v_sbo = mn.lbo_is_kblock ? nblk : kblk;
-    launch_pdl(k_flow_attn<96, 128>, dim3(cdiv(p.T, 128), heads, p.B), dim3(192), tc_flow_attn_smem(dk, KT), st, p);
+    // key split: as many CTAs per query tile as keep the grid within one wave of the SMs and leave each CTA at least one key tile
+    const int qtiles = cdiv(p.T, 128), ctas = qtiles * heads * p.B;
+    int ks = 1;
+    while (ks < 4 && 2 * ks <= qtiles && ctas * 2 * ks <= num_sms) ks *= 2;  // the merge is written for 2 or 4 splits
+    if (ks_override > 0) ks = ks_override;
+    p.ks = ks;
+    if (ks == 1) launch_pdl(k_flow_attn<96, 128>, dim3(qtiles, heads, p.B), dim3(192), tc_flow_attn_smem(dk, KT), st, p);
+    else launch_pdl_cluster(k_flow_attn<96, 128>, dim3(qtiles * ks, heads, p.B), dim3(192), tc_flow_attn_smem(dk, KT), st, ks, p);
 }
 
 }  // namespace bv2

@@ -62,24 +62,81 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 __device__ __forceinline__ float unlrelu10(float a) { return a >= 0.f ? a : a * 10.f; }
 }  // namespace tc
 
-// MMAs of one weight stage (chunk c, tap j): MG m-tiles x NK k-steps.  Unrolled in bodies of 4 m-tiles so that the compiler rotates the
-// uniform registers that carry descriptors into UTCHMMA: a rolled loop re-uses one register set and serialises every MMA behind the
-// R2UR round trip of its predecessor (measured: ~190 cycles per MMA of any size; the unrolled issue path runs at the 64-cycle floor of
-// an N = 128 MMA, tests/cuda/mma_rate.cu).
-template <int NK>
-__device__ __forceinline__ void g2_issue_stage(uint32_t d0, uint32_t a_lo0, uint32_t b_lo0, uint32_t a_kstep, uint32_t b_kstep, uint32_t desc_hi, uint32_t nt, int MG,
-                                               uint32_t idesc, uint32_t acc0) {
-    const uint64_t hi = (uint64_t)desc_hi << 32;
-    for (int mt0 = 0; mt0 < MG; mt0 += 4) {
+// MMAs of one weight stage (chunk c, tap j): MG m-tiles x NK k-steps, both compile-time: the stage is straight-line code, every
+// UTCHMMA gets its own freshly computed uniform registers and nothing but independent UIADD3/UMOV sits between two MMAs.
+// (History, all measured with the in-kernel phase accounting of tests/cuda/g2_probe.cu, N = 128: per-thread issue path with an
+//  ELECT + R2UR waterfall per MMA 280-570 clk/MMA -> uniform registers 185 -> no runtime division per stage 162 -> this.  The uniform
+//  datapath issues one instruction at a time with ~10-cycle dependent latency: a guarded MMA (UISETP + BRA.U + address math) costs
+//  ~100 cycles of issuer time whatever its size, so loops over runtime MG with per-MMA predicates never reach the tensor rate.)
+template <int NK, int MG>
+__device__ __forceinline__ void g2_issue_stage(uint32_t d0, uint32_t a_lo0, uint32_t b_lo0, uint32_t a_kstep, uint32_t b_kstep, uint64_t hi, uint32_t nt, uint32_t idesc) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (mt0 + u < MG) {
-                const uint32_t d = d0 + (uint32_t)(mt0 + u) * nt, a_lo = a_lo0 + (uint32_t)(mt0 + u) * 128u;
+    for (int mt = 0; mt < MG; mt++) {
 #pragma unroll
-                for (int kk = 0; kk < NK; kk++)
-                    tc::umma_el<1>(d, hi | (a_lo + kk * a_kstep), hi | (b_lo0 + kk * b_kstep), idesc, kk ? 1u : acc0);
+        for (int kk = 0; kk < NK; kk++)
+            tc::umma_el<1>(d0 + (uint32_t)mt * nt, hi | (a_lo0 + (uint32_t)(mt * 128) + kk * a_kstep), hi | (b_lo0 + kk * b_kstep), idesc, 1u);
+    }
+}
+
+// State the MMA issuer carries through its loops (all warp-uniform)
+struct G2Issue {
+    uint32_t bar_af, bar_ae, bar_wf, bar_we, bar_acc;      // first barrier of each group
+    uint32_t a_lo_base, w_lo_base, a_stage16, w_stage16;   // descriptor low words of ring slot 0, slot strides (16-byte units)
+    uint32_t a_kstep, b_kstep, nt, idesc, tapstep, tm;
+    uint32_t nas, nws;
+    int NG, NCH, K, streamed, wcommit, nostale, nofence;
+    uint64_t hi;
+};
+
+// The issuer's loop nest for one (NK, MG) instantiation.  Ring slots, parities, barrier addresses and descriptor words are carried
+// incrementally (adds and compares only; an earlier version recomputed slot = i % n, parity = (i / n) & 1 per stage: ~120 dependent
+// instructions of runtime integer division in front of every 2-8 MMAs, profiles/r02c_g2_ncu_full.md).
+template <int NK, int MG>
+__device__ __forceinline__ void g2_issuer(const G2Issue& q, long long* prof, int lane) {
+    using namespace tc;
+    uint32_t sa = 0, aph = 0, a_cur = q.a_lo_base;   // activation ring slot, parity, descriptor low word of the slot
+    uint32_t sw = 0, wph = 0, w_cur = q.w_lo_base;   // weight ring (streamed) / tap cursor (resident)
+    uint32_t dg = q.tm;
+    int s = 0, wi = 0;
+    long long waitA = 0, waitW = 0;
+    for (int g = 0; g < q.NG; g++, dg += (uint32_t)MG * q.nt) {
+        if (!q.streamed) w_cur = q.w_lo_base;
+        for (int c = 0; c < q.NCH; c++, s++) {
+            long long c0 = prof ? clock64() : 0;
+            if (q.nostale || s < (int)q.nas) mbar_wait_u(q.bar_af + 8u * sa, aph);
+            fence_after();
+            if (prof) { waitA += clock64() - c0; if (s == 0 && lane == 0) { prof[3] = gtime(); prof[10] = clock64(); } }
+            uint32_t a_tap = a_cur;
+            for (int j = 0; j < q.K; j++, wi++, a_tap += q.tapstep) {
+                if (q.streamed) {
+                    c0 = prof ? clock64() : 0;
+                    if (q.nostale || wi < (int)q.nws) mbar_wait_u(q.bar_wf + 8u * sw, wph);
+                    if (!q.nofence) fence_after();
+                    if (prof) waitW += clock64() - c0;
+                }
+                g2_issue_stage<NK, MG>(dg, a_tap, w_cur, q.a_kstep, q.b_kstep, q.hi, q.nt, q.idesc);
+                if (q.wcommit) umma_commit_el(q.bar_we + 8u * sw);
+                w_cur += q.w_stage16;
+                if (q.streamed && ++sw == q.nws) { sw = 0; wph ^= 1u; w_cur = q.w_lo_base; }
             }
+            umma_commit_el(q.bar_ae + 8u * sa);
+            a_cur += q.a_stage16;
+            if (++sa == q.nas) { sa = 0; aph ^= 1u; a_cur = q.a_lo_base; }
         }
+        umma_commit_el(q.bar_acc + 8u * (uint32_t)g);
+    }
+    if (prof && lane == 0) { prof[4] = gtime(); prof[8] = waitA; prof[9] = waitW; prof[11] = clock64(); prof[12] = (long long)q.NG * q.NCH * q.K * MG * NK; }
+}
+// MG dispatch as a binary tree of two-way branches (a switch would become a jump table: BRX on a vector register makes ptxas treat
+// the code after it as divergent and takes the descriptors out of the uniform datapath)
+template <int NK>
+__device__ __forceinline__ void g2_issuer_mg(const G2Issue& q, int MG, long long* prof, int lane) {
+    if (MG <= 4) {
+        if (MG <= 2) { if (MG == 1) g2_issuer<NK, 1>(q, prof, lane); else g2_issuer<NK, 2>(q, prof, lane); }
+        else { if (MG == 3) g2_issuer<NK, 3>(q, prof, lane); else g2_issuer<NK, 4>(q, prof, lane); }
+    } else {
+        if (MG <= 6) { if (MG == 5) g2_issuer<NK, 5>(q, prof, lane); else g2_issuer<NK, 6>(q, prof, lane); }
+        else { if (MG == 7) g2_issuer<NK, 7>(q, prof, lane); else g2_issuer<NK, 8>(q, prof, lane); }
     }
 }
 
@@ -179,59 +236,19 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
         const uint32_t a_kstep = 2u * (uint32_t)R, b_kstep = 2u * (uint32_t)nt;
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
         const int nk = p.KC / 16;
-        const uint32_t tapstep = (p.dbg_flags & 1) ? 0u : (uint32_t)p.dil;
         if (p.resident) { mbar_wait_u(BAR(B_WFULL), 0); fence_after(); }
         mbar_wait_u(BAR(B_INIT), 0);  // accumulators hold the bias: every MMA accumulates
         fence_after();
-        // Ring slots, parities, barrier addresses and descriptor words are carried incrementally (adds and compares only): the first
-        // uniform-path version recomputed slot = i % n, parity = (i / n) & 1 and the descriptor bases per stage -- ~120 dependent
-        // uniform/ALU instructions (integer division by a runtime value) in front of every 2-8 MMAs, which ncu's source view showed as the
-        // whole MMA phase (tensor pipe active 21 %, no single stall site: profiles/r02c_g2_c128k11_ncu.md).
-        const uint32_t a_stage16 = p.a_stage_bytes >> 4, w_stage16 = p.w_stage_bytes >> 4;
-        const uint32_t a_lo_base = ((smem_u32(sA) & 0x3ffffu) >> 4) | a_lo_c, w_lo_base = ((smem_u32(sW) & 0x3ffffu) >> 4) | b_lo_c;
-        const uint32_t bar_af = BAR(B_AFULL), bar_ae = BAR(B_AEMPTY), bar_wf = BAR(B_WFULL), bar_we = BAR(B_WEMPTY);
-        const uint32_t nas_u = (uint32_t)NAS, nws_u = (uint32_t)NWS, gcols = (uint32_t)(MG * nt);
-        const bool streamed = !p.resident, wcommit = streamed && !p.dbg_skip_wcommit, nostale = !(p.dbg_flags & 4);
-        uint32_t sa = 0, aph = 0, a_cur = a_lo_base;   // activation ring slot, parity, descriptor low word of the slot
-        uint32_t sw = 0, wph = 0, w_cur = w_lo_base;   // weight ring (streamed) / tap cursor (resident)
-        uint32_t dg = tm;
-        int s = 0, wi = 0;
-        long long waitA = 0, waitW = 0;
-        for (int g = 0; g < NG; g++, dg += gcols) {
-            if (!streamed) w_cur = w_lo_base;
-            for (int c = 0; c < NCH; c++, s++) {
-                long long c0 = prof ? clock64() : 0;
-                if (nostale || s < NAS) mbar_wait_u(bar_af + 8u * sa, aph);
-                fence_after();
-                if (prof) { waitA += clock64() - c0; if (s == 0 && lane == 0) { prof[3] = gtime(); prof[10] = clock64(); } }
-                uint32_t a_tap = a_cur;
-                for (int j = 0; j < p.K; j++, wi++, a_tap += tapstep) {
-                    if (streamed) {
-                        c0 = prof ? clock64() : 0;
-                        if (nostale || wi < NWS) mbar_wait_u(bar_wf + 8u * sw, wph);
-                        if (!(p.dbg_flags & 2)) fence_after();
-                        if (prof) waitW += clock64() - c0;
-                    }
-                    if (nk == 2) g2_issue_stage<2>(dg, a_tap, w_cur, a_kstep, b_kstep, desc_hi, (uint32_t)nt, MG, p.idesc, 1u);
-                    else if (nk == 1) g2_issue_stage<1>(dg, a_tap, w_cur, a_kstep, b_kstep, desc_hi, (uint32_t)nt, MG, p.idesc, 1u);
-                    else
-                        for (int mt = 0; mt < MG; mt++) {
-                            uint32_t a_lo = a_tap + (uint32_t)(mt * 128), b_lo = w_cur;
-                            const uint32_t d = dg + (uint32_t)(mt * nt);
-                            for (int kk = 0; kk < nk; kk++, a_lo += a_kstep, b_lo += b_kstep)
-                                umma_el<1>(d, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, p.idesc, 1u);
-                        }
-                    if (wcommit) umma_commit_el(bar_we + 8u * sw);
-                    w_cur += w_stage16;
-                    if (streamed && ++sw == nws_u) { sw = 0; wph ^= 1u; w_cur = w_lo_base; }
-                }
-                umma_commit_el(bar_ae + 8u * sa);
-                a_cur += a_stage16;
-                if (++sa == nas_u) { sa = 0; aph ^= 1u; a_cur = a_lo_base; }
-            }
-            umma_commit_el(BAR(B_ACC + g));
-        }
-        if (prof && lane == 0) { prof[4] = gtime(); prof[8] = waitA; prof[9] = waitW; prof[11] = clock64(); prof[12] = (long long)NG * NCH * p.K * MG * nk; }
+        G2Issue q;
+        q.bar_af = BAR(B_AFULL); q.bar_ae = BAR(B_AEMPTY); q.bar_wf = BAR(B_WFULL); q.bar_we = BAR(B_WEMPTY); q.bar_acc = BAR(B_ACC);
+        q.a_lo_base = ((smem_u32(sA) & 0x3ffffu) >> 4) | a_lo_c; q.w_lo_base = ((smem_u32(sW) & 0x3ffffu) >> 4) | b_lo_c;
+        q.a_stage16 = p.a_stage_bytes >> 4; q.w_stage16 = p.w_stage_bytes >> 4;
+        q.a_kstep = a_kstep; q.b_kstep = b_kstep; q.nt = (uint32_t)nt; q.idesc = p.idesc; q.tapstep = (p.dbg_flags & 1) ? 0u : (uint32_t)p.dil; q.tm = tm;
+        q.nas = (uint32_t)NAS; q.nws = (uint32_t)NWS; q.NG = NG; q.NCH = NCH; q.K = p.K;
+        q.streamed = !p.resident; q.wcommit = q.streamed && !p.dbg_skip_wcommit; q.nostale = !(p.dbg_flags & 4); q.nofence = (p.dbg_flags & 2) ? 1 : 0;
+        q.hi = (uint64_t)desc_hi << 32;
+        if (nk == 2) g2_issuer_mg<2>(q, MG, prof, lane);
+        else g2_issuer_mg<1>(q, MG, prof, lane);  // g2_conv() admits KC = 16 or 32 only
     } else if (warp >= 4) {
         // ===== epilogue, 12 warps: TMEM lane quarter q = warp & 3; the 3 warps of a quarter share the (m-tile, 32-column batch) items
         // round-robin.  Two phases:
@@ -417,7 +434,7 @@ inline int g2_kc(int Cin) { return Cin >= 128 ? 32 : 16; }
 inline void g2_conv(const TcConvW& w, const float* bias, const H8& x, const H8& y, const G2Epi& e, cudaStream_t st, int num_sms) {
     const int u = w.ups_u ? w.ups_u : 1;
     BV2_CHECK(w.w && w.f16 && bias && x.B == y.B && y.T == x.T * u && x.C == w.Cin && (w.ups_u ? y.C == w.ups_cout : y.C == w.Cout), "g2_conv shapes");
-    BV2_CHECK(w.nt <= 128 && w.KC % 16 == 0 && w.KC <= 256 && x.C % 8 == 0 && y.C % 8 == 0, "g2_conv tiling");
+    BV2_CHECK(w.nt <= 128 && (w.KC == 16 || w.KC == 32) && x.C % 8 == 0 && y.C % 8 == 0, "g2_conv tiling (K chunk of 16 or 32 channels)");
     G2Params p{};
     p.x = x.p; p.y = y.p; p.w = w.w; p.bias = bias; p.bias_b = e.bias_b; p.bias_b_stride = e.bias_b_stride;
     p.x_cg = x.C / 8; p.x_Tp = x.Tp; p.y_cg = y.C / 8; p.y_Tp = y.Tp;
@@ -446,7 +463,7 @@ inline void g2_conv(const TcConvW& w, const float* bias, const H8& x, const H8& 
         int best_ng = 1, best_mg = ST; long long best_cost = -1;
         for (int ng : {4, 2, 1}) {
             const int mg = cdiv(ST, ng);
-            if (ng * mg > mgmax || ng > ST) continue;
+            if (ng * mg > mgmax || ng > ST || mg > 8) continue;  // the issuer is instantiated for MG <= 8
             const long long ctas = (long long)cdiv(mtiles, ng * mg) * x.B;
             const long long waves = (ctas + num_sms - 1) / num_sms;
             const long long cost = waves * ng * mg;  // m-tile slots per SM
@@ -456,6 +473,7 @@ inline void g2_conv(const TcConvW& w, const float* bias, const H8& x, const H8& 
     } else {
         while (MG > 1 && 2 * a_bytes(MG) + 4 * (size_t)p.w_stage_bytes + 1024 > budget) MG--;
     }
+    MG = std::min(MG, 8);
     p.NG = NG; p.MG = MG; p.R = MG * 128 + halo;
     p.a_stage_bytes = (uint32_t)a_bytes(MG);
     const int a_steps = NG * w.nchunks;

@@ -374,7 +374,7 @@ static int run_mn_probe() {
 
 // Fused flow attention (tc_attn.cuh) against a double-precision CPU evaluation of reference attentions.py:272-322 on the same
 // FP16-rounded q/k/v (banded relative-key logits, masked softmax, relative-value term).
-static int run_attn(int T, int B, std::vector<int> lens, int lbo_is_kblock, int iters) {
+static int run_attn(int T, int B, std::vector<int> lens, int lbo_is_kblock, int iters, int ks = 0) {
     const int H = 192, heads = 2, dk = 96, w = 4, nrel = 9;
     std::mt19937 rng(T * 7 + B);
     std::normal_distribution<float> nd(0.f, 1.f);
@@ -393,7 +393,7 @@ static int run_attn(int T, int B, std::vector<int> lens, int lbo_is_kblock, int 
     Act aq; aq.B = B; aq.C = 3 * H; aq.T = T; aq.p = (float*)dq;
     Act aa; aa.B = B; aa.C = H; aa.T = T; aa.p = (float*)da;
     AttnMnConv mn; mn.lbo_is_kblock = lbo_is_kblock;
-    tc_flow_attn(aq, aa, dek, dev_, dl, heads, w, 0, mn);
+    tc_flow_attn(aq, aa, dek, dev_, dl, heads, w, 0, mn, 148, ks);
     cudaError_t er = cudaDeviceSynchronize();
     if (er != cudaSuccess) { printf("CUDA error (attn): %s\n", cudaGetErrorString(er)); return 1; }
     std::vector<uint16_t> got((size_t)B * H * T);
@@ -432,13 +432,13 @@ static int run_attn(int T, int B, std::vector<int> lens, int lbo_is_kblock, int 
     float ms = 0;
     if (iters > 0) {
         cudaEvent_t a, c; cudaEventCreate(&a); cudaEventCreate(&c);
-        for (int i = 0; i < 3; i++) tc_flow_attn(aq, aa, dek, dev_, dl, heads, w, 0, mn);
+        for (int i = 0; i < 3; i++) tc_flow_attn(aq, aa, dek, dev_, dl, heads, w, 0, mn, 148, ks);
         cudaEventRecord(a);
-        for (int i = 0; i < iters; i++) tc_flow_attn(aq, aa, dek, dev_, dl, heads, w, 0, mn);
+        for (int i = 0; i < iters; i++) tc_flow_attn(aq, aa, dek, dev_, dl, heads, w, 0, mn, 148, ks);
         cudaEventRecord(c); cudaEventSynchronize(c); cudaEventElapsedTime(&ms, a, c); ms /= iters;
     }
     const bool ok = maxerr < 4e-3 * std::max(1.0, maxref) && maxerr == maxerr;
-    printf("%s ATTN T=%d B=%d len0=%d mn=%d : maxerr %.3e (ref max %.3f)", ok ? "PASS" : "FAIL", T, B, lens[0], lbo_is_kblock, maxerr, maxref);
+    printf("%s ATTN T=%d B=%d len0=%d mn=%d key-split=%d (0 = auto) : maxerr %.3e (ref max %.3f)", ok ? "PASS" : "FAIL", T, B, lens[0], lbo_is_kblock, ks, maxerr, maxref);
     if (iters > 0) printf("  | %.3f ms", ms);
     printf("\n"); fflush(stdout);
     cudaFree(dq); cudaFree(da); cudaFree(dl);
@@ -462,6 +462,13 @@ int main(int argc, char** argv) {
             fails += run_attn(1573, 1, {1573}, mn, perf ? 20 : 0);
             fails += run_attn(1024, 1, {1024}, mn, perf ? 20 : 0);
             fails += run_attn(800, 32, std::vector<int>(32, 640), mn, perf ? 10 : 0);
+            for (int ks : {1, 2, 4}) {  // key split over a cluster (distributed-shared-memory merge), ragged lengths leave some ranks without tiles
+                fails += run_attn(100, 1, {100}, mn, 0, ks);
+                fails += run_attn(300, 2, {300, 170}, mn, 0, ks);
+                fails += run_attn(700, 3, {1, 700, 129}, mn, 0, ks);
+                fails += run_attn(1023, 1, {1023}, mn, perf ? 20 : 0, ks);
+                fails += run_attn(1573, 1, {1573}, mn, perf ? 20 : 0, ks);
+            }
             fails += g_timeouts;
             printf("%s (%d failing, %d barrier timeouts)\n", fails ? "ATTN PROBE FAILED" : "ATTN PROBE OK", fails, g_timeouts);
             return fails ? 1 : 0;
