@@ -59,6 +59,7 @@ struct TcEpi {
     int out_f16 = 0;     // store y as a 16-bit c8 tensor
     int gate = 0;        // WN gate fused into the tail (reference commons.py:98-105): columns (2c, 2c+1) hold the tanh / sigmoid pre-activations of
                          // channel c (weights interleaved at load time); y gets tanh(a) * sigmoid(b) as a 16-bit c8 tensor with Cout/2 channels
+    long long* prof = nullptr;  // probes: per-CTA phase timestamps (k_tc_conv1d)
     const float* ln_gamma = nullptr; const float* ln_beta = nullptr;  // LayerNorm over the Cout channels of each time step fused into the
                                                                       // tail (one N tile = all channels; combine with res for norm(x + conv))
 };
@@ -174,6 +175,7 @@ struct TcParams {
     long long w_zstride;        // packed-weight offset per z (floats)
     int w_mode;                 // 1: B operand rows come from a c4 activation tensor (K == 1): w = tensor base
     int w_ld, w_rows, w_c_total, w_c_off, w_c_zstride;
+    long long* prof;            // probes only: per-CTA globaltimer stamps [ctas][8] (k_tc_conv1d); nullptr in the engine
 };
 
 // Device-side error flags: a barrier timeout raises both and lets the kernel run to completion instead of trapping the context
@@ -643,15 +645,22 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
     fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // shfl: a warp-uniform value for ptxas (uniform registers in the MMA issuer)
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the
-    // previous kernel in the stream; from here on this grid reads activations that kernel produced.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // previous kernel in the stream; from here on this grid reads activations that kernel produced.  The dependents are released
+    // at once (their prologue and weight prefetch overlap this kernel); the weight producer itself does not wait either: packed weights
+    // are static, so its ring fills while the upstream kernel is still draining.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    auto gtimer = [] { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    long long* prof = p.prof ? p.prof + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
+    if (prof && threadIdx.x == 0) prof[0] = gtimer();
+    const bool static_role = warp == 6 && !p.w_mode;  // weight producer: touches nothing the upstream kernel wrote
+    if (!static_role) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (prof && threadIdx.x == 0) prof[1] = gtimer();
 
     const int R = p.R;
     const int G = F16 ? 8 : 4;                                  // channels per 16-byte operand group
     const int ncg_in = (F16 && !p.in_f16) ? p.KC / 4 : p.KC / G;  // 16-byte groups per chunk in the GLOBAL tensor
     const int gdiv = (F16 && p.in_f16) ? 8 : 4;                 // channels per 16-byte group in the global tensor
-    const int len = p.lens ? p.lens[b] : p.T;
+    const int len = (p.lens && !static_role) ? p.lens[b] : p.T;
     // rows r of the staged tile map to t = t0 - pad + r; rows outside [0, T) are the conv's zero padding
     const int r_lo = max(0, p.pad - t0);
     const int r_hi = min(R, p.T - (t0 - p.pad));
@@ -728,6 +737,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
             for (int c = 0; c < p.nchunks; c++) {
                 mbar_wait_u(bar_ar + 8u * sa, aph);
                 fence_after();
+                if (prof && c == 0 && lane == 0) prof[2] = gtimer();
                 uint64_t a_tap = a_cur;
                 for (int j = 0; j < p.K; j++, a_tap += (uint64_t)(uint32_t)p.dil) {
                     mbar_wait_u(bar_wf + 8u * sw, wph);
@@ -743,6 +753,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
                 if (++sa == nas_u) { sa = 0; aph ^= 1u; a_cur = a_desc_base; }
             }
             umma_commit_e(BAR(B_ACC));
+            if (prof && lane == 0) prof[3] = gtimer();
         }
     } else {
         const int tid2 = threadIdx.x - 64;
@@ -752,11 +763,13 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
             acc_init_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, yb, cout_off);
         fence_before();
         mbar_arrive(BAR(B_INIT));
+        if (prof && tid2 == 0) prof[4] = gtimer();
         // ===== operand prologue on the staged tile (generic proxy), then hand over to the async proxy
         const float slope = p.in_slope;
         for (int c = 0; c < p.nchunks; c++) {
             const int sa = c % NAS;
             mbar_wait(BAR(B_AFULL + sa), (c / NAS) & 1);
+            if (prof && tid2 == 0 && c == 0) prof[7] = gtimer();
             uint8_t* st = sA + (size_t)sa * p.a_stage_bytes;
             if (F16) {
                 if (!p.in_f16) xform16_stage(reinterpret_cast<const float4*>(st), reinterpret_cast<uint4*>(st + p.a_op_off), p.KC / 8, R, r_lo, r_mask_hi, slope, tid2);
@@ -769,12 +782,14 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
         // ===== tail
         mbar_wait(BAR(B_ACC), 0);
         fence_after();
+        if (prof && tid2 == 0) prof[5] = gtimer();
         if (GEN && p.ln_gamma) {
             acc_tail_ln(p, tmem + ((uint32_t)(q * 32) << 16), b, t0 + q * 32 + lane, nt, len);
         } else {
             for (int mt = 0; mt < MT; mt++)
                 acc_tail_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, len, yb, cout_off);
         }
+        if (prof && tid2 == 0) prof[6] = gtimer();
     }
     fence_before();
     __syncthreads();
@@ -1405,7 +1420,7 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     p.in_slope = e.in_slope; p.out_scale = e.out_scale; p.accumulate = e.accumulate; p.relu = e.relu; p.res_mode = e.res ? (e.res_mode ? e.res_mode : 1) : 0;
     p.in_mask = e.in_mask; p.out_mask = e.out_mask; p.ups_u = w.ups_u; p.ups_cout = w.ups_cout;
     p.out_tf32 = e.out_tf32; p.skip_xform = e.skip_xform; p.in_f16 = e.in_f16; p.out_f16 = e.out_f16;
-    p.ln_gamma = e.ln_gamma; p.ln_beta = e.ln_beta; p.gate = e.gate;
+    p.ln_gamma = e.ln_gamma; p.ln_beta = e.ln_beta; p.gate = e.gate; p.prof = e.prof;
     if (e.gate) BV2_CHECK(F16 && !w.ups_u && !e.res && !e.accumulate && !e.relu && !e.out_f16 && !e.ln_gamma && e.cout_off % 8 == 0 && y.C % 8 == 0 && 2 * y.C >= w.Cout, "gate epilogue");
     if (e.ln_gamma) BV2_CHECK(e.ln_beta && ntiles == 1 && nt % 32 == 0 && !w.ups_u && !e.out_f16 && !e.out_tf32 && !e.relu && e.out_scale == 1.f && e.res_mode != 2 && e.cout_off % 4 == 0, "LayerNorm tail needs one N tile holding every channel");
     if (e.skip_xform) BV2_CHECK(!F16 && w.K == 1 && e.in_slope == 1.f && !e.in_mask, "skip_xform needs a TF32 plain 1x1 conv input");

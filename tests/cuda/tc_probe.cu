@@ -372,6 +372,55 @@ static int run_mn_probe() {
 }
 
 
+
+// Timeline of one flow-shaped conv (FP16 engine, T frames, B = 1): back-to-back PDL launches, per-CTA phase stamps of the last one.
+// mode bits: 1 = out_f16, 2 = relu, 4 = residual, 8 = LayerNorm tail (needs nt == Cout), 16 = 16-bit c8 input (K = 1; timing only: the
+// fp32 test tensor is reinterpreted)
+static void run_flow_timeline(const char* name, int Cin, int Cout, int K, int nt, int kc, int T, int mode) {
+    std::mt19937 rng(Cin + Cout * 3 + K);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    std::vector<float> x((size_t)Cin * T), w((size_t)Cout * Cin * K), bias(Cout), r((size_t)Cout * T), g(Cout, 1.f), be(Cout, 0.f);
+    for (auto& v : x) v = nd(rng);
+    for (auto& v : w) v = nd(rng) / std::sqrt((float)(Cin * K));
+    for (auto& v : bias) v = nd(rng);
+    for (auto& v : r) v = nd(rng);
+    std::function<float*(const std::vector<float>&)> upf = up;
+    TcConvW tw = tc_pack_weights(upf, w, Cout, Cin, K, nt, 1, kc);
+    Act ax; ax.B = 1; ax.C = Cin; ax.T = T; ax.p = up(to_c4(x, 1, Cin, T));
+    Act ay; ay.B = 1; ay.C = Cout; ay.T = T; ay.p = up(std::vector<float>((size_t)Cout * T, 0.f));
+    float* dres = up(to_c4(r, 1, Cout, T)); float* dbias = up(bias); float* dg = up(g); float* dbe = up(be);
+    TcEpi e;
+    if (mode & 1) e.out_f16 = 1;
+    if (mode & 2) e.relu = 1;
+    if (mode & 4) { e.res = dres; e.res_mode = 1; e.res_C_total = Cout; }
+    if (mode & 8) { e.ln_gamma = dg; e.ln_beta = dbe; }
+    if (mode & 16) e.in_f16 = 1;
+    const int nctas = ((T + 127) / 128) * (Cout / tw.nt);
+    long long* dprof; cudaMalloc(&dprof, (size_t)nctas * 8 * 8); cudaMemset(dprof, 0, (size_t)nctas * 8 * 8);
+    cudaEvent_t a, c; cudaEventCreate(&a); cudaEventCreate(&c);
+    for (int i = 0; i < 3; i++) tc_conv1d(tw, dbias, ax, ay, e, 0, 148);
+    cudaEventRecord(a);
+    const int iters = 20;
+    for (int i = 0; i < iters; i++) { e.prof = i == iters - 1 ? dprof : nullptr; tc_conv1d(tw, dbias, ax, ay, e, 0, 148); }
+    cudaEventRecord(c); cudaEventSynchronize(c);
+    float ms; cudaEventElapsedTime(&ms, a, c); ms /= iters;
+    cudaError_t er = cudaDeviceSynchronize();
+    std::vector<long long> h((size_t)nctas * 8);
+    cudaMemcpy(h.data(), dprof, h.size() * 8, cudaMemcpyDeviceToHost);
+    long long t0 = h[0];
+    for (int i = 0; i < nctas; i++) if (h[i * 8]) t0 = std::min(t0, h[i * 8]);
+    printf("FLOW %-10s Cin=%3d Cout=%3d K=%d nt=%3d kc=%2d T=%d : %d CTAs, %.2f us per launch (back to back)%s\n", name, Cin, Cout, K, tw.nt, tw.KC, T, nctas, ms * 1e3,
+           er == cudaSuccess ? "" : "  CUDA ERROR");
+    printf("   ns since first CTA start: cta: start | pdl-wait end | acc init done | first A landed | first A ready (MMA starts) | MMA issue end | acc full | tail end\n");
+    for (int i : {0, nctas / 2, nctas - 1}) {
+        const long long* q = &h[(size_t)i * 8];
+        printf("   cta %3d: %6lld | %6lld | %6lld | %6lld | %6lld | %6lld | %6lld | %6lld\n", i, q[0] - t0, q[1] - t0, q[4] - t0, q[7] - t0, q[2] - t0, q[3] - t0, q[5] - t0, q[6] - t0);
+    }
+    fflush(stdout);
+    cudaFree(dprof);
+    free_all();
+}
+
 // Fused flow attention (tc_attn.cuh) against a double-precision CPU evaluation of reference attentions.py:272-322 on the same
 // FP16-rounded q/k/v (banded relative-key logits, masked softmax, relative-value term).
 static int run_attn(int T, int B, std::vector<int> lens, int lbo_is_kblock, int iters, int ks = 0) {
@@ -452,6 +501,17 @@ int main(int argc, char** argv) {
     try {
         g_flag = tc_init_device();
         fails += run_mn_probe();
+        if (getenv("PROBE_FLOW")) {  // timelines of the flow's conv shapes (FP16 engine) at config 2 (F = 1023 frames)
+            const int F = 1023;
+            run_flow_timeline("qkv", 192, 576, 1, 96, 64, F, 1);
+            run_flow_timeline("conv_o+LN", 192, 192, 1, 192, 64, F, 4 | 8 | 16);
+            run_flow_timeline("conv_1", 192, 768, 3, 128, 64, F, 2);
+            run_flow_timeline("conv_2", 768, 192, 3, 32, 64, F, 0);
+            run_flow_timeline("conv_2+LN", 768, 192, 3, 192, 32, F, 4 | 8);
+            run_flow_timeline("conv_2 n96", 768, 192, 3, 96, 64, F, 0);
+            run_flow_timeline("post", 192, 96, 1, 96, 64, F, 4);
+            return 0;
+        }
         if (getenv("PROBE_ATTN")) {
             tc_flow_attn_init_device();
             const int mn = atoi(getenv("PROBE_ATTN"));
