@@ -675,6 +675,20 @@ void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const fl
                 conv(L.o, att16, x, s, ao, 0, 0, true);
             }
             ws.release(mk);
+            if (L.f2.tc.nt != H) {
+                // FFN hidden tensor as the 16-bit operand image of conv_2 (relu and x_mask applied by conv_1's tail, the conv's zero padding
+                // cleared in the staged tile): conv_2 runs without an operand prologue -- the fp32 -> f16 conversion of its 768-channel
+                // input was the whole MMA phase (1.7 us per 64-channel chunk, profiles/r02g_flow_conv_timelines.log)
+                Act f16 = f;  // same workspace block, half of it used
+                ConvArgs a1; a1.in_mask = 1; a1.act = 1; a1.out_mask = 1; a1.lens = lens;
+                tc_out_f16 = 1;
+                conv(L.f1, x, f16, s, a1, 0, 0, true);
+                ConvArgs a2; a2.out_mask = 1; a2.lens = lens;
+                tc_in_f16 = 1;
+                conv(L.f2, f16, y, s, a2, 0, 0, true);
+                layernorm(L.n2, x, y.p, x, s, 0, nullptr, lens, i == nl - 1 ? 1 : 0);
+                continue;
+            }
             ConvArgs a1; a1.in_mask = 1; a1.act = 1; a1.lens = lens;
             conv(L.f1, x, f, s, a1, 0, 0, true);
             if (L.f2.tc.nt == H) {

@@ -644,27 +644,29 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
     __syncthreads();
     fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // shfl: a warp-uniform value for ptxas (uniform registers in the MMA issuer)
-    // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the
-    // previous kernel in the stream; from here on this grid reads activations that kernel produced.  The dependents are released
-    // at once (their prologue and weight prefetch overlap this kernel); the weight producer itself does not wait either: packed weights
-    // are static, so its ring fills while the upstream kernel is still draining.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation) overlapped the tail of the previous kernel in
+    // the stream.  Roles that touch only static data do not wait for it: the weight producer fills its ring and, when the accumulator
+    // init is bias-only, the epilogue warps pre-load the accumulators while the upstream kernel is still running (timelines in
+    // profiles/r02g_flow_conv_timelines.log: the init cost 5-6 us AFTER the wait before).  Everybody else waits, then releases the
+    // dependents (releasing them before the wait let the whole rest of the stream become resident at once: measured slower).
     auto gtimer = [] { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     long long* prof = p.prof ? p.prof + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
     if (prof && threadIdx.x == 0) prof[0] = gtimer();
-    const bool static_role = warp == 6 && !p.w_mode;  // weight producer: touches nothing the upstream kernel wrote
-    if (!static_role) asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool bias_only = !p.res_mode && !p.accumulate;
+    const bool static_role = (warp == 6 && !p.w_mode) || (warp >= 2 && warp <= 5 && bias_only);
+    if (!static_role) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     if (prof && threadIdx.x == 0) prof[1] = gtimer();
 
     const int R = p.R;
     const int G = F16 ? 8 : 4;                                  // channels per 16-byte operand group
     const int ncg_in = (F16 && !p.in_f16) ? p.KC / 4 : p.KC / G;  // 16-byte groups per chunk in the GLOBAL tensor
     const int gdiv = (F16 && p.in_f16) ? 8 : 4;                 // channels per 16-byte group in the global tensor
-    const int len = (p.lens && !static_role) ? p.lens[b] : p.T;
     // rows r of the staged tile map to t = t0 - pad + r; rows outside [0, T) are the conv's zero padding
     const int r_lo = max(0, p.pad - t0);
     const int r_hi = min(R, p.T - (t0 - p.pad));
-    const int r_mask_hi = p.in_mask ? min(r_hi, len - (t0 - p.pad)) : r_hi;  // rows >= this read as zero (x * x_mask)
 
     if (warp == 0) {
         // ===== activation producer: lane 0 owns the mbarrier protocol, lanes 0..ncg_in-1 each issue one TMA bulk copy (one
@@ -710,6 +712,8 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
             uint32_t sw = 0, ph = 1u, dst = dst0;
             const int nst = p.nchunks * p.K;
             for (int i = 0; i < nst; i++, src += p.w_stage_bytes) {
+                // (no griddepcontrol here: once the ring is full a slot only frees after MMAs ran, i.e. after the waiting roles saw the
+                //  upstream kernel complete; the first launch_dependents of ANY thread releases the CTA's dependents, so this role stays silent)
                 mbar_wait_u(bar_we + 8u * sw, ph);
                 mbar_expect_tx(bar_wf + 8u * sw, p.w_stage_bytes);
                 bulk_g2s(dst, src, p.w_stage_bytes, bar_wf + 8u * sw);
@@ -764,6 +768,12 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
         fence_before();
         mbar_arrive(BAR(B_INIT));
         if (prof && tid2 == 0) prof[4] = gtimer();
+        if (bias_only) {  // the init above touched static data only; everything below reads / overwrites tensors of the upstream kernel
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        }
+        const int len = p.lens ? p.lens[b] : p.T;
+        const int r_mask_hi = p.in_mask ? min(r_hi, len - (t0 - p.pad)) : r_hi;  // rows >= this read as zero (x * x_mask)
         // ===== operand prologue on the staged tile (generic proxy), then hand over to the async proxy
         const float slope = p.in_slope;
         for (int c = 0; c < p.nchunks; c++) {
@@ -773,6 +783,16 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
             uint8_t* st = sA + (size_t)sa * p.a_stage_bytes;
             if (F16) {
                 if (!p.in_f16) xform16_stage(reinterpret_cast<const float4*>(st), reinterpret_cast<uint4*>(st + p.a_op_off), p.KC / 8, R, r_lo, r_mask_hi, slope, tid2);
+                else if (r_lo > 0 || r_hi < R) {
+                    // 16-bit operand image with taps: the conv's zero padding is not part of the tensor; clear those rows of the staged
+                    // tile (the TMA copies covered rows [r_lo, r_hi) only); rows t >= len are zero in the tensor itself (producer's mask)
+                    uint4* A = reinterpret_cast<uint4*>(st);
+                    const int ncg = p.KC / 8, nz = r_lo + (R - r_hi);
+                    for (int i = tid2; i < ncg * nz; i += 128) {
+                        const int g = i / nz, k = i - g * nz;
+                        A[(size_t)g * R + (k < r_lo ? k : r_hi + (k - r_lo))] = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                }
             } else if (!p.skip_xform) {
                 xform_stage(reinterpret_cast<float4*>(st), p.KC / 4, R, r_lo, r_mask_hi, slope, tid2);
             }
@@ -1424,7 +1444,7 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     if (e.gate) BV2_CHECK(F16 && !w.ups_u && !e.res && !e.accumulate && !e.relu && !e.out_f16 && !e.ln_gamma && e.cout_off % 8 == 0 && y.C % 8 == 0 && 2 * y.C >= w.Cout, "gate epilogue");
     if (e.ln_gamma) BV2_CHECK(e.ln_beta && ntiles == 1 && nt % 32 == 0 && !w.ups_u && !e.out_f16 && !e.out_tf32 && !e.relu && e.out_scale == 1.f && e.res_mode != 2 && e.cout_off % 4 == 0, "LayerNorm tail needs one N tile holding every channel");
     if (e.skip_xform) BV2_CHECK(!F16 && w.K == 1 && e.in_slope == 1.f && !e.in_mask, "skip_xform needs a TF32 plain 1x1 conv input");
-    if (e.in_f16) BV2_CHECK(F16 && w.K == 1 && e.in_slope == 1.f && !e.in_mask && e.cin_off % 8 == 0 && x.C % 8 == 0, "in_f16 needs an FP16 plain 1x1 conv");
+    if (e.in_f16) BV2_CHECK(F16 && e.in_slope == 1.f && !e.in_mask && e.cin_off % 8 == 0 && x.C % 8 == 0, "in_f16: the 16-bit tensor is the operand image (activation / mask applied by its producer)");
     if (e.out_f16) BV2_CHECK(F16 && !w.ups_u && e.cout_off % 8 == 0 && y.C % 8 == 0 && !e.res && !e.accumulate, "out_f16 epilogue");
     if (p.in_mask || p.out_mask) BV2_CHECK(e.lens != nullptr, "mask needs lens");
     BV2_CHECK(!(p.relu && (p.res_mode || p.accumulate)), "relu cannot be combined with residual/accumulate (accumulator-init fusion)");

@@ -507,8 +507,9 @@ int main(int argc, char** argv) {
             run_flow_timeline("conv_o+LN", 192, 192, 1, 192, 64, F, 4 | 8 | 16);
             run_flow_timeline("conv_1", 192, 768, 3, 128, 64, F, 2);
             run_flow_timeline("conv_2", 768, 192, 3, 32, 64, F, 0);
-            run_flow_timeline("conv_2+LN", 768, 192, 3, 192, 32, F, 4 | 8);
-            run_flow_timeline("conv_2 n96", 768, 192, 3, 96, 64, F, 0);
+            run_flow_timeline("conv_1 f16o", 192, 768, 3, 128, 64, F, 1 | 2);
+            run_flow_timeline("conv_2 f16i", 768, 192, 3, 32, 64, F, 16);
+            run_flow_timeline("conv_2 f16i n96", 768, 192, 3, 96, 64, F, 16);
             run_flow_timeline("post", 192, 96, 1, 96, 64, F, 4);
             return 0;
         }
