@@ -10,6 +10,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "libbv2.so")
+TUNING_LIB_PATH = os.path.join(HERE, "libbv2_tuning.so")  # development build (-DBV2_TUNING: the BV2_* environment knobs of the probes are live)
 SOURCES = [os.path.join(HERE, "csrc", "engine.cu")]
 HEADERS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith(".cuh")) + [
     os.path.join(ROOT, "include", "bv2.h")]
@@ -77,24 +78,26 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS if os.path.isfile(p))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile libbv2.so in-tree for sm_100a with nvcc (cross-compiles without a GPU)."""
+def build(force: bool = False, verbose: bool = False, tuning: bool = False) -> str:
+    """Compile libbv2.so in-tree for sm_100a with nvcc (cross-compiles without a GPU).
+    tuning=True builds libbv2_tuning.so instead (same sources, -DBV2_TUNING); it is only ever loaded when BV2_LIB points at it."""
     with _lock:
-        if not force and not needs_build():
+        out = TUNING_LIB_PATH if tuning else LIB_PATH
+        if not tuning and not force and not needs_build():
             return LIB_PATH
-        tmp = LIB_PATH + ".tmp"  # link to a temporary name, then rename: a reader never sees a half-written library
+        tmp = out + ".tmp"  # link to a temporary name, then rename: a reader never sees a half-written library
         cmd = ["nvcc"] + NVCC_FLAGS + ["-o", tmp] + SOURCES
-        if os.environ.get("BV2_BUILD_TUNING"):  # development builds: BV2_* environment knobs of the probes become active (tc_conv.cuh tune_env)
+        if tuning or os.environ.get("BV2_BUILD_TUNING"):  # development builds: BV2_* environment knobs of the probes become active (tc_conv.cuh tune_env)
             cmd.insert(1, "-DBV2_TUNING")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-        os.replace(tmp, LIB_PATH)
+        os.replace(tmp, out)
         if verbose:
             print(r.stderr)
-        return LIB_PATH
+        return out
 
 
 def load():
@@ -102,10 +105,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.isfile(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'`. "
+    path = os.environ.get("BV2_LIB") or LIB_PATH  # BV2_LIB: development A/B runs against libbv2_tuning.so
+    if not os.path.isfile(path):
+        raise RuntimeError(f"{path} not built; run `python -c 'import __graft_entry__ as g; g.build()'`. "
                            "There is no CPU/PyTorch fallback for the engine.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype = res

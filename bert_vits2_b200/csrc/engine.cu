@@ -100,6 +100,7 @@ struct bv2_engine {
     ConvW dp_c1, dp_c2, dp_proj; LnW dp_n1, dp_n2;
     std::vector<CouplingW> flows;
     ConvW conv_pre; std::vector<UpW> ups; std::vector<ResBlockW> resblocks; float* conv_post_w = nullptr;
+    PostW<16, 7> conv_post_h{};  // host copy of conv_post's weights (kernel-parameter operand of k_conv_post_tanh_h8), read back in finalize()
     float *gproj_w = nullptr, *gproj_b = nullptr; int gproj_n = 0;
     int goff_dec = 0, goff_sdp = 0, goff_dp = 0;
     float dconst = 0.f;
@@ -472,6 +473,10 @@ void bv2_engine::finalize(const uint8_t* packed, size_t packed_bytes) {
         std::vector<uint8_t>().swap(wmirror);
     }
     if (!h_ylen) BV2_CUDA(cudaMallocHost(&h_ylen, 4100 * sizeof(long long)));
+    if (use_g2) {  // same bytes whichever way the arena was filled (state_dict or packed file)
+        BV2_CHECK(c.upsample_initial_channel >> c.n_ups == 16, "conv_post kernel instantiated for 16 input channels, 7 taps");
+        BV2_CUDA(cudaMemcpy(conv_post_h.w, conv_post_w, sizeof(conv_post_h.w), cudaMemcpyDeviceToHost));
+    }
     host.clear();
     finalized = true;
 }
@@ -669,13 +674,14 @@ void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const fl
             tc_out_f16 = 1;
             conv(L.qkv, x, qkv16, s, ConvArgs(), 0, 0, true);
             tc_flow_attn(qkv16, att16, L.relk, L.relv, lens, nh, (int)cfg.window_size, s, attn_mn); launches++;
-            {   // x = norm_1(x + conv_o(att)): the residual is pre-loaded into the accumulator, LayerNorm runs in the tail
+            {   // x = norm_1(x + conv_o(att)): LayerNorm runs in the conv's tail; the residual tile is staged in shared memory by TMA (small grids)
+                // or pre-loaded into the accumulator (more CTAs than SMs)
                 ConvArgs ao; ao.res = x.p; ao.res_mode = 1; ao.res_C_total = H;
                 tc_in_f16 = 1; tc_ln = &L.n1;
                 conv(L.o, att16, x, s, ao, 0, 0, true);
             }
             ws.release(mk);
-            if (L.f2.tc.nt != H) {
+            {
                 // FFN hidden tensor as the 16-bit operand image of conv_2 (relu and x_mask applied by conv_1's tail, the conv's zero padding
                 // cleared in the staged tile): conv_2 runs without an operand prologue -- the fp32 -> f16 conversion of its 768-channel
                 // input was the whole MMA phase (1.7 us per 64-channel chunk, profiles/r02g_flow_conv_timelines.log)
@@ -683,25 +689,19 @@ void bv2_engine::run_encoder(const EncoderW& E, Act x, const int* lens, const fl
                 ConvArgs a1; a1.in_mask = 1; a1.act = 1; a1.out_mask = 1; a1.lens = lens;
                 tc_out_f16 = 1;
                 conv(L.f1, x, f16, s, a1, 0, 0, true);
-                ConvArgs a2; a2.out_mask = 1; a2.lens = lens;
-                tc_in_f16 = 1;
-                conv(L.f2, f16, y, s, a2, 0, 0, true);
-                layernorm(L.n2, x, y.p, x, s, 0, nullptr, lens, i == nl - 1 ? 1 : 0);
-                continue;
+                if (L.f2.tc.nt == H) {
+                    // x = norm_2(x + ffn(x)): conv_2 on one full-width N tile, LayerNorm in the tail, residual tile staged by TMA
+                    // (rows t >= len skip the reference's y * x_mask; they only ever feed masked positions and are zeroed by the last layer)
+                    ConvArgs a2; a2.lens = lens; a2.res = x.p; a2.res_mode = 1; a2.res_C_total = H; a2.out_mask = i == nl - 1 ? 1 : 0;
+                    tc_in_f16 = 1; tc_ln = &L.n2;
+                    conv(L.f2, f16, x, s, a2, 0, 0, true);
+                } else {
+                    ConvArgs a2; a2.out_mask = 1; a2.lens = lens;
+                    tc_in_f16 = 1;
+                    conv(L.f2, f16, y, s, a2, 0, 0, true);
+                    layernorm(L.n2, x, y.p, x, s, 0, nullptr, lens, i == nl - 1 ? 1 : 0);
+                }
             }
-            ConvArgs a1; a1.in_mask = 1; a1.act = 1; a1.lens = lens;
-            conv(L.f1, x, f, s, a1, 0, 0, true);
-            if (L.f2.tc.nt == H) {
-                // x = norm_2(x + ffn(x)): conv_2 on one full-width N tile, residual pre-loaded into the accumulator, LayerNorm in the tail
-                // (rows t >= len skip the reference's y * x_mask; they only ever feed masked positions and are zeroed by the last layer)
-                ConvArgs a2; a2.in_mask = 1; a2.lens = lens; a2.res = x.p; a2.res_mode = 1; a2.res_C_total = H; a2.out_mask = i == nl - 1 ? 1 : 0;
-                tc_ln = &L.n2;
-                conv(L.f2, f, x, s, a2, 0, 0, true);
-                continue;
-            }
-            ConvArgs a2; a2.in_mask = 1; a2.out_mask = 1; a2.lens = lens;
-            conv(L.f2, f, y, s, a2, 0, 0, true);
-            layernorm(L.n2, x, y.p, x, s, 0, nullptr, lens, i == nl - 1 ? 1 : 0);
             continue;
         }
         if (tc == 0 && H == 192) {
@@ -1045,16 +1045,8 @@ void bv2_engine::run_generator_g2(Act z, const int* lens, const float* gdec, int
         t.p = reinterpret_cast<uint4*>(ws.alloc(H8::bytes(B, C, T) / 4)) + G2_PADL;
         return t;
     };
-    auto zero_halos = [&](std::initializer_list<const H8*> ts) {
-        G2HaloList l{}; l.n = 0;
-        for (const H8* t : ts) { l.p[l.n] = t->p; l.cg_rows[l.n] = t->B * (t->C / 8); l.T[l.n] = t->T; l.Tp[l.n] = t->Tp; l.n++; }
-        int mx = 0; for (int i = 0; i < l.n; i++) mx = std::max(mx, l.cg_rows[i]);
-        k_g2_zero_halo<<<dim3(std::max(1, std::min(cdiv(mx * (G2_PADL + G2_PADR), 128), 64)), l.n), 128, 0, s>>>(l);
-        BV2_CUDA(cudaGetLastError()); launches++;
-    };
     int ch = cfg.upsample_initial_channel, L = F;
-    H8 zh = h8(I, F), x = h8(ch, L);
-    zero_halos({&zh, &x});
+    H8 zh = h8(I, F), x = h8(ch, L);  // zero halos: every producer clears the halo rows of its own output (k_c4_to_h8, k_g2_conv)
     k_c4_to_h8<<<dim3(cdiv(F, 128), I / 8, B), 128, 0, s>>>(reinterpret_cast<const float4*>(z.p), zh.p, I, F, zh.Tp, lens);
     BV2_CUDA(cudaGetLastError()); launches++;
     {
@@ -1072,14 +1064,6 @@ void bv2_engine::run_generator_g2(Act z, const int* lens, const float* gdec, int
         H8 xu = h8(u.Cout, Lo);
         H8 xt[4], ra[4], rb[4];
         for (int j = 0; j < nk; j++) { xt[j] = h8(u.Cout, Lo); ra[j] = h8(u.Cout, Lo); rb[j] = h8(u.Cout, Lo); }
-        {
-            G2HaloList l{}; l.n = 0;
-            auto add = [&](const H8& t) { l.p[l.n] = t.p; l.cg_rows[l.n] = t.B * (t.C / 8); l.T[l.n] = t.T; l.Tp[l.n] = t.Tp; l.n++; };
-            add(S); add(xu);
-            for (int j = 0; j < nk; j++) { add(xt[j]); add(ra[j]); add(rb[j]); }
-            k_g2_zero_halo<<<dim3(std::max(1, std::min(cdiv(l.cg_rows[0] * (G2_PADL + G2_PADR), 128), 64)), l.n), 128, 0, s>>>(l);
-            BV2_CUDA(cudaGetLastError()); launches++;
-        }
         g2_conv(u.tc, u.b, x, xu, G2Epi(), s, num_sms); launches++;
         BV2_CUDA(cudaEventRecord(ev_fork, s));
         for (int j = 0; j < nk; j++) {
@@ -1105,7 +1089,7 @@ void bv2_engine::run_generator_g2(Act z, const int* lens, const float* gdec, int
         ws.release(mark_after_S);
     }
     BV2_CHECK(ch == 16, "conv_post kernel instantiated for 16 input channels");
-    launch_pdl(k_conv_post_tanh_h8<16, 7>, dim3(cdiv(L, 256), B), dim3(256), 0, s, (const uint4*)x.p, x.Tp, (const float*)conv_post_w, o, L);
+    launch_pdl(k_conv_post_tanh_h8<16, 7>, dim3(cdiv(L, 512), B), dim3(256), 0, s, (const uint4*)x.p, x.Tp, conv_post_h, o, L);
     launches++;
 }
 

@@ -35,6 +35,7 @@ struct AttnParams {
     int B, T, H, heads, window;
     int ks;             // key split: a cluster of ks CTAs shares one 128-query tile, CTA r takes key tiles r, r + ks, ... (1 = no cluster)
     uint32_t idesc_qk, idesc_pv, v_lbo, v_sbo;
+    long long* prof;    // probes only: per-CTA globaltimer stamps [ctas][10]; nullptr in the engine
 };
 
 namespace tc {
@@ -70,6 +71,10 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
     const int q0 = ((int)blockIdx.x / KS) * 128, h = blockIdx.y, b = blockIdx.z;
     const int H8 = p.H / 8;
     const int w = p.window, nrel = 2 * w + 1;
+    auto gtimer = [] { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    long long* prof = p.prof ? p.prof + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 10 : nullptr;
+    const bool stamp = prof && threadIdx.x == 64;  // first softmax thread
+    if (prof && threadIdx.x == 0) prof[0] = gtimer();
 
     if (threadIdx.x == 0) {
         mbar_init(BAR(B_QFULL), 1); mbar_init(BAR(B_OFULL), 1);
@@ -94,6 +99,7 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // shfl: a warp-uniform value for ptxas (uniform registers in the MMA issuer)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (prof && threadIdx.x == 0) prof[1] = gtimer();
 
     const int len = min(p.lens ? p.lens[b] : p.T, p.T);
     const int NT_all = q0 < len ? (len + KT - 1) / KT : 0;  // key tiles that hold at least one valid key (same for the whole cluster)
@@ -198,6 +204,7 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
 #pragma unroll
                 for (int r = 0; r < NREL; r++) v = (r == d) ? qrel[r] : v;
                 return v; };
+            if (stamp) prof[2] = gtimer();
             // ---- pass A: row maximum over the valid keys (of this CTA's key tiles)
             for (int s = 0; s < NT; s++) {
                 const int st = s & 1, k0 = (rk + KS * s) * KT, nvalid = len - k0;
@@ -225,6 +232,7 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                 fence_before();
                 mbar_arrive(BAR(B_SEMPTY + st));
             }
+            if (stamp) prof[3] = gtimer();
             // ---- pass B: p = exp(s - M) -> FP16 operand image in shared memory; row sum; relative-value weights
             const float M2 = M * LOG2E;
             for (int j = 0; j < NT; j++) {
@@ -271,8 +279,10 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                 mbar_arrive(BAR(B_PFULL + pb));
                 mbar_arrive(BAR(B_SEMPTY + st));
             }
+            if (stamp) prof[4] = gtimer();
             mbar_wait(BAR(B_OFULL), 0);  // every MMA of this CTA has completed: O is final, the K/V/P stages are free
             fence_after();
+            if (stamp) prof[5] = gtimer();
             }  // NT > 0
             if (KS > 1) {
                 // ---- park this CTA's partial row in its own shared memory (the K stages): [27 float4][128 rows]
@@ -326,7 +336,9 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
     }
     if (KS > 1 && NT_all > 0) {
         // ---- merge the key splits (every thread of every CTA of the cluster takes part in both barriers)
+        if (stamp) prof[6] = gtimer();
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (stamp) prof[7] = gtimer();
         // CTA rk merges rows [rk * 128/KS, (rk + 1) * 128/KS); KS threads share a row (96/KS channels each), consecutive lanes take
         // consecutive rows (coalesced distributed-shared-memory reads)
         if (warp >= 2) {
@@ -407,8 +419,10 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                 }
             }
         }
+        if (stamp) prof[8] = gtimer();
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");  // peers are done reading this CTA's rows
     }
+    if (stamp) prof[9] = gtimer();
     fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -428,13 +442,13 @@ inline void tc_flow_attn_init_device() {
 
 // qkv16: 16-bit c8 tensor with C = 3H channels (Act.p reinterpreted); att16: 16-bit c8 tensor with C = H channels.
 inline void tc_flow_attn(const Act& qkv16, const Act& att16, const float* rel_k, const float* rel_v, const int* lens, int heads, int window,
-                         cudaStream_t st, AttnMnConv mn = AttnMnConv(), int num_sms = 148, int ks_override = 0) {
+                         cudaStream_t st, AttnMnConv mn = AttnMnConv(), int num_sms = 148, int ks_override = 0, long long* prof = nullptr) {
     const int H = att16.C, dk = H / heads, KT = 128;
     BV2_CHECK(qkv16.C == 3 * H && dk == 96 && H % 8 == 0 && window <= 4 && qkv16.T == att16.T && qkv16.B == att16.B, "tc_flow_attn shapes (head dim 96, window <= 4)");
     AttnParams p{};
     p.qkv = reinterpret_cast<const uint4*>(qkv16.p); p.att = reinterpret_cast<uint4*>(att16.p);
     p.rel_k = rel_k; p.rel_v = rel_v; p.lens = lens;
-    p.B = qkv16.B; p.T = qkv16.T; p.H = H; p.heads = heads; p.window = window;
+    p.B = qkv16.B; p.T = qkv16.T; p.H = H; p.heads = heads; p.window = window; p.prof = prof;
     p.idesc_qk = tc::make_idesc(1, KT);
     p.idesc_pv = tc::make_idesc(1, dk) | (1u << 16);  // b_major = MN
     const uint32_t kblk = 128u, nblk = (uint32_t)KT * 16u;

@@ -168,6 +168,8 @@ struct TcParams {
     int accumulate, relu, res_mode, in_mask, out_mask, ups_u, ups_cout;
     int out_tf32, skip_xform, in_f16, out_f16, gate;
     const float* ln_gamma; const float* ln_beta;
+    uint32_t res_soff;          // LayerNorm tail only: byte offset (in dynamic shared memory) of the TMA-staged residual tile [nt/4][128 rows][16 B];
+                                // 0 = residual pre-loaded into the accumulator by the epilogue warps (acc_init_tile)
     // batched-GEMM extensions (TF32 attention GEMMs of the fp32/tf32 engines): grid z = b * zsplit + h
     int zsplit;                 // 0/1: z == batch
     int x_batch_z, y_batch_z;   // 1: tensor's batch index is z (else b)
@@ -378,7 +380,7 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(int f16, int n, int m = 
 // GEN = 1: generic epilogue (polyphase ConvTranspose scatter, per-batch bias, relu, 16-bit output); GEN = 0: plain conv
 // epilogue.  The plain instantiation is 10-20 % faster on the MRF convs (measured): these kernels run at their register caps.
 template <int NG, int GEN>
-__device__ __forceinline__ void acc_init_tile(const TcParams& p, uint32_t trow, int b, int t, int n0, int nt, int yb = -1, int coff = -1) {
+__device__ __forceinline__ void acc_init_tile(const TcParams& p, uint32_t trow, int b, int t, int n0, int nt, int yb = -1, int coff = -1, bool skip_res = false) {
     const bool ok = t < p.T;
     const size_t tstride = (size_t)p.T * ((GEN && p.ups_u) ? p.ups_u : 1);
     if (yb < 0) yb = b;
@@ -403,7 +405,7 @@ __device__ __forceinline__ void acc_init_tile(const TcParams& p, uint32_t trow, 
                 }
             }
         }
-        if (ok && p.res_mode) {
+        if (ok && p.res_mode && !(GEN && skip_res)) {
             float4 r[NG];
 #pragma unroll
             for (int g = 0; g < NG; g++) if (col0 + 4 * g < nt) r[g] = resb[(size_t)((p.res_c_off + cos[g]) / 4) * tstride + tts[g]];
@@ -502,7 +504,9 @@ __device__ __forceinline__ void acc_tail_tile(const TcParams& p, uint32_t trow, 
 // Tail with a fused LayerNorm over the nt = Cout channels of each row (reference attentions.py:21-24 after the residual add of
 // attentions.py:114,118): the accumulator already holds bias + residual + conv (accumulator-init fusion), so the row statistics
 // are three cheap passes over TMEM (16 TB/s) instead of a separate kernel with an HBM round trip.
-__device__ __forceinline__ void acc_tail_ln(const TcParams& p, uint32_t trow, int b, int t, int nt, int len) {
+__device__ __forceinline__ void acc_tail_ln(const TcParams& p, uint32_t trow, int b, int t, int nt, int len, const float4* rs = nullptr) {
+    // rs: this thread's row of the TMA-staged residual tile ([nt/4][128 rows] float4, already offset by the row); nullptr = the residual
+    // was pre-loaded into the accumulator.  x = acc + residual is re-formed in each pass (shared-memory reads are cheap, TMEM is not written).
     const bool ok = t < p.T;
     float4* ybp = reinterpret_cast<float4*>(p.y) + (size_t)b * (p.Cout_total / 4) * p.T;
     float s = 0.f;
@@ -510,8 +514,16 @@ __device__ __forceinline__ void acc_tail_ln(const TcParams& p, uint32_t trow, in
         uint32_t v[32];
         tmem_ld32(trow + (uint32_t)c0, v);
         tmem_wait_ld();
+        if (rs) {
 #pragma unroll
-        for (int e = 0; e < 32; e++) s += __uint_as_float(v[e]);
+            for (int g = 0; g < 8; g++) {
+                const float4 r = rs[(size_t)(c0 / 4 + g) * 128];
+                s += (__uint_as_float(v[4 * g]) + r.x) + (__uint_as_float(v[4 * g + 1]) + r.y) + (__uint_as_float(v[4 * g + 2]) + r.z) + (__uint_as_float(v[4 * g + 3]) + r.w);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; e++) s += __uint_as_float(v[e]);
+        }
     }
     const float mean = s / (float)nt;
     float q = 0.f;
@@ -519,8 +531,20 @@ __device__ __forceinline__ void acc_tail_ln(const TcParams& p, uint32_t trow, in
         uint32_t v[32];
         tmem_ld32(trow + (uint32_t)c0, v);
         tmem_wait_ld();
+        if (rs) {
 #pragma unroll
-        for (int e = 0; e < 32; e++) { const float d = __uint_as_float(v[e]) - mean; q = fmaf(d, d, q); }
+            for (int g = 0; g < 8; g++) {
+                const float4 r = rs[(size_t)(c0 / 4 + g) * 128];
+                float d;
+                d = __uint_as_float(v[4 * g]) + r.x - mean; q = fmaf(d, d, q);
+                d = __uint_as_float(v[4 * g + 1]) + r.y - mean; q = fmaf(d, d, q);
+                d = __uint_as_float(v[4 * g + 2]) + r.z - mean; q = fmaf(d, d, q);
+                d = __uint_as_float(v[4 * g + 3]) + r.w - mean; q = fmaf(d, d, q);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 32; e++) { const float d = __uint_as_float(v[e]) - mean; q = fmaf(d, d, q); }
+        }
     }
     const float rstd = rsqrtf(q / (float)nt + 1e-5f);
     const float m = (p.out_mask && t >= len) ? 0.f : 1.f;
@@ -532,11 +556,53 @@ __device__ __forceinline__ void acc_tail_ln(const TcParams& p, uint32_t trow, in
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             const float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c0 + 4 * g)), be = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c0 + 4 * g));
+            float4 x = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+            if (rs) { const float4 r = rs[(size_t)(c0 / 4 + g) * 128]; x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w; }
             float4 o;
-            o.x = ((__uint_as_float(v[4 * g]) - mean) * rstd * ga.x + be.x) * m; o.y = ((__uint_as_float(v[4 * g + 1]) - mean) * rstd * ga.y + be.y) * m;
-            o.z = ((__uint_as_float(v[4 * g + 2]) - mean) * rstd * ga.z + be.z) * m; o.w = ((__uint_as_float(v[4 * g + 3]) - mean) * rstd * ga.w + be.w) * m;
+            o.x = ((x.x - mean) * rstd * ga.x + be.x) * m; o.y = ((x.y - mean) * rstd * ga.y + be.y) * m;
+            o.z = ((x.z - mean) * rstd * ga.z + be.z) * m; o.w = ((x.w - mean) * rstd * ga.w + be.w) * m;
             ybp[(size_t)((p.cout_off + c0) / 4 + g) * p.T + t] = o;
         }
+    }
+}
+
+// LayerNorm tail with the whole row in registers (NT columns: one TMEM read instead of three passes, every tcgen05.ld in flight at once).
+// Needs ~NT + 40 registers per thread: only the LNT instantiation of k_tc_conv1d (one CTA per SM, small grids) uses it.
+template <int NT>
+__device__ __forceinline__ void acc_tail_ln_regs(const TcParams& p, uint32_t trow, int b, int t, int len, const float4* rs) {
+    static_assert(NT % 32 == 0, "row width");
+    uint32_t v[NT];
+#pragma unroll
+    for (int c0 = 0; c0 < NT; c0 += 32) tmem_ld32(trow + (uint32_t)c0, v + c0);
+    tmem_wait_ld();
+    float x[NT];
+#pragma unroll
+    for (int e = 0; e < NT; e++) x[e] = __uint_as_float(v[e]);
+    if (rs) {
+#pragma unroll
+        for (int g = 0; g < NT / 4; g++) {
+            const float4 r = rs[(size_t)g * 128];
+            x[4 * g] += r.x; x[4 * g + 1] += r.y; x[4 * g + 2] += r.z; x[4 * g + 3] += r.w;
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < NT; e++) s += x[e];
+    const float mean = s / (float)NT;
+    float q = 0.f;
+#pragma unroll
+    for (int e = 0; e < NT; e++) { const float d = x[e] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(q / (float)NT + 1e-5f);
+    if (t >= p.T) return;
+    const float m = (p.out_mask && t >= len) ? 0.f : 1.f;
+    float4* ybp = reinterpret_cast<float4*>(p.y) + ((size_t)b * (p.Cout_total / 4) + p.cout_off / 4) * p.T + t;
+#pragma unroll
+    for (int g = 0; g < NT / 4; g++) {
+        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + 4 * g)), be = __ldg(reinterpret_cast<const float4*>(p.ln_beta + 4 * g));
+        float4 o;
+        o.x = ((x[4 * g] - mean) * rstd * ga.x + be.x) * m; o.y = ((x[4 * g + 1] - mean) * rstd * ga.y + be.y) * m;
+        o.z = ((x[4 * g + 2] - mean) * rstd * ga.z + be.z) * m; o.w = ((x[4 * g + 3] - mean) * rstd * ga.w + be.w) * m;
+        ybp[(size_t)g * p.T] = o;
     }
 }
 
@@ -606,8 +672,10 @@ __device__ __forceinline__ void xform16_stage(const float4* S, uint4* O, int ncg
 // Accumulator-init fusion: before the first MMA the epilogue warps pre-load  bias (+ per-batch bias) (+/- residual)
 // (+ previous output when accumulating)  into the TMEM accumulator with tcgen05.st while the first TMA loads are in
 // flight; every MMA then accumulates, and the tail is only  TMEM -> [relu] -> scale/mask -> store.
-template <int GEN, int F16>
-__global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
+// LNT = 1: instantiation for the LayerNorm tail on small grids (one CTA per SM): 255 registers per thread, the tail keeps its whole
+// 192-column row in registers (acc_tail_ln_regs).
+template <int GEN, int F16, int LNT = 0>
+__global__ void __launch_bounds__(224, LNT ? 1 : 4) k_tc_conv1d(TcParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -622,18 +690,19 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
     const int NAS = p.nas;
     uint8_t* sW = smem + (size_t)NAS * p.a_stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (size_t)p.nws * p.w_stage_bytes);
-    // barrier map: a_full[NAS], a_ready[NAS], a_empty[NAS], w_full[nws], w_empty[nws], acc_full, acc_init
+    // barrier map: a_full[NAS], a_ready[NAS], a_empty[NAS], w_full[nws], w_empty[nws], acc_full, acc_init, res_full
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     const int B_AFULL = 0, B_AREADY = NAS, B_AEMPTY = 2 * NAS, B_WFULL = 3 * NAS, B_WEMPTY = 3 * NAS + p.nws, B_ACC = 3 * NAS + 2 * p.nws,
-              B_INIT = B_ACC + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_INIT + 1);
+              B_INIT = B_ACC + 1, B_RES = B_ACC + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_RES + 1);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NAS; i++) { mbar_init(BAR(B_AFULL + i), 1); mbar_init(BAR(B_AREADY + i), 128); mbar_init(BAR(B_AEMPTY + i), 1); }
         for (int i = 0; i < p.nws; i++) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
         mbar_init(BAR(B_ACC), 1);
         mbar_init(BAR(B_INIT), 128);
+        mbar_init(BAR(B_RES), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -652,7 +721,13 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
     auto gtimer = [] { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     long long* prof = p.prof ? p.prof + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 : nullptr;
     if (prof && threadIdx.x == 0) prof[0] = gtimer();
-    const bool bias_only = !p.res_mode && !p.accumulate;
+    // LayerNorm tail with a TMA-staged residual (p.res_soff): the residual tile is copied into shared memory by the activation producer
+    // right after the PDL wait and added by the tail, so the accumulator init is bias-only (static data, runs ahead of the wait) and the
+    // MMAs never wait for residual loads.  (Pre-loading the residual into the accumulator took 15 us of a 24 us conv_o + LN launch: 12
+    // dependent rounds of 4 float4 loads per thread AFTER the wait, with the MMA issuer parked on the init barrier,
+    // profiles/r02h_flow_conv_timelines_f16_ffn.log.)
+    const bool res_smem = GEN && p.res_soff != 0;
+    const bool bias_only = (!p.res_mode || res_smem) && !p.accumulate;
     const bool static_role = (warp == 6 && !p.w_mode) || (warp >= 2 && warp <= 5 && bias_only);
     if (!static_role) {
         asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -684,6 +759,15 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
                 const uint4* src = xg + ((size_t)xb * (p.Cin_total / gdiv) + cin_off / gdiv + (size_t)c * ncg_in + lane) * p.T + (t0 - p.pad + r_lo);
                 const uint32_t dst = smem_u32(sA + (size_t)sa * p.a_stage_bytes) + ((uint32_t)lane * R + (uint32_t)r_lo) * 16u;
                 bulk_g2s(dst, src, row_bytes, BAR(B_AFULL + sa));
+            }
+            if (res_smem && c == min(NAS, p.nchunks) - 1) {
+                // residual tile -> shared memory, one bulk copy per channel group (behind the first ring fill: the operand tiles gate the MMAs)
+                const int nrows = min(128, p.T - t0);
+                if (lane == 0) mbar_expect_tx(BAR(B_RES), (uint32_t)nrows * 16u * (uint32_t)(nt / 4));
+                __syncwarp();
+                const float4* rg = reinterpret_cast<const float4*>(p.res) + ((size_t)yb * (p.res_C_total / 4) + p.res_c_off / 4) * p.T + t0;
+                for (int g = lane; g < nt / 4; g += 32)
+                    bulk_g2s(smem_u32(smem + p.res_soff) + (uint32_t)g * 2048u, rg + (size_t)g * p.T, (uint32_t)nrows * 16u, BAR(B_RES));
             }
         }
     } else if (warp == 6) {
@@ -764,7 +848,7 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
         const int q = warp & 3;
         // ===== accumulator init (overlaps the first TMA loads)
         for (int mt = 0; mt < MT; mt++)
-            acc_init_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, yb, cout_off);
+            acc_init_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, yb, cout_off, res_smem);
         fence_before();
         mbar_arrive(BAR(B_INIT));
         if (prof && tid2 == 0) prof[4] = gtimer();
@@ -804,7 +888,10 @@ __global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
         fence_after();
         if (prof && tid2 == 0) prof[5] = gtimer();
         if (GEN && p.ln_gamma) {
-            acc_tail_ln(p, tmem + ((uint32_t)(q * 32) << 16), b, t0 + q * 32 + lane, nt, len);
+            const float4* rs = nullptr;
+            if (res_smem) { mbar_wait(BAR(B_RES), 0); rs = reinterpret_cast<const float4*>(smem + p.res_soff) + (q * 32 + lane); }
+            if (LNT && nt == 192) acc_tail_ln_regs<192>(p, tmem + ((uint32_t)(q * 32) << 16), b, t0 + q * 32 + lane, len, rs);
+            else acc_tail_ln(p, tmem + ((uint32_t)(q * 32) << 16), b, t0 + q * 32 + lane, nt, len, rs);
         } else {
             for (int mt = 0; mt < MT; mt++)
                 acc_tail_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, len, yb, cout_off);
@@ -1402,7 +1489,7 @@ inline void tc_clear_error() {
 inline int* tc_init_device() {
     const int mx = 227 * 1024;
 #define BV2_SMEM_ATTR(k) BV2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
-    BV2_SMEM_ATTR((k_tc_conv1d<0, 0>)); BV2_SMEM_ATTR((k_tc_conv1d<1, 0>)); BV2_SMEM_ATTR((k_tc_conv1d<0, 1>)); BV2_SMEM_ATTR((k_tc_conv1d<1, 1>));
+    BV2_SMEM_ATTR((k_tc_conv1d<0, 0>)); BV2_SMEM_ATTR((k_tc_conv1d<1, 0>)); BV2_SMEM_ATTR((k_tc_conv1d<0, 1>)); BV2_SMEM_ATTR((k_tc_conv1d<1, 1>)); BV2_SMEM_ATTR((k_tc_conv1d<1, 1, 1>));
     BV2_SMEM_ATTR((k_tc_conv1d_persist<0, 2, 0>)); BV2_SMEM_ATTR((k_tc_conv1d_persist<1, 2, 0>));
     BV2_SMEM_ATTR((k_tc_conv1d_persist<0, 2, 1>)); BV2_SMEM_ATTR((k_tc_conv1d_persist<1, 2, 1>));
     BV2_SMEM_ATTR((k_tc_conv1d_pstream<0, 0>)); BV2_SMEM_ATTR((k_tc_conv1d_pstream<1, 0>));
@@ -1511,17 +1598,28 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     uint32_t budget = (nctas > num_sms && nt <= 128) ? (uint32_t)tune_env("BV2_TC_SMEM_KB", 48) * 1024 : 200 * 1024;
     if (nt > 128 && 2 * nctas > num_sms && 2ull * p.a_stage_bytes + 2ull * p.w_stage_bytes + 2048 <= 112 * 1024)
         budget = 112 * 1024;  // wide layer launched on three streams at once (MRF resblock chains): let two CTAs share an SM
+    // LayerNorm tail with a residual, at most one CTA per SM (small batches: the launch is a latency chain, not a throughput problem):
+    // the residual tile is staged in shared memory by TMA (nt/4 channel groups x 128 rows x 16 B) instead of being pre-loaded into the
+    // accumulator; the rings shrink to make room (the weight ring never needs more stages than the conv has)
+    const bool res_smem = e.ln_gamma && p.res_mode == 1 && !p.accumulate && nctas <= num_sms && p.res_c_off % 4 == 0 && tune_env("BV2_LN_RES_SMEM", 1);
+    const uint32_t res_bytes = res_smem ? (uint32_t)nt * 512u : 0u;
+    if (res_smem) budget = 224 * 1024 - res_bytes;
     int nas = std::min(3, std::max(2, p.nchunks));
     while (nas > 2 && (size_t)nas * p.a_stage_bytes + 4 * (size_t)p.w_stage_bytes + 1024 > budget) nas--;
     p.nas = nas;
     int nws = ((int)budget - nas * (int)p.a_stage_bytes - 1024) / (int)p.w_stage_bytes;
-    p.nws = std::max(2, std::min(nws, 8));
+    // one CTA per SM anyway (small grid): as deep a weight ring as fits, up to every stage of the conv -- the weight producer is a static
+    // role that runs ahead of the PDL wait, so the whole weight set of a 36-stage FFN conv_2 tile is resident before its operands arrive
+    p.nws = std::max(2, std::min(nws, nctas <= num_sms ? tune_env("BV2_TC_NWS_MAX", 40) : 8));
+    p.nws = std::max(2, std::min(p.nws, p.nchunks * p.K));
     uint32_t cols = 32; while ((int)cols < nt) cols <<= 1;
     p.tmem_cols = cols;
-    const size_t smem = (size_t)p.nas * p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + (size_t)(3 * p.nas + 2 * p.nws + 2) * 8 + 16;
+    size_t smem = (size_t)p.nas * p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + (size_t)(3 * p.nas + 2 * p.nws + 3) * 8 + 16;
+    if (res_smem) { smem = (smem + 15) & ~(size_t)15; p.res_soff = (uint32_t)smem; smem += res_bytes; }
     BV2_CHECK(smem <= 227 * 1024, "tc_conv1d shared memory");
     dim3 grid(cdiv(p.T, 128), ntiles, p.B);
-    if (generic) launch_pdl(F16 ? k_tc_conv1d<1, 1> : k_tc_conv1d<1, 0>, grid, dim3(224), smem, st, p);
+    if (res_smem && F16 && nt == 192 && tune_env("BV2_LN_REGS", 1)) launch_pdl(k_tc_conv1d<1, 1, 1>, grid, dim3(224), smem, st, p);
+    else if (generic) launch_pdl(F16 ? k_tc_conv1d<1, 1> : k_tc_conv1d<1, 0>, grid, dim3(224), smem, st, p);
     else launch_pdl(F16 ? k_tc_conv1d<0, 1> : k_tc_conv1d<0, 0>, grid, dim3(224), smem, st, p);
 }
 
@@ -1541,7 +1639,7 @@ inline void tc_launch_simple(TcParams& p, int ntiles, int zdim, cudaStream_t st)
     uint32_t cols = 32; while ((int)cols < p.nt) cols <<= 1;
     p.tmem_cols = cols;
     p.idesc = tc::make_idesc(0, p.nt);
-    const size_t smem = (size_t)p.nas * p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + (size_t)(3 * p.nas + 2 * p.nws + 2) * 8 + 16;
+    const size_t smem = (size_t)p.nas * p.a_stage_bytes + (size_t)p.nws * p.w_stage_bytes + (size_t)(3 * p.nas + 2 * p.nws + 3) * 8 + 16;
     BV2_CHECK(smem <= 227 * 1024, "tc gemm shared memory");
     dim3 grid(cdiv(p.T, 128), ntiles, zdim);
     launch_pdl(k_tc_conv1d<0, 0>, grid, dim3(224), smem, st, p);

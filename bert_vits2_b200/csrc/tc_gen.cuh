@@ -249,6 +249,20 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
         q.hi = (uint64_t)desc_hi << 32;
         if (nk == 2) g2_issuer_mg<2>(q, MG, prof, lane);
         else g2_issuer_mg<1>(q, MG, prof, lane);  // g2_conv() admits KC = 16 or 32 only
+    } else if (warp == 3) {
+        // ===== zero halo of the OUTPUT tensor (= the conv padding of its consumers), written by its producer: the CTA of the first super-tile
+        // clears rows [-G2_PADL, 0), the CTA of the last one rows [T_out, T_out + G2_PADR), for every channel group of batch b (N tile 0 only).
+        // (Round 2 until now: one k_g2_zero_halo launch per Generator stage -- six plain launches, each a full drain of the PDL chain.)
+        if (ntile == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");  // the rows may alias a tensor an upstream kernel is still reading
+            uint4* yb = p.y + (size_t)b * p.y_cg * p.y_Tp;
+            const int Tout = p.T * (p.ups_u ? p.ups_u : 1);
+            const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+            if (blockIdx.x == 0)
+                for (int i = lane; i < p.y_cg * G2_PADL; i += 32) yb[(size_t)(i / G2_PADL) * p.y_Tp + (i % G2_PADL) - G2_PADL] = z4;
+            if (blockIdx.x == gridDim.x - 1)
+                for (int i = lane; i < p.y_cg * G2_PADR; i += 32) yb[(size_t)(i / G2_PADR) * p.y_Tp + Tout + (i % G2_PADR)] = z4;
+        }
     } else if (warp >= 4) {
         // ===== epilogue, 12 warps: TMEM lane quarter q = warp & 3; the 3 warps of a quarter share the (m-tile, 32-column batch) items
         // round-robin.  Two phases:
@@ -359,7 +373,8 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
     }
 }
 
-// ---- halo zeroing: the zero rows around every H8 tensor are the conv padding of its consumers.  One launch per Generator stage
+// ---- halo zeroing as a separate launch (probes; the engine's producers clear the halos of their own outputs, see k_g2_conv warp 3): the zero
+// rows around every H8 tensor are the conv padding of its consumers.  One launch per Generator stage
 // covers all tensors of the stage (the workspace is a bump arena: a stage's buffers alias whatever the previous call left there).
 struct G2HaloList { uint4* p[16]; int cg_rows[16]; int T[16]; int Tp[16]; int n; };  // cg_rows = B * C/8 channel-group runs
 __global__ void __launch_bounds__(128) k_g2_zero_halo(G2HaloList l) {
@@ -376,6 +391,9 @@ __global__ void __launch_bounds__(128) k_g2_zero_halo(G2HaloList l) {
 // fp32 c4 [B][C/4][T][4] (rows t >= lens[b] read as zero) -> raw f16 H8 (no activation): the Generator's input z * y_mask
 __global__ void __launch_bounds__(128) k_c4_to_h8(const float4* __restrict__ x, uint4* __restrict__ y, int C, int T, int Tp, const int* __restrict__ lens) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x, g = blockIdx.y, b = blockIdx.z;
+    // zero halo of the output (conv_pre's padding): first / last block of each channel-group run
+    if (blockIdx.x == 0 && threadIdx.x < G2_PADL) y[((size_t)b * (C / 8) + g) * Tp + (int)threadIdx.x - G2_PADL] = make_uint4(0u, 0u, 0u, 0u);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x < G2_PADR) y[((size_t)b * (C / 8) + g) * Tp + T + threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
     if (t >= T) return;
     const bool in = !lens || t < lens[b];
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
@@ -387,27 +405,43 @@ __global__ void __launch_bounds__(128) k_c4_to_h8(const float4* __restrict__ x, 
 
 // conv_post (C -> 1, K taps, no bias) + tanh on an H8 input (reference models.py:553-555: F.leaky_relu default slope 0.01,
 // recovered from the stored lrelu_0.1 value as a >= 0 ? a : 0.1 a); the zero halo supplies the conv padding.
+// The kernel is issue-bound, not HBM-bound (17 MB at config 2): with one output per thread reading its own K rows every element was
+// unpacked + activated K times and every FMA fetched its weight from shared memory (~40 instructions per 16-byte load, 24 us).  Here a block
+// stages TB + K - 1 rows ONCE as activated fp32 in shared memory (coalesced 16-byte loads, conflict-free stores), the weights ride in the
+// kernel parameters (constant bank: FFMA takes them as an operand), and a thread's inner loop is one conflict-free LDS + one FFMA per tap.
+template <int C, int K> struct PostW { float w[C * K]; };  // [C][K]
 template <int C, int K>
-__global__ void __launch_bounds__(256) k_conv_post_tanh_h8(const uint4* __restrict__ x, int Tp, const float* __restrict__ w, float* __restrict__ y, int T) {
-    __shared__ float sw[C * K];
-    for (int i = threadIdx.x; i < C * K; i += blockDim.x) sw[i] = w[i];  // [C][K]
+__global__ void __launch_bounds__(256) k_conv_post_tanh_h8(const uint4* __restrict__ x, int Tp, const __grid_constant__ PostW<C, K> pw, float* __restrict__ y, int T) {
+    constexpr int TB = 512, RW = TB + K - 1, LD = RW + 2;  // outputs per block, staged rows, row stride of the staged tile
+    __shared__ float sx[C][LD];
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    __syncthreads();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-    if (t >= T) return;
-    float acc = 0.f;
+    const int t0 = blockIdx.x * TB, b = blockIdx.y;
+    for (int i = threadIdx.x; i < (C / 8) * RW; i += blockDim.x) {
+        const int g = i / RW, r = i - g * RW, row = t0 - K / 2 + r;  // row >= -K/2 >= -G2_PADL; rows >= T + G2_PADR lie outside the allocation
+        float f[8];
+        if (row < T + G2_PADR) tc::unpack8(x[((size_t)b * (C / 8) + g) * Tp + row], f);
+        else {
 #pragma unroll
-    for (int g = 0; g < C / 8; g++) {
-        const uint4* xr = x + ((size_t)b * (C / 8) + g) * Tp + t - K / 2;
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            float f[8];
-            tc::unpack8(xr[j], f);
-#pragma unroll
-            for (int k = 0; k < 8; k++) acc = fmaf(f[k] >= 0.f ? f[k] : 0.1f * f[k], sw[(g * 8 + k) * K + j], acc);
+            for (int k = 0; k < 8; k++) f[k] = 0.f;
         }
+#pragma unroll
+        for (int k = 0; k < 8; k++) sx[g * 8 + k][r] = fmaxf(f[k], 0.1f * f[k]);  // a >= 0 ? a : 0.1 a
     }
-    y[(size_t)b * T + t] = tanhf(acc);
+    __syncthreads();
+#pragma unroll
+    for (int o = 0; o < TB / 256; o++) {
+        const int tl = threadIdx.x + o * 256, t = t0 + tl;
+        float acc = 0.f;
+#pragma unroll
+        for (int g = 0; g < C / 8; g++) {
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc = fmaf(sx[g * 8 + k][tl + j], pw.w[(g * 8 + k) * K + j], acc);
+            }
+        }
+        if (t < T) y[(size_t)b * T + t] = tanhf(acc);
+    }
 }
 
 inline void g2_init_device() {

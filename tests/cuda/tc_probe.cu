@@ -409,7 +409,7 @@ static void run_flow_timeline(const char* name, int Cin, int Cout, int K, int nt
     cudaMemcpy(h.data(), dprof, h.size() * 8, cudaMemcpyDeviceToHost);
     long long t0 = h[0];
     for (int i = 0; i < nctas; i++) if (h[i * 8]) t0 = std::min(t0, h[i * 8]);
-    printf("FLOW %-10s Cin=%3d Cout=%3d K=%d nt=%3d kc=%2d T=%d : %d CTAs, %.2f us per launch (back to back)%s\n", name, Cin, Cout, K, tw.nt, tw.KC, T, nctas, ms * 1e3,
+    printf("FLOW %-24s Cin=%3d Cout=%3d K=%d nt=%3d kc=%2d T=%d : %d CTAs, %.2f us per launch (back to back)%s\n", name, Cin, Cout, K, tw.nt, tw.KC, T, nctas, ms * 1e3,
            er == cudaSuccess ? "" : "  CUDA ERROR");
     printf("   ns since first CTA start: cta: start | pdl-wait end | acc init done | first A landed | first A ready (MMA starts) | MMA issue end | acc full | tail end\n");
     for (int i : {0, nctas / 2, nctas - 1}) {
@@ -485,6 +485,24 @@ static int run_attn(int T, int B, std::vector<int> lens, int lbo_is_kblock, int 
         cudaEventRecord(a);
         for (int i = 0; i < iters; i++) tc_flow_attn(aq, aa, dek, dev_, dl, heads, w, 0, mn, 148, ks);
         cudaEventRecord(c); cudaEventSynchronize(c); cudaEventElapsedTime(&ms, a, c); ms /= iters;
+        if (getenv("PROBE_ATTN_TIMELINE") && B == 1) {  // per-CTA phase stamps of one more launch behind a back-to-back train
+            const int ksr = ks > 0 ? ks : 4, nctas = ((T + 127) / 128) * ksr * heads;  // upper bound on the grid
+            long long* dprof; cudaMalloc(&dprof, (size_t)nctas * 10 * 8); cudaMemset(dprof, 0, (size_t)nctas * 10 * 8);
+            for (int i = 0; i < 5; i++) tc_flow_attn(aq, aa, dek, dev_, dl, heads, w, 0, mn, 148, ks, i == 4 ? dprof : nullptr);
+            cudaDeviceSynchronize();
+            std::vector<long long> hp((size_t)nctas * 10);
+            cudaMemcpy(hp.data(), dprof, hp.size() * 8, cudaMemcpyDeviceToHost);
+            long long t0 = 0;
+            for (int i = 0; i < nctas; i++) if (hp[(size_t)i * 10] && (!t0 || hp[(size_t)i * 10] < t0)) t0 = hp[(size_t)i * 10];
+            printf("   ATTN timeline (ns since first CTA start): cta: start | pdl-wait end | q.Ek done | pass A end | pass B end | O full | parked | cluster barrier 1 | merged+stored | end\n");
+            for (int i : {0, 1, nctas / 2, nctas - 1}) {
+                const long long* q = &hp[(size_t)i * 10];
+                if (!q[0]) continue;
+                printf("   cta %3d:", i);
+                for (int k = 0; k < 10; k++) printf(" %6lld %s", q[k] ? q[k] - t0 : -1, k < 9 ? "|" : "\n");
+            }
+            cudaFree(dprof);
+        }
     }
     const bool ok = maxerr < 4e-3 * std::max(1.0, maxref) && maxerr == maxerr;
     printf("%s ATTN T=%d B=%d len0=%d mn=%d key-split=%d (0 = auto) : maxerr %.3e (ref max %.3f)", ok ? "PASS" : "FAIL", T, B, lens[0], lbo_is_kblock, ks, maxerr, maxref);
@@ -511,6 +529,12 @@ int main(int argc, char** argv) {
             run_flow_timeline("conv_2 f16i", 768, 192, 3, 32, 64, F, 16);
             run_flow_timeline("conv_2 f16i n96", 768, 192, 3, 96, 64, F, 16);
             run_flow_timeline("post", 192, 96, 1, 96, 64, F, 4);
+            // LayerNorm tails: residual staged in shared memory by TMA (default) vs pre-loaded into the accumulator (BV2_LN_RES_SMEM=0)
+            run_flow_timeline("conv_2+LN f16i n192", 768, 192, 3, 192, 64, F, 4 | 8 | 16);
+            setenv("BV2_LN_RES_SMEM", "0", 1);
+            run_flow_timeline("conv_o+LN res->acc", 192, 192, 1, 192, 64, F, 4 | 8 | 16);
+            run_flow_timeline("conv_2+LN n192 res->acc", 768, 192, 3, 192, 64, F, 4 | 8 | 16);
+            unsetenv("BV2_LN_RES_SMEM");
             return 0;
         }
         if (getenv("PROBE_ATTN")) {
