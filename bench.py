@@ -494,7 +494,10 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "Generator stage (conv_pre .. conv_post+tanh, 98 convolutions)", "achieved": ach, "peak": hbm,
                          "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "traffic_source": traffic_note, "peak_source": how, "stage_ms": g_ms,
-                         "tensor_tflops": GEN_FLOP_PER_FRAME * fpu / (g_ms * 1e-3) / 1e12, "build_id": bid},
+                         "tensor_tflops": GEN_FLOP_PER_FRAME * fpu / (g_ms * 1e-3) / 1e12, "build_id": bid,
+                         "algorithmic_bytes_convention": "SURVEY.md 8d: fp32 layer-boundary tensors, 6 830 852 B per frame; the fp16 engine keeps the "
+                                                         "Generator's tensors as 16-bit operand images, so its DRAM traffic is well below that figure",
+                         "dram_gbs_actual": (traffic / (g_ms * 1e-3) / 1e9) if traffic else None},
             "stage_ms": {"encoder_duration": enc_ms, "flow": flow_ms, "generator": g_ms},
             "launches_per_step": launches / args.steps,
         }

@@ -47,6 +47,78 @@ __device__ __forceinline__ void unpack_h8(const uint4& u, float* f) {
 }
 }  // namespace tc
 
+// Merge of the key splits (flash-decoding style) for one thread: row m of the query tile, 96/KSC channels.  Every distributed-shared-memory
+// load is issued before the first dependent instruction (a ld.shared::cluster round trip is ~0.2 us; interleaved with the arithmetic the 36
+// loads of a 4-way merge ran one after the other: 8.4 us of the 30 us kernel at config 2, profiles/r02j_attn_timeline.log).
+// Peers are combined in fixed rank order: deterministic.
+template <int KSC, int DK>
+__device__ __forceinline__ void attn_merge_rows(uint32_t sK_addr, const float* sEv, int rk, int t, int q0, int len, int T, int nrel, uint4* obase) {
+    using namespace tc;
+    constexpr int NREL = 9, rows_per = 128 / KSC, nf4 = (DK / 4) / KSC;  // float4 slots (4 channels each) of this thread: 12 (KSC = 2) or 6 (KSC = 4)
+    constexpr float LOG2E = 1.4426950408889634f;
+    static_assert(DK == 96 && nf4 % 2 == 0, "channel split of the merge");
+    const int m = rk * rows_per + t % rows_per, part = t / rows_per, i = q0 + m;
+    const uint32_t local = sK_addr + (uint32_t)m * 16u;
+    float4 st4[KSC][3], ov[KSC][nf4];
+#pragma unroll
+    for (int r2 = 0; r2 < KSC; r2++) {
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r2));
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(st4[r2][k].x), "=f"(st4[r2][k].y), "=f"(st4[r2][k].z), "=f"(st4[r2][k].w) : "r"(remote + (24u + (uint32_t)k) * 2048u));
+        const uint32_t rbase = remote + (uint32_t)(part * nf4) * 2048u;
+#pragma unroll
+        for (int g = 0; g < nf4; g++)
+            asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ov[r2][g].x), "=f"(ov[r2][g].y), "=f"(ov[r2][g].z), "=f"(ov[r2][g].w) : "r"(rbase + (uint32_t)g * 2048u));
+    }
+    float M = -INFINITY;
+#pragma unroll
+    for (int r2 = 0; r2 < KSC; r2++) M = fmaxf(M, st4[r2][0].x);
+    float L = 0.f;
+    float prel[NREL];
+#pragma unroll
+    for (int r = 0; r < NREL; r++) prel[r] = 0.f;
+    float o[4 * nf4];
+#pragma unroll
+    for (int e = 0; e < 4 * nf4; e++) o[e] = 0.f;
+#pragma unroll
+    for (int r2 = 0; r2 < KSC; r2++) {
+        const float4 a4 = st4[r2][0], b4 = st4[r2][1], c4 = st4[r2][2];  // (m, l, prel0, prel1), prel2..5, prel6..8
+        const float wgt = a4.x == -INFINITY ? 0.f : ex2_approx((a4.x - M) * LOG2E);
+        L = fmaf(wgt, a4.y, L);
+        prel[0] = fmaf(wgt, a4.z, prel[0]); prel[1] = fmaf(wgt, a4.w, prel[1]);
+        prel[2] = fmaf(wgt, b4.x, prel[2]); prel[3] = fmaf(wgt, b4.y, prel[3]); prel[4] = fmaf(wgt, b4.z, prel[4]); prel[5] = fmaf(wgt, b4.w, prel[5]);
+        prel[6] = fmaf(wgt, c4.x, prel[6]); prel[7] = fmaf(wgt, c4.y, prel[7]); prel[8] = fmaf(wgt, c4.z, prel[8]);
+#pragma unroll
+        for (int g = 0; g < nf4; g++) {
+            const float4 v4 = ov[r2][g];
+            o[4 * g] = fmaf(wgt, v4.x, o[4 * g]); o[4 * g + 1] = fmaf(wgt, v4.y, o[4 * g + 1]);
+            o[4 * g + 2] = fmaf(wgt, v4.z, o[4 * g + 2]); o[4 * g + 3] = fmaf(wgt, v4.w, o[4 * g + 3]);
+        }
+    }
+    const float inv = (i < len && L > 0.f) ? 1.f / L : 0.f;
+    const int ch0 = part * nf4 * 4;  // first channel of this thread
+#pragma unroll
+    for (int r = 0; r < NREL; r++) {
+        if (r < nrel) {
+            const float pw = prel[r];
+            const float* ev = &sEv[r * DK + ch0];
+#pragma unroll
+            for (int e = 0; e < 4 * nf4; e++) o[e] = fmaf(pw, ev[e], o[e]);
+        }
+    }
+    if (i < T) {
+#pragma unroll
+        for (int g = 0; g < nf4 / 2; g++) {
+            uint4 u;
+            u.x = pack_h2(o[8 * g] * inv, o[8 * g + 1] * inv); u.y = pack_h2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
+            u.z = pack_h2(o[8 * g + 4] * inv, o[8 * g + 5] * inv); u.w = pack_h2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
+            obase[(size_t)(ch0 / 8 + g) * T + i] = u;
+        }
+    }
+}
+
 template <int DK, int KT>
 __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
     using namespace tc;
@@ -342,82 +414,9 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
         // CTA rk merges rows [rk * 128/KS, (rk + 1) * 128/KS); KS threads share a row (96/KS channels each), consecutive lanes take
         // consecutive rows (coalesced distributed-shared-memory reads)
         if (warp >= 2) {
-            const int t = (warp - 2) * 32 + lane, rows_per = 128 / KS;
-            const int m = rk * rows_per + t % rows_per, part = t / rows_per, i = q0 + m;
-            const int nf4 = 24 / KS;  // float4 slots (4 channels each) of this thread: 12 (KS = 2) or 6 (KS = 4)
-            const uint32_t local = smem_u32(sK) + (uint32_t)m * 16u;
-            float Mr[4], wr[4];
-            float M = -INFINITY;
-#pragma unroll
-            for (int r2 = 0; r2 < 4; r2++) {
-                Mr[r2] = -INFINITY;
-                if (r2 < KS) {
-                    uint32_t remote;
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local + 24u * 2048u), "r"(r2));
-                    float4 s4;
-                    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w) : "r"(remote));
-                    Mr[r2] = s4.x; M = fmaxf(M, s4.x);
-                }
-            }
-            float L = 0.f;
-            float prel[NREL];
-#pragma unroll
-            for (int r = 0; r < NREL; r++) prel[r] = 0.f;
-            float o[48];
-#pragma unroll
-            for (int e = 0; e < 48; e++) o[e] = 0.f;
-#pragma unroll
-            for (int r2 = 0; r2 < 4; r2++) {  // fixed rank order: deterministic
-                wr[r2] = 0.f;
-                if (r2 < KS) {
-                    const float wgt = Mr[r2] == -INFINITY ? 0.f : ex2_approx((Mr[r2] - M) * LOG2E);
-                    wr[r2] = wgt;
-                    uint32_t remote;
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r2));
-                    float4 a4, b4, c4;
-                    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a4.x), "=f"(a4.y), "=f"(a4.z), "=f"(a4.w) : "r"(remote + 24u * 2048u));
-                    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(remote + 25u * 2048u));
-                    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w) : "r"(remote + 26u * 2048u));
-                    L = fmaf(wgt, a4.y, L);
-                    prel[0] = fmaf(wgt, a4.z, prel[0]); prel[1] = fmaf(wgt, a4.w, prel[1]);
-                    prel[2] = fmaf(wgt, b4.x, prel[2]); prel[3] = fmaf(wgt, b4.y, prel[3]); prel[4] = fmaf(wgt, b4.z, prel[4]); prel[5] = fmaf(wgt, b4.w, prel[5]);
-                    prel[6] = fmaf(wgt, c4.x, prel[6]); prel[7] = fmaf(wgt, c4.y, prel[7]); prel[8] = fmaf(wgt, c4.z, prel[8]);
-                    const uint32_t rbase = remote + (uint32_t)(part * nf4) * 2048u;
-#pragma unroll
-                    for (int g = 0; g < 12; g++) {
-                        if (g < nf4) {
-                            float4 v4;
-                            asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v4.x), "=f"(v4.y), "=f"(v4.z), "=f"(v4.w) : "r"(rbase + (uint32_t)g * 2048u));
-                            o[4 * g] = fmaf(wgt, v4.x, o[4 * g]); o[4 * g + 1] = fmaf(wgt, v4.y, o[4 * g + 1]);
-                            o[4 * g + 2] = fmaf(wgt, v4.z, o[4 * g + 2]); o[4 * g + 3] = fmaf(wgt, v4.w, o[4 * g + 3]);
-                        }
-                    }
-                }
-            }
-            const float inv = (i < len && L > 0.f) ? 1.f / L : 0.f;
-            const int ch0 = part * nf4 * 4;  // first channel of this thread
-#pragma unroll
-            for (int r = 0; r < NREL; r++) {
-                if (r < nrel) {
-                    const float pw = prel[r];
-                    const float* ev = &sEv[r * DK + ch0];
-#pragma unroll
-                    for (int e = 0; e < 48; e++)
-                        if (e < 4 * nf4) o[e] = fmaf(pw, ev[e], o[e]);
-                }
-            }
-            if (i < p.T) {
-                uint4* obase = p.att + ((size_t)b * H8 + (size_t)h * NG) * p.T;
-#pragma unroll
-                for (int g = 0; g < 6; g++) {
-                    if (2 * g < nf4) {
-                        uint4 u;
-                        u.x = pack_h2(o[8 * g] * inv, o[8 * g + 1] * inv); u.y = pack_h2(o[8 * g + 2] * inv, o[8 * g + 3] * inv);
-                        u.z = pack_h2(o[8 * g + 4] * inv, o[8 * g + 5] * inv); u.w = pack_h2(o[8 * g + 6] * inv, o[8 * g + 7] * inv);
-                        obase[(size_t)(ch0 / 8 + g) * p.T + i] = u;
-                    }
-                }
-            }
+            uint4* obase = p.att + ((size_t)b * H8 + (size_t)h * NG) * p.T;
+            if (KS == 4) attn_merge_rows<4, DK>(smem_u32(sK), sEv, rk, (warp - 2) * 32 + lane, q0, len, p.T, nrel, obase);
+            else attn_merge_rows<2, DK>(smem_u32(sK), sEv, rk, (warp - 2) * 32 + lane, q0, len, p.T, nrel, obase);
         }
         if (stamp) prof[8] = gtimer();
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");  // peers are done reading this CTA's rows

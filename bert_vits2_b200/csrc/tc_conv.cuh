@@ -566,46 +566,6 @@ __device__ __forceinline__ void acc_tail_ln(const TcParams& p, uint32_t trow, in
     }
 }
 
-// LayerNorm tail with the whole row in registers (NT columns: one TMEM read instead of three passes, every tcgen05.ld in flight at once).
-// Needs ~NT + 40 registers per thread: only the LNT instantiation of k_tc_conv1d (one CTA per SM, small grids) uses it.
-template <int NT>
-__device__ __forceinline__ void acc_tail_ln_regs(const TcParams& p, uint32_t trow, int b, int t, int len, const float4* rs) {
-    static_assert(NT % 32 == 0, "row width");
-    uint32_t v[NT];
-#pragma unroll
-    for (int c0 = 0; c0 < NT; c0 += 32) tmem_ld32(trow + (uint32_t)c0, v + c0);
-    tmem_wait_ld();
-    float x[NT];
-#pragma unroll
-    for (int e = 0; e < NT; e++) x[e] = __uint_as_float(v[e]);
-    if (rs) {
-#pragma unroll
-        for (int g = 0; g < NT / 4; g++) {
-            const float4 r = rs[(size_t)g * 128];
-            x[4 * g] += r.x; x[4 * g + 1] += r.y; x[4 * g + 2] += r.z; x[4 * g + 3] += r.w;
-        }
-    }
-    float s = 0.f;
-#pragma unroll
-    for (int e = 0; e < NT; e++) s += x[e];
-    const float mean = s / (float)NT;
-    float q = 0.f;
-#pragma unroll
-    for (int e = 0; e < NT; e++) { const float d = x[e] - mean; q = fmaf(d, d, q); }
-    const float rstd = rsqrtf(q / (float)NT + 1e-5f);
-    if (t >= p.T) return;
-    const float m = (p.out_mask && t >= len) ? 0.f : 1.f;
-    float4* ybp = reinterpret_cast<float4*>(p.y) + ((size_t)b * (p.Cout_total / 4) + p.cout_off / 4) * p.T + t;
-#pragma unroll
-    for (int g = 0; g < NT / 4; g++) {
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + 4 * g)), be = __ldg(reinterpret_cast<const float4*>(p.ln_beta + 4 * g));
-        float4 o;
-        o.x = ((x[4 * g] - mean) * rstd * ga.x + be.x) * m; o.y = ((x[4 * g + 1] - mean) * rstd * ga.y + be.y) * m;
-        o.z = ((x[4 * g + 2] - mean) * rstd * ga.z + be.z) * m; o.w = ((x[4 * g + 3] - mean) * rstd * ga.w + be.w) * m;
-        ybp[(size_t)g * p.T] = o;
-    }
-}
-
 // TF32 operand prologue of one staged activation chunk [ncg][R][4] (generic proxy), in place: leaky-relu + RN-TF32, zero
 // rows outside [r_lo, r_hi).  The stage is contiguous, so the loop runs over flat 16-byte elements with 4 independent
 // load->store chains per thread (the un-unrolled per-row loop exposed the full LDS latency on every element).
@@ -672,10 +632,8 @@ __device__ __forceinline__ void xform16_stage(const float4* S, uint4* O, int ncg
 // Accumulator-init fusion: before the first MMA the epilogue warps pre-load  bias (+ per-batch bias) (+/- residual)
 // (+ previous output when accumulating)  into the TMEM accumulator with tcgen05.st while the first TMA loads are in
 // flight; every MMA then accumulates, and the tail is only  TMEM -> [relu] -> scale/mask -> store.
-// LNT = 1: instantiation for the LayerNorm tail on small grids (one CTA per SM): 255 registers per thread, the tail keeps its whole
-// 192-column row in registers (acc_tail_ln_regs).
-template <int GEN, int F16, int LNT = 0>
-__global__ void __launch_bounds__(224, LNT ? 1 : 4) k_tc_conv1d(TcParams p) {
+template <int GEN, int F16>
+__global__ void __launch_bounds__(224, 4) k_tc_conv1d(TcParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -890,8 +848,9 @@ __global__ void __launch_bounds__(224, LNT ? 1 : 4) k_tc_conv1d(TcParams p) {
         if (GEN && p.ln_gamma) {
             const float4* rs = nullptr;
             if (res_smem) { mbar_wait(BAR(B_RES), 0); rs = reinterpret_cast<const float4*>(smem + p.res_soff) + (q * 32 + lane); }
-            if (LNT && nt == 192) acc_tail_ln_regs<192>(p, tmem + ((uint32_t)(q * 32) << 16), b, t0 + q * 32 + lane, len, rs);
-            else acc_tail_ln(p, tmem + ((uint32_t)(q * 32) << 16), b, t0 + q * 32 + lane, nt, len, rs);
+            // (a 255-register instantiation that kept the 192-column row in registers -- one tcgen05.ld round trip instead of 24 -- ran
+            //  11.1 us instead of 13.2 us per launch back to back but 1 us per layer SLOWER inside the flow: profiles/r02k_ab_ln_regs_weight_ring.jsonl)
+            acc_tail_ln(p, tmem + ((uint32_t)(q * 32) << 16), b, t0 + q * 32 + lane, nt, len, rs);
         } else {
             for (int mt = 0; mt < MT; mt++)
                 acc_tail_tile<4, GEN>(p, tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * nt), b, t0 + mt * 128 + q * 32 + lane, n0, nt, len, yb, cout_off);
@@ -1489,7 +1448,7 @@ inline void tc_clear_error() {
 inline int* tc_init_device() {
     const int mx = 227 * 1024;
 #define BV2_SMEM_ATTR(k) BV2_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, mx))
-    BV2_SMEM_ATTR((k_tc_conv1d<0, 0>)); BV2_SMEM_ATTR((k_tc_conv1d<1, 0>)); BV2_SMEM_ATTR((k_tc_conv1d<0, 1>)); BV2_SMEM_ATTR((k_tc_conv1d<1, 1>)); BV2_SMEM_ATTR((k_tc_conv1d<1, 1, 1>));
+    BV2_SMEM_ATTR((k_tc_conv1d<0, 0>)); BV2_SMEM_ATTR((k_tc_conv1d<1, 0>)); BV2_SMEM_ATTR((k_tc_conv1d<0, 1>)); BV2_SMEM_ATTR((k_tc_conv1d<1, 1>));
     BV2_SMEM_ATTR((k_tc_conv1d_persist<0, 2, 0>)); BV2_SMEM_ATTR((k_tc_conv1d_persist<1, 2, 0>));
     BV2_SMEM_ATTR((k_tc_conv1d_persist<0, 2, 1>)); BV2_SMEM_ATTR((k_tc_conv1d_persist<1, 2, 1>));
     BV2_SMEM_ATTR((k_tc_conv1d_pstream<0, 0>)); BV2_SMEM_ATTR((k_tc_conv1d_pstream<1, 0>));
@@ -1608,9 +1567,9 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     while (nas > 2 && (size_t)nas * p.a_stage_bytes + 4 * (size_t)p.w_stage_bytes + 1024 > budget) nas--;
     p.nas = nas;
     int nws = ((int)budget - nas * (int)p.a_stage_bytes - 1024) / (int)p.w_stage_bytes;
-    // one CTA per SM anyway (small grid): as deep a weight ring as fits, up to every stage of the conv -- the weight producer is a static
-    // role that runs ahead of the PDL wait, so the whole weight set of a 36-stage FFN conv_2 tile is resident before its operands arrive
-    p.nws = std::max(2, std::min(nws, nctas <= num_sms ? tune_env("BV2_TC_NWS_MAX", 40) : 8));
+    // (a ring as deep as the conv on small grids -- every weight stage of a 36-stage FFN conv_2 tile in flight ahead of the PDL wait -- measured
+    //  no gain: 14.2 -> 14.1 us per launch, profiles/r02k_ab_ln_regs_weight_ring.jsonl)
+    p.nws = std::max(2, std::min(nws, tune_env("BV2_TC_NWS_MAX", 8)));
     p.nws = std::max(2, std::min(p.nws, p.nchunks * p.K));
     uint32_t cols = 32; while ((int)cols < nt) cols <<= 1;
     p.tmem_cols = cols;
@@ -1618,8 +1577,7 @@ inline void tc_conv1d(const TcConvW& w, const float* bias, const Act& x, const A
     if (res_smem) { smem = (smem + 15) & ~(size_t)15; p.res_soff = (uint32_t)smem; smem += res_bytes; }
     BV2_CHECK(smem <= 227 * 1024, "tc_conv1d shared memory");
     dim3 grid(cdiv(p.T, 128), ntiles, p.B);
-    if (res_smem && F16 && nt == 192 && tune_env("BV2_LN_REGS", 1)) launch_pdl(k_tc_conv1d<1, 1, 1>, grid, dim3(224), smem, st, p);
-    else if (generic) launch_pdl(F16 ? k_tc_conv1d<1, 1> : k_tc_conv1d<1, 0>, grid, dim3(224), smem, st, p);
+    if (generic) launch_pdl(F16 ? k_tc_conv1d<1, 1> : k_tc_conv1d<1, 0>, grid, dim3(224), smem, st, p);
     else launch_pdl(F16 ? k_tc_conv1d<0, 1> : k_tc_conv1d<0, 0>, grid, dim3(224), smem, st, p);
 }
 

@@ -48,7 +48,7 @@ struct G2Params {
     int dbg_skip_wcommit;  // probes only: no weight-stage commits (valid only when every weight stage fits the ring)
     int dbg_flags;         // probes only (timing studies, wrong results): 1 = no tap shift (aligned A operand), 2 = no tcgen05.fence after the stage waits,
                            // 4 = no TMA traffic after the first ring fill (stale operands re-used: isolates shared-memory contention), 8 = epilogue warps
-                           // park in nanosleep polling instead of the hinted try_wait
+                           // park in nanosleep polling instead of the hinted try_wait, 16 = no halo zeroing of the output
     long long* prof;  // probes only: per-CTA timestamps [grid][16] (globaltimer ns / clock64 sums); nullptr in the engine
 };
 
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(512, 1) k_g2_conv(G2Params p) {
         // ===== zero halo of the OUTPUT tensor (= the conv padding of its consumers), written by its producer: the CTA of the first super-tile
         // clears rows [-G2_PADL, 0), the CTA of the last one rows [T_out, T_out + G2_PADR), for every channel group of batch b (N tile 0 only).
         // (Round 2 until now: one k_g2_zero_halo launch per Generator stage -- six plain launches, each a full drain of the PDL chain.)
-        if (ntile == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+        if (!(p.dbg_flags & 16) && ntile == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
             asm volatile("griddepcontrol.wait;" ::: "memory");  // the rows may alias a tensor an upstream kernel is still reading
             uint4* yb = p.y + (size_t)b * p.y_cg * p.y_Tp;
             const int Tout = p.T * (p.ups_u ? p.ups_u : 1);

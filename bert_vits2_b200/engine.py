@@ -55,7 +55,7 @@ class Engine:
     operands) or 'fp16' (tcgen05 with FP16 operands -- same 11-bit significand as TF32, twice the tensor rate, half the
     operand traffic; fp32 accumulate and fp32 activations in HBM).  Everything that feeds ceil(durations) is FP32 FMA in all three."""
 
-    def __init__(self, cfg: ModelConfig, state_dict: Optional[Dict[str, torch.Tensor]], device="cuda:0", precision: str = "tf32",
+    def __init__(self, cfg: ModelConfig, state_dict: Optional[Dict[str, torch.Tensor]], device="cuda:0", precision: str = "fp16",
                  packed_path: Optional[str] = None):
         self.lib = _lib.load()
         self.cfg = cfg

@@ -79,7 +79,7 @@ class SynthesizerTrn(nn.Module):
                  n_layers, kernel_size, p_dropout, resblock, resblock_kernel_sizes, resblock_dilation_sizes, upsample_rates,
                  upsample_initial_channel, upsample_kernel_sizes, n_speakers=256, gin_channels=256, use_sdp=True,
                  n_flow_layer=4, n_layers_trans_flow=4, flow_share_parameter=False, use_transformer_flow=True,
-                 precision: str = "tf32", init_seed: Optional[int] = 0, **kwargs):
+                 precision: str = "fp16", init_seed: Optional[int] = 0, **kwargs):
         super().__init__()
         if n_speakers < 1:
             raise ValueError("n_speakers == 0 (ReferenceEncoder path, models.py:752-808) is a training-only configuration")

@@ -16,7 +16,7 @@ from bert_vits2_b200.spec import ModelConfig  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=2)
-ap.add_argument("--precision", default="tf32")
+ap.add_argument("--precision", default="fp16")
 ap.add_argument("--T", type=int, default=256)
 ap.add_argument("--generator-only", type=int, default=0, help="frames; run bv2_generator only (config 5)")
 a = ap.parse_args()
