@@ -182,7 +182,7 @@ def cpu_oracle_rate(cfg, sd, budget_s=25.0, max_iters=3):
 def config_dict(frames, world=1, precision=None, parallelism="single GPU"):
     d = {"workload": WORKLOAD_NAME, "global_batch": world * WORKLOAD["B"], "T": WORKLOAD["T"], "length_scale": LENGTH_SCALE_CAL,
          "frames_per_utterance": frames, "audio_seconds_per_utterance": frames * HOP / SR, "parallelism": parallelism,
-         "l2": "no explicit flush: each step streams ~0.5 GB of fp32 activations (> 126 MB L2)"}
+         "l2": "no explicit flush: the working set of one step is far beyond the 126 MB L2 (ncu: the Generator alone moves 2.2 GB through DRAM per step, profiles/r02m_generator_traffic.json)"}
     if precision:
         d["precision"] = precision
     return d

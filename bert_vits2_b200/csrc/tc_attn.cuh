@@ -266,9 +266,11 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
 #pragma unroll
                 for (int r = 0; r < NREL; r++) {
                     if (r < nrel) {
-                        const float* e = &sEk[r * DK + g * 8];
-#pragma unroll
-                        for (int c = 0; c < 8; c++) qrel[r] = fmaf(qf[c], e[c], qrel[r]);
+                        const float4 e0 = *reinterpret_cast<const float4*>(&sEk[r * DK + g * 8]), e1 = *reinterpret_cast<const float4*>(&sEk[r * DK + g * 8 + 4]);
+                        float a = qrel[r];  // same accumulation order as a scalar loop over the 8 channels
+                        a = fmaf(qf[0], e0.x, a); a = fmaf(qf[1], e0.y, a); a = fmaf(qf[2], e0.z, a); a = fmaf(qf[3], e0.w, a);
+                        a = fmaf(qf[4], e1.x, a); a = fmaf(qf[5], e1.y, a); a = fmaf(qf[6], e1.z, a); a = fmaf(qf[7], e1.w, a);
+                        qrel[r] = a;
                     }
                 }
             }
@@ -287,7 +289,9 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                     uint32_t v[32];
                     tmem_ld32(trow + (uint32_t)(st * KT + c0), v);
                     tmem_wait_ld();
-                    if (band) {
+                    // relative-key terms only in the 32-column chunks that can hold a key within +-w of one of THIS warp's 32 query rows
+                    // (warp-uniform; the band logic costs ~8x the plain path per element and used to run on every chunk of an in-band tile)
+                    if (band && (k0 + c0 + 31 >= q0 + 32 * q - w) && (k0 + c0 <= q0 + 32 * q + 31 + w)) {
 #pragma unroll
                         for (int e = 0; e < 32; e++) {
                             const int d = k0 + c0 + e - i + w;
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                     tmem_ld32(trow + (uint32_t)(st * KT + c0), v);
                     tmem_wait_ld();
                     float pe[32];
-                    if (band) {
+                    if (band && (k0 + c0 + 31 >= q0 + 32 * q - w) && (k0 + c0 <= q0 + 32 * q + 31 + w)) {
 #pragma unroll
                         for (int e = 0; e < 32; e++) {
                             const int d = k0 + c0 + e - i + w;

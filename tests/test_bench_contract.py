@@ -35,6 +35,24 @@ def test_committed_bench_line_has_the_contract_keys():
     assert abs(d["value"] - d["config"]["audio_seconds_per_step"] / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
 
 
+def test_round2_bench_line_has_the_contract_keys_and_the_named_workloads():
+    """profiles/r02l_bench_fp16.json: the default `python bench.py` line of the round-2 build (written on the B200 box)."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02l_bench_fp16.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "stage_ms",
+              "config3_batched", "config5_generator", "flow_wn", "config2_length_scale_1"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0 and "workload" in d["config"] and "model" not in d["config"]
+    assert abs(d["value"] - d["config"]["audio_seconds_per_utterance"] * d["config"]["global_batch"] / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
+    e = d["e2e"]
+    assert 0 < e["value"] <= d["value"] * 1.02 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["workspace_regrowths_in_timed_loops"] == 0
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and "traffic" in r
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and "T=256" in c["sample"]  # same utterance as the GPU arm
+    assert len(d["config5_generator"]["sweep"]) >= 6 and d["config3_batched"]["value"] > 0 and d["flow_wn"]["value"] > 0
+
+
 def test_algorithmic_constants_match_the_survey():
     b = _bench()
     # SURVEY.md section 8d: Generator layer-boundary bytes and FLOPs per 512-sample frame
