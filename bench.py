@@ -64,14 +64,23 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def build_id():
+def build_id(only=None):
     """Hash of the CUDA sources: profile-derived numbers (roofline.traffic) are only attached when they were captured on this build."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "bert_vits2_b200", "csrc")
     for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
+        if f.endswith((".cu", ".cuh")) and (only is None or f in only):
             h.update(open(os.path.join(d, f), "rb").read())
     return h.hexdigest()[:16]
+
+
+#: the sources the Generator's launches are compiled from (k_g2_conv, conv_post, the H8 conversion, their host code): the DRAM bytes of
+#: those launches cannot change with an edit elsewhere (e.g. the attention kernel), so the traffic capture is keyed on these files
+GENERATOR_SOURCES = ("common.cuh", "tc_conv.cuh", "tc_gen.cuh", "engine.cu")
+
+
+def generator_build_id():
+    return build_id(GENERATOR_SOURCES)
 
 
 class ClockSampler:
@@ -473,9 +482,9 @@ def main():
         for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
             if name.endswith("_generator_traffic.json"):
                 tj = json.load(open(os.path.join(ROOT, "profiles", name)))
-                if tj.get("build_id") == bid:  # dram__bytes_read+write summed over the Generator launches of one ncu capture (per frame)
+                if tj.get("build_id") == bid or tj.get("generator_build_id") == generator_build_id():  # dram__bytes_read+write summed over the Generator launches of one ncu capture (per frame)
                     traffic = tj["generator_dram_bytes_per_frame"] * fpu
-                    traffic_note = f"profiles/{name} (same build)"
+                    traffic_note = f"profiles/{name} (" + ("same build" if tj.get("build_id") == bid else "same Generator sources") + ")"
                     break
         ach = GEN_BYTES_PER_FRAME * fpu / (g_ms * 1e-3) / 1e9
         par = (f"dp{world} (utterance sharding, identical utterance on every rank; waveforms to rank 0: " +

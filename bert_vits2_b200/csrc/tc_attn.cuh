@@ -133,7 +133,9 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
     uint8_t* sP = sV + 2 * KB;
     float* sEk = reinterpret_cast<float*>(sP + 2 * PB);
     float* sEv = sEk + NREL * DK;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sEv + NREL * DK);
+    float* sQrel = sEv + NREL * DK;    // [NREL][128 rows]: q_i . Ek[r] of this CTA's query rows (each thread reads back only its own row)
+    float* sPrel = sQrel + NREL * 128; // [NREL][128 rows]: p[i, i + r - w], written by the pass-B thread that meets that key
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPrel + NREL * 128);
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 3, B_VFULL = 5, B_VEMPTY = 7, B_SFULL = 9, B_SEMPTY = 11, B_PFULL = 13, B_PEMPTY = 15, B_OFULL = 17, NBARS = 18 };
@@ -274,10 +276,12 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                     }
                 }
             }
-            auto rel_of = [&](int d) { float v = 0.f;
+            // per-row tables in shared memory, indexed by the relative position d = j - i + w (a per-lane value): one predicated LDS / STS per
+            // in-band element instead of a 9-way select chain over registers (the chains were ~8x the plain softmax path per element and
+            // ran on every element of the in-band chunks: 3.6 us of pass A and 5.7 us of pass B on the CTA that owns the diagonal tile,
+            // which is the one the whole cluster waits for: profiles/r02m_attn_timeline.log).  [r][row] layout: conflict-free (stride 127 mod 32).
 #pragma unroll
-                for (int r = 0; r < NREL; r++) v = (r == d) ? qrel[r] : v;
-                return v; };
+            for (int r = 0; r < NREL; r++) { sQrel[r * 128 + m] = qrel[r]; sPrel[r * 128 + m] = 0.f; }
             if (stamp) prof[2] = gtimer();
             // ---- pass A: row maximum over the valid keys (of this CTA's key tiles)
             for (int s = 0; s < NT; s++) {
@@ -296,7 +300,7 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                         for (int e = 0; e < 32; e++) {
                             const int d = k0 + c0 + e - i + w;
                             float x = __uint_as_float(v[e]);
-                            if ((unsigned)d < (unsigned)nrel) x += rel_of(d);
+                            if ((unsigned)d < (unsigned)nrel) x += sQrel[d * 128 + m];
                             if (c0 + e < nvalid) M = fmaxf(M, x);
                         }
                     } else {
@@ -329,12 +333,9 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                             const int d = k0 + c0 + e - i + w;
                             float x = __uint_as_float(v[e]);
                             const bool inb = (unsigned)d < (unsigned)nrel;
-                            if (inb) x += rel_of(d);
+                            if (inb) x += sQrel[d * 128 + m];
                             pe[e] = (c0 + e < nvalid) ? ex2_approx(fmaf(x, LOG2E, -M2)) : 0.f;
-                            if (inb) {
-#pragma unroll
-                                for (int r = 0; r < NREL; r++) prel[r] = (r == d) ? pe[e] : prel[r];
-                            }
+                            if (inb) sPrel[d * 128 + m] = pe[e];  // key j = i + d - w is met exactly once
                         }
                     } else {
 #pragma unroll
@@ -355,6 +356,8 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
                 mbar_arrive(BAR(B_PFULL + pb));
                 mbar_arrive(BAR(B_SEMPTY + st));
             }
+#pragma unroll
+            for (int r = 0; r < NREL; r++) prel[r] = sPrel[r * 128 + m];
             if (stamp) prof[4] = gtimer();
             mbar_wait(BAR(B_OFULL), 0);  // every MMA of this CTA has completed: O is final, the K/V/P stages are free
             fence_after();
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(192, 1) k_flow_attn(AttnParams p) {
 // between 8-channel blocks (KT*16 B).  tests/cuda/tc_probe.cu (run_mn_probe) measures the convention on hardware.
 struct AttnMnConv { int lbo_is_kblock = 1; };
 
-inline size_t tc_flow_attn_smem(int DK, int KT) { return (size_t)DK * 128 * 2 + 4 * (size_t)DK * KT * 2 + 2 * (size_t)KT * 128 * 2 + 2 * 9 * (size_t)DK * 4 + 18 * 8 + 16; }
+inline size_t tc_flow_attn_smem(int DK, int KT) { return (size_t)DK * 128 * 2 + 4 * (size_t)DK * KT * 2 + 2 * (size_t)KT * 128 * 2 + 2 * 9 * (size_t)DK * 4 + 2 * 9 * 128 * 4 + 18 * 8 + 16; }
 
 inline void tc_flow_attn_init_device() {
     BV2_CUDA(cudaFuncSetAttribute(k_flow_attn<96, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

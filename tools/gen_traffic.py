@@ -29,7 +29,7 @@ gen = [i for i in ids if first <= i <= end]
 tot = sum(per[i]["bytes"] for i in gen)
 import bench
 out = {"frames": a.frames, "generator_dram_bytes": tot, "generator_dram_bytes_per_frame": tot / a.frames, "generator_launches": len(gen),
-       "generator_us_serialised": sum(per[i]["us"] for i in gen), "build_id": bench.build_id(),
+       "generator_us_serialised": sum(per[i]["us"] for i in gen), "build_id": bench.build_id(), "generator_build_id": bench.generator_build_id(),
        "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum ({os.path.basename(a.csv)}), config 2, {a.precision} engine, last captured step"}
 json.dump(out, open(a.out, "w"), indent=1)
 print(json.dumps(out))
